@@ -1,0 +1,23 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a real B200 (run with -m gpu on the GPU box)')
+
+
+@pytest.fixture(scope='session')
+def golden_meta():
+    return json.load(open(os.path.join(GOLD, 'meta.json')))
+
+
+def golden_path(name):
+    return os.path.join(GOLD, name)

@@ -1,0 +1,211 @@
+/*
+ * nbasr.h -- C ABI of libnbasr.so: the B200 (sm_100a) kernels behind the NAS-Bench-ASR
+ * candidate train/eval step.
+ *
+ * The reference (SamsungLabs/nb-asr) has no FFI of its own: its hot path is a chain of
+ * torch library calls.  Each entry point below therefore cites the reference
+ * call site(s) it replaces (paths under /root/reference/nasbench_asr/).  INTEGRATION.md shows
+ * the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated;
+ *   - caller allocates all outputs/workspaces; no hidden allocation, no sync, no host<->device
+ *     copies; every launch goes to the `stream` argument (a cudaStream_t passed as void*);
+ *   - return 0 on success, non-zero on error (nbasr_last_error() gives the message);
+ *   - dtype codes: NBASR_F32 = 0, NBASR_BF16 = 1.
+ *
+ * Activation layout ("frames x channels", channels-last): a tensor of one encoder block is
+ * (B, Tp, C) contiguous with Tp = T + NBASR_PAD_L + NBASR_PAD_R; frame t of utterance b is row
+ * b*Tp + NBASR_PAD_L + t.  Pad rows are zero and are never written, so every (dilated /
+ * strided) convolution tap is a plain row offset and zero padding comes for free.
+ */
+#ifndef NBASR_H
+#define NBASR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBASR_F32 0
+#define NBASR_BF16 1
+#define NBASR_PAD_L 8
+#define NBASR_PAD_R 4
+#define NBASR_MAX_ADD 3
+
+/* Fused output stage shared by the dense GEMM, grouped-conv and element-wise kernels.
+ * For an accumulator value v at output row rho, column n:
+ *   v += bias[n]                                   (ops.py:26,45 bias of Conv1d / Linear)
+ *   m  = (0 < v <= 20); v = min(max(v,0),20)       (ops.py:27-28,46-47 ReLU + clamp_max 20)
+ *   keep ~ Bernoulli(1-p); m &= keep; v = keep ? v/(1-p) : 0   (ops.py:22,29,40,48 Dropout)
+ *   v += add[0][rho,n] + add[1][rho,n] + ...       (model.py:16-22 skip-connection sum)
+ *   out[rho,n] = v ; mask_out bit(rho,n) = m
+ *   out2[rho,n] = bit(mask2,rho,n) ? v*scale2 : 0  (backward: gradient through ReLU20/Dropout)
+ * All row-indexed tensors share the row mapping of the call; ld_* are row pitches in elements
+ * (mask pitches in 32-bit words).  Columns are processed in aligned chunks of 32; N % 8 == 0. */
+typedef struct nbasr_epilogue {
+  const float* bias;
+  int32_t relu20;
+  float drop_p;
+  uint64_t drop_seed;           /* per-call salt */
+  const uint64_t* drop_step;    /* optional device counter mixed into the seed (graph replay) */
+  int32_t n_add;
+  const void* add[NBASR_MAX_ADD];
+  int32_t add_dtype;
+  void* out;
+  int32_t out_dtype;
+  int64_t ld_out;
+  uint32_t* mask_out;
+  void* out2;
+  int32_t out2_dtype;
+  const uint32_t* mask2;
+  float scale2;
+  int64_t ld_mask;
+  int32_t accumulate;   /* out += v instead of out = v (fp32 out only, SIMT path) */
+} nbasr_epilogue;
+
+/* Dense GEMM  C[(b,r), n] = sum_k A[(b,r), k] * W[n, k]  followed by the epilogue.
+ * A element (b,r,k) is a[b*a_bs + r*a_rs + k]; rows may overlap (a_rs < K), which is how the
+ * k=8 time-reduction convolutions (model.py:82-89 -> ops.py:25-26) become one GEMM with
+ * K = 8*C_in over the zero-padded channels-last input (stride 2: a_rs = 2*C_in).
+ * Output row rho = o_r0 + b*o_bs + r*o_rs.  Replaces: nn.Conv1d(groups=1) (ops.py:26),
+ * nn.Linear edge (ops.py:45), LSTM input projection (model.py:100), and their input-gradients
+ * (W pre-packed by nbasr_pack_weight).  dtype BF16 -> tcgen05/TMEM/TMA kernel; F32 -> SIMT. */
+typedef struct nbasr_gemm {
+  int32_t dtype;          /* of A and W */
+  const void* a;
+  int64_t a_bs, a_rs;
+  int32_t nb, nr, K, N;
+  const void* w;
+  int64_t ldw;
+  int64_t o_r0, o_bs, o_rs;
+  nbasr_epilogue epi;
+} nbasr_gemm;
+
+int nbasr_gemm_tn(const nbasr_gemm* p, void* stream);
+
+/* Weight-gradient GEMM  dW[m, n] += sum_{b,r} dY[(b,r), m] * X[(b,r), n]   (fp32, atomic add)
+ * dY element (b,r,m) = dy[b*dy_bs + r*dy_rs + m]; X element = x[b*x_bs + r*x_rs + n] (overlapping
+ * rows give all conv taps at once: n = tap*C_in + c_in).  Replaces the weight-gradient half of
+ * autograd for Conv1d/Linear/LSTM (trainer.py:223 `_regu_loss.backward()`). */
+typedef struct nbasr_wgrad {
+  int32_t dtype;
+  const void* dy;
+  int64_t dy_bs, dy_rs;
+  const void* x;
+  int64_t x_bs, x_rs;
+  int32_t nb, nr, M, N;
+  float* dw;
+  int64_t ldw;
+} nbasr_wgrad;
+
+int nbasr_gemm_wgrad(const nbasr_wgrad* p, void* stream);
+
+/* Grouped (groups = C/cpg) 1-D convolution edge, channels-last, taps at row offsets
+ * off0 + j*dstep (j < ktaps):  ops.py:73-76 conv5/conv5d2/conv7/conv7d2 (groups=100).
+ * w is (C, cpg, ktaps) fp32 in the reference layout (forward) or the group-transposed pack
+ * made by nbasr_pack_gconv_dgrad (input gradient, with negated offsets). */
+typedef struct nbasr_gconv {
+  int32_t dtype;
+  const void* x;          /* (B, Tp, C) padded activation, pointer to row 0 of the buffer */
+  int32_t B, T, Tp, C, cpg, ktaps, off0, dstep;
+  const float* w;
+  nbasr_epilogue epi;     /* rows rho = b*Tp + PAD_L + t */
+} nbasr_gconv;
+
+int nbasr_gconv_fwd(const nbasr_gconv* p, void* stream);
+int nbasr_pack_gconv_dgrad(const float* w, float* wt, int C, int cpg, int ktaps, void* stream);
+/* dw[c_out][i][j] += sum_{b,t} dz[b,t,c_out] * x[b, t+off0+j*dstep, g*cpg+i];  db[c] += sum dz */
+int nbasr_gconv_wgrad(int dtype, const void* dz, const void* x, int B, int T, int Tp, int C, int cpg,
+                      int ktaps, int off0, int dstep, float* dw, void* stream);
+
+/* Element-wise pass through the epilogue: v = src ? src[rho,n] : 0 over rows (b,t) of a padded
+ * (B,Tp,C) geometry.  Used for `zero` main ops (ops.py:62-68), the LSTM input dropout
+ * (model.py:99) and gradient masking. */
+int nbasr_eltwise(int src_dtype, const void* src, int64_t ld_src, int B, int T, int Tp, int C,
+                  const nbasr_epilogue* epi, void* stream);
+
+/* column sums  out[c] += sum_{b,t} x[b,t,c]  (bias gradients). */
+int nbasr_colsum(int dtype, const void* x, int B, int T, int Tp, int C, float* out, void* stream);
+
+/* LayerNorm over channels, eps given (model.py:47,92: nn.LayerNorm(C, eps=1e-3)), biased
+ * variance, affine.  Saves mean / rstd per row for the backward pass. */
+int nbasr_layernorm_fwd(int dtype, const void* x, void* y, int B, int T, int Tp, int C,
+                        const float* gamma, const float* beta, float eps, float* mean, float* rstd,
+                        void* stream);
+/* dx (+ optional dx2 = dx * bit(mask2) * scale2), dgamma += , dbeta += */
+int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* mean, const float* rstd,
+                        const float* gamma, int B, int T, int Tp, int C, void* dx, void* dx2,
+                        const uint32_t* mask2, float scale2, int64_t ld_mask, float* dgamma,
+                        float* dbeta, void* stream);
+
+/* (B, F, T) fp32 channel-first input (trainer.py:210) -> padded channels-last (B, Tp, F). */
+int nbasr_transpose_in(const float* audio, void* out, int dtype, int B, int F, int T, int Tp, void* stream);
+
+/* Weight packing: out[n][q*M + m] = w[m*ws_m + n*ws_n + (t0 + q*tstep)*ws_t],  q < nq.
+ * Produces the bf16 / fp32 operand copies (plain, transposed, tap-flipped) used by gemm_tn. */
+int nbasr_pack_weight(const float* w, void* out, int out_dtype, int M, int N, int nq, int t0, int tstep,
+                      int64_t ws_m, int64_t ws_n, int64_t ws_t, void* stream);
+int nbasr_convert(const float* src, void* dst, int dst_dtype, int64_t n, void* stream);
+
+/* LSTM (model.py:100 nn.LSTM(1200,500,batch_first), zero initial state, gates i,f,g,o).
+ * gx: (B, T, 4H) fp32 input projection incl. both biases; w_hh (4H, H) fp32.
+ * Outputs: h_seq (B, Tp?, ld_h) act dtype written at row b*h_bs + t*h_rs; saves gates (B,T,4H)
+ * post-activation and c (B,T,H) for BPTT.  work: 2*B*H floats (h ping-pong). Cooperative launch. */
+int nbasr_lstm_fwd(const float* gx, const float* w_hh, int T, int B, int H, void* h_seq, int h_dtype,
+                   int64_t h_bs, int64_t h_rs, int64_t ld_h, float* gates, float* cstate, float* hstate,
+                   float* work, void* stream);
+/* BPTT: dh_seq (same addressing as h_seq, fp32) -> dgx (B,T,4H) fp32 (gradient of gx).
+ * dW_hh / dW_ih / biases then follow from nbasr_gemm_wgrad / nbasr_colsum over dgx. */
+int nbasr_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, int64_t ld_dh, const float* w_hh,
+                   const float* gates, const float* cstate, int T, int B, int H, float* dgx, float* work,
+                   void* stream);
+
+/* Classifier + log-softmax: logits = h W^T + b (model.py:101 nn.Linear(500,49)),
+ * logp = log_softmax(logits) (trainer.py:218). h rows at b*h_bs + t*h_rs, pitch implied by strides. */
+int nbasr_head_fwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B, int T, int K, int V,
+                   const float* w, const float* bias, float* logits, float* logp, void* stream);
+/* dlogits (B,T,V) fp32 -> dh (fp32, same addressing as h), dw += , db += */
+int nbasr_head_bwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B, int T, int K, int V,
+                   const float* w, const float* dlogits, float* dh, int64_t dh_bs, int64_t dh_rs,
+                   float* dw, float* db, void* stream);
+
+/* CTC (trainer.py:36-44: F.ctc_loss(reduction='none', zero_infinity=True) / output_len, mean).
+ * logp (B,T,V) fp32, blank 0; targets (B,S) int32 zero padded; lens int64 (audio_len is the INPUT
+ * length; output_len = audio_len / len_div, trainer.py:219 uses 4).  Outputs: nll[b] (already
+ * zero-infinity'd, NOT divided), loss (scalar mean of nll/output_len), and, if dlogits != NULL,
+ * d loss / d logits (B,T,V) (log-softmax backward folded in).  work: 2*B*T*(2S+1) floats. */
+int nbasr_ctc(const float* logp, int B, int T, int V, const int32_t* targets, int S,
+              const int64_t* audio_len, int len_div, const int64_t* targets_len, float* nll, float* loss,
+              float* dlogits, float* work, void* stream);
+
+/* Greedy CTC decode + fold + Levenshtein PER (trainer.py:229-247 with beam search replaced by
+ * argmax/merge-repeats/drop-blank, tf/metrics/ctc.py:76-81; fold encoder.py:64-74 via `lut`
+ * (V entries) or NULL).  Outputs: hyp (B,T) int32 folded hypotheses, hyp_len (B), dist (B) edit
+ * distances, per[0] = mean_b dist/ref_len in fp64 (sequential), per[1] = same as fp32 in a float
+ * slot.  work: B*(S+2) int32. */
+int nbasr_greedy_per(const float* logp, int B, int T, int V, const int64_t* audio_len, int len_div,
+                     const int32_t* targets, int S, const int64_t* targets_len, const int32_t* lut,
+                     int32_t* hyp, int32_t* hyp_len, int32_t* dist, double* per, int32_t* work,
+                     void* stream);
+
+/* Optimiser tail of Trainer.step (trainer.py:221-225): regulariser 0.01*sum_i ||W_i||_F over the
+ * PadConvRelu weights (segments), clip_grad_norm_(5), Adam(eps=1e-7).  Flat fp32 buffers of n
+ * elements.  seg_off/seg_len (nseg, int64, device) delimit the regularised tensors.
+ * state: [0]=step count (as float), [1]=lr, [2]=sum of squares scratch, [3]=clip coef,
+ *        [4..4+nseg) per-segment sum of squares.  All on device, so the step is graph-replayable. */
+int nbasr_optim_step(float* param, float* grad, float* m, float* v, int64_t n, const int64_t* seg_off,
+                     const int64_t* seg_len, int nseg, float reg_coef, float max_norm, float beta1,
+                     float beta2, float eps, float* state, void* stream);
+
+/* misc */
+int nbasr_fill_u32(uint32_t* p, uint32_t val, int64_t n, void* stream);
+int nbasr_version(void);
+int nbasr_sm_count(void);
+const char* nbasr_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,58 @@
+// C-ABI glue: error reporting, device queries and the GEMM dispatch (bf16 -> tcgen05, fp32 -> SIMT).
+#include <cstdarg>
+
+#include "common.cuh"
+#include "kernels.h"
+
+thread_local char g_nbasr_err[512] = {0};
+
+int nbasr_fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_nbasr_err, sizeof(g_nbasr_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+extern "C" {
+
+const char* nbasr_last_error(void) { return g_nbasr_err; }
+int nbasr_version(void) { return 100; }
+
+int nbasr_sm_count(void) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return sms;
+}
+
+int nbasr_gemm_tn(const nbasr_gemm* p, void* stream) {
+  if (p->nb <= 0 || p->nr <= 0 || p->N <= 0) return 0;
+  if (p->dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT")) return sm100_gemm_tn(p, as_stream(stream));
+  SimtGemmArgs a{};
+  a.a = p->a; a.a_dtype = p->dtype; a.a_ib = p->a_bs; a.a_ir = p->a_rs; a.a_kb = 0; a.a_kr = 1;
+  a.nib = p->nb; a.nir = p->nr;
+  a.b = p->w; a.b_dtype = p->dtype; a.b_j = p->ldw; a.b_kb = 0; a.b_kr = 1;
+  a.nkb = 1; a.nkr = p->K; a.N = p->N;
+  a.o_r0 = p->o_r0; a.o_bs = p->o_bs; a.o_rs = p->o_rs;
+  a.epi = p->epi;
+  return simt_gemm_launch(a, as_stream(stream));
+}
+
+int nbasr_gemm_wgrad(const nbasr_wgrad* p, void* stream) {
+  if (p->nb <= 0 || p->nr <= 0 || p->N <= 0 || p->M <= 0) return 0;
+  if (p->dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT")) return sm100_gemm_wgrad(p, as_stream(stream));
+  SimtGemmArgs a{};
+  a.a = p->dy; a.a_dtype = p->dtype; a.a_ib = 0; a.a_ir = 1; a.a_kb = p->dy_bs; a.a_kr = p->dy_rs;
+  a.nib = 1; a.nir = p->M;
+  a.b = p->x; a.b_dtype = p->dtype; a.b_j = 1; a.b_kb = p->x_bs; a.b_kr = p->x_rs;
+  a.nkb = p->nb; a.nkr = p->nr; a.N = p->N;
+  a.o_r0 = 0; a.o_bs = 0; a.o_rs = 1;
+  a.epi.out = p->dw; a.epi.out_dtype = NBASR_F32; a.epi.ld_out = p->ldw; a.epi.accumulate = 1;
+  return simt_gemm_launch(a, as_stream(stream));
+}
+
+}  // extern "C"

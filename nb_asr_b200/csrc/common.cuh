@@ -1,0 +1,173 @@
+// Shared device helpers for libnbasr (sm_100a). See include/nbasr.h for the ABI.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/nbasr.h"
+
+typedef __nv_bfloat16 bf16;
+
+extern thread_local char g_nbasr_err[512];
+int nbasr_fail(const char* fmt, ...);
+
+#define NBASR_CHECK_LAUNCH()                                                     \
+  do {                                                                           \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) return nbasr_fail("%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+#define NBASR_REQUIRE(cond, msg)                                                 \
+  do {                                                                           \
+    if (!(cond)) return nbasr_fail("%s:%d requirement failed: %s (%s)", __FILE__, __LINE__, #cond, msg); \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---------------------------------------------------------------------------------------------
+// 8-wide vector load/store with dtype conversion (all row pitches / chunk offsets are 8-aligned)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const float* p, float* v) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float* v) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float* v) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+__device__ __forceinline__ void load8_dt(const void* base, int dtype, int64_t idx, float* v) {
+  if (dtype == NBASR_BF16) load8(reinterpret_cast<const bf16*>(base) + idx, v);
+  else load8(reinterpret_cast<const float*>(base) + idx, v);
+}
+__device__ __forceinline__ void store8_dt(void* base, int dtype, int64_t idx, const float* v) {
+  if (dtype == NBASR_BF16) store8(reinterpret_cast<bf16*>(base) + idx, v);
+  else store8(reinterpret_cast<float*>(base) + idx, v);
+}
+// tail-safe variants: nrem = number of valid elements in this group of 8 (may be < 8)
+__device__ __forceinline__ void load8_dt_n(const void* base, int dtype, int64_t idx, float* v, int nrem) {
+  if (nrem >= 8) { load8_dt(base, dtype, idx, v); return; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    v[i] = (i < nrem) ? (dtype == NBASR_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(base)[idx + i])
+                                             : reinterpret_cast<const float*>(base)[idx + i]) : 0.f;
+}
+__device__ __forceinline__ void store8_dt_n(void* base, int dtype, int64_t idx, const float* v, int nrem) {
+  if (nrem >= 8) { store8_dt(base, dtype, idx, v); return; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nrem) {
+      if (dtype == NBASR_BF16) reinterpret_cast<bf16*>(base)[idx + i] = __float2bfloat16(v[i]);
+      else reinterpret_cast<float*>(base)[idx + i] = v[i];
+    }
+}
+__device__ __forceinline__ float ld_dt(const void* base, int dtype, int64_t idx) {
+  return dtype == NBASR_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(base)[idx])
+                             : reinterpret_cast<const float*>(base)[idx];
+}
+
+// Counter-based RNG for dropout: one 32-bit hash per element (seed, element index).
+__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
+  uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return static_cast<uint32_t>(z >> 32);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused output stage on one (row, 32-column chunk). v[32] holds the accumulator values.
+// ncol = number of valid columns in the tensor (row pitches must keep 16-byte alignment).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const nbasr_epilogue& e, int64_t rho, int c0, int ncol,
+                                               float* v) {
+  const int nvalid = min(32, ncol - c0);
+  uint32_t m = 0xffffffffu;
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) v[i] += __ldg(e.bias + c0 + i);
+  }
+  if (e.relu20) {
+    m = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float z = v[i];
+      if (z > 0.f && z <= 20.f) m |= (1u << i);
+      v[i] = fminf(fmaxf(z, 0.f), 20.f);
+    }
+  }
+  if (e.drop_p > 0.f) {
+    const float scale = 1.f / (1.f - e.drop_p);
+    const uint32_t thr = static_cast<uint32_t>(e.drop_p * 4294967296.0);
+    const uint64_t seed = e.drop_seed + (e.drop_step ? __ldg(e.drop_step) * 0xD1B54A32D192ED03ull : 0ull);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      uint32_t h = hash_u32(seed, static_cast<uint64_t>(rho) * 4096ull + c0 + i);
+      bool keep = h >= thr;
+      if (!keep) m &= ~(1u << i);
+      v[i] = keep ? v[i] * scale : 0.f;
+    }
+  }
+  for (int a = 0; a < e.n_add; ++a) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g * 8 < nvalid) {
+        float t[8];
+        load8_dt_n(e.add[a], e.add_dtype, rho * e.ld_out + c0 + g * 8, t, nvalid - g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[g * 8 + i] += t[i];
+      }
+    }
+  }
+  if (e.out) {
+    if (e.accumulate) {
+      float* o = reinterpret_cast<float*>(e.out) + rho * e.ld_out + c0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) o[i] += v[i];
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g * 8 < nvalid) store8_dt_n(e.out, e.out_dtype, rho * e.ld_out + c0 + g * 8, v + g * 8, nvalid - g * 8);
+    }
+  }
+  if (e.mask_out) e.mask_out[rho * e.ld_mask + (c0 >> 5)] = m;
+  if (e.out2) {
+    uint32_t w = e.mask2 ? e.mask2[rho * e.ld_mask + (c0 >> 5)] : 0xffffffffu;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g * 8 < nvalid) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = ((w >> (g * 8 + i)) & 1u) ? v[g * 8 + i] * e.scale2 : 0.f;
+        store8_dt_n(e.out2, e.out2_dtype, rho * e.ld_out + c0 + g * 8, t, nvalid - g * 8);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

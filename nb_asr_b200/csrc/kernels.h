@@ -1,0 +1,26 @@
+// Internal declarations shared between the translation units of libnbasr.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nbasr.h"
+
+// C[i, j] = sum_{kb, kr} A[ib*a_ib + ir*a_ir + kb*a_kb + kr*a_kr] * B[j*b_j + kb*b_kb + kr*b_kr]
+// with i = (ib, ir); output row rho = o_r0 + ib*o_bs + ir*o_rs.
+struct SimtGemmArgs {
+  const void* a;
+  int a_dtype;
+  int64_t a_ib, a_ir, a_kb, a_kr;
+  int nib, nir;
+  const void* b;
+  int b_dtype;
+  int64_t b_j, b_kb, b_kr;
+  int nkb, nkr, N;
+  int64_t o_r0, o_bs, o_rs;
+  nbasr_epilogue epi;
+};
+int simt_gemm_launch(const SimtGemmArgs& a, cudaStream_t st);
+
+// tcgen05 paths (gemm_sm100.cu)
+int sm100_gemm_tn(const nbasr_gemm* p, cudaStream_t st);
+int sm100_gemm_wgrad(const nbasr_wgrad* p, cudaStream_t st);

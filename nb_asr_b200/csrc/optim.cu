@@ -1,0 +1,99 @@
+// Optimiser tail of Trainer.step (trainer.py:221-225) over flat fp32 buffers:
+//   grad += 0.01 * W / ||W||_F for every PadConvRelu weight (gradient of the norm regulariser),
+//   coef = min(1, max_norm / (||grad||_2 + 1e-6))   (torch.nn.utils.clip_grad_norm_),
+//   Adam(betas, eps) with bias correction (torch.optim.Adam, amsgrad=False, weight_decay=0).
+// Step count, lr and every reduction result live in a small device `state` array, so the whole
+// step replays inside a CUDA graph.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float red[32];
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  if (w == 0) v = warp_sum(v);
+  return v;
+}
+
+__global__ void seg_sumsq_kernel(const float* __restrict__ p, const int64_t* __restrict__ off, const int64_t* __restrict__ len,
+                                 float* __restrict__ state) {
+  int s = blockIdx.y;
+  const float* x = p + off[s];
+  int64_t n = len[s];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += x[i] * x[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0 && acc != 0.f) atomicAdd(state + 4 + s, acc);
+}
+
+__global__ void reg_grad_kernel(const float* __restrict__ p, float* __restrict__ g, const int64_t* __restrict__ off,
+                                const int64_t* __restrict__ len, const float* __restrict__ state, float reg_coef) {
+  int s = blockIdx.y;
+  float nrm = sqrtf(state[4 + s]);
+  float k = nrm > 0.f ? reg_coef / nrm : 0.f;
+  const float* x = p + off[s];
+  float* gg = g + off[s];
+  int64_t n = len[s];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) gg[i] += k * x[i];
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += g[i] * g[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, float max_norm, float b1, float b2, float eps, float* __restrict__ state) {
+  const float step = state[0] + 1.f;
+  const float lr = state[1];
+  const float total = sqrtf(state[2]);
+  const float coef = fminf(1.f, max_norm / (total + 1e-6f));
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2s = sqrtf(1.f - powf(b2, step));
+  const float step_size = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * coef;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) / bc2s + eps);
+  }
+}
+
+__global__ void optim_finish_kernel(float* state, int nseg, float max_norm) {
+  if (threadIdx.x == 0) {
+    state[3] = fminf(1.f, max_norm / (sqrtf(state[2]) + 1e-6f));
+    state[0] += 1.f;
+  }
+}
+
+}  // namespace
+
+extern "C" int nbasr_optim_step(float* param, float* grad, float* m, float* v, int64_t n, const int64_t* seg_off,
+                                const int64_t* seg_len, int nseg, float reg_coef, float max_norm, float beta1, float beta2,
+                                float eps, float* state, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(state + 2, 0, sizeof(float) * (2 + nseg), st);
+  if (nseg > 0 && reg_coef != 0.f) {
+    seg_sumsq_kernel<<<dim3(32, nseg), 256, 0, st>>>(param, seg_off, seg_len, state);
+    NBASR_CHECK_LAUNCH();
+    reg_grad_kernel<<<dim3(32, nseg), 256, 0, st>>>(param, grad, seg_off, seg_len, state, reg_coef);
+    NBASR_CHECK_LAUNCH();
+  }
+  sumsq_kernel<<<592, 256, 0, st>>>(grad, n, state + 2);
+  NBASR_CHECK_LAUNCH();
+  adam_kernel<<<1184, 256, 0, st>>>(param, grad, m, v, n, max_norm, beta1, beta2, eps, state);
+  NBASR_CHECK_LAUNCH();
+  optim_finish_kernel<<<1, 32, 0, st>>>(state, nseg, max_norm);
+  NBASR_CHECK_LAUNCH();
+  return 0;
+}

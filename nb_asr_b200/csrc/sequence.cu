@@ -1,0 +1,375 @@
+// Classifier + log-softmax, CTC loss / gradient (log-space alpha-beta), greedy decode + fold +
+// Levenshtein PER.  Small, latency-bound kernels; all arithmetic in fp32 (fp64 for the PER mean).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int HEAD_MAXK32 = 40;  // K <= 1280
+
+// ---------------------------------------------------------------- head forward: warp per frame row
+__global__ void __launch_bounds__(256) head_fwd_kernel(int h_dtype, const void* __restrict__ h, int64_t h_bs, int64_t h_rs,
+                                                       int B, int T, int K, int V, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ logits,
+                                                       float* __restrict__ logp) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nk = (K + 31) / 32;
+  for (int64_t r = warp; r < (int64_t)B * T; r += nwarps) {
+    int b = (int)(r / T), t = (int)(r % T);
+    int64_t base = (int64_t)b * h_bs + (int64_t)t * h_rs;
+    float hv[HEAD_MAXK32];
+#pragma unroll
+    for (int q = 0; q < HEAD_MAXK32; ++q) {
+      int k = lane + 32 * q;
+      hv[q] = (q < nk && k < K) ? ld_dt(h, h_dtype, base + k) : 0.f;
+    }
+    float l0 = -CUDART_INF_F, l1 = -CUDART_INF_F;  // lane v holds logit v and v+32
+    for (int v = 0; v < V; ++v) {
+      const float* wr = w + (int64_t)v * K;
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < HEAD_MAXK32; ++q) {
+        int k = lane + 32 * q;
+        if (q < nk && k < K) s = fmaf(hv[q], __ldg(wr + k), s);
+      }
+      s = warp_sum(s) + bias[v];
+      if ((v & 31) == lane) {
+        if (v < 32) l0 = s; else l1 = s;
+      }
+    }
+    float m = fmaxf(l0, l1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float e = (lane < V ? __expf(l0 - m) : 0.f) + (lane + 32 < V ? __expf(l1 - m) : 0.f);
+    float lse = m + __logf(warp_sum(e));
+    if (lane < V) {
+      if (logits) logits[r * V + lane] = l0;
+      if (logp) logp[r * V + lane] = l0 - lse;
+    }
+    if (lane + 32 < V) {
+      if (logits) logits[r * V + lane + 32] = l1;
+      if (logp) logp[r * V + lane + 32] = l1 - lse;
+    }
+  }
+}
+
+// head backward (input + bias gradient): warp per row
+__global__ void __launch_bounds__(256) head_bwd_kernel(int B, int T, int K, int V, const float* __restrict__ w,
+                                                       const float* __restrict__ dl, float* __restrict__ dh,
+                                                       int64_t dh_bs, int64_t dh_rs, float* __restrict__ db) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nk = (K + 31) / 32;
+  float db0 = 0.f, db1 = 0.f;
+  for (int64_t r = warp; r < (int64_t)B * T; r += nwarps) {
+    int b = (int)(r / T), t = (int)(r % T);
+    float d0 = lane < V ? dl[r * V + lane] : 0.f;
+    float d1 = lane + 32 < V ? dl[r * V + lane + 32] : 0.f;
+    db0 += d0; db1 += d1;
+    float acc[HEAD_MAXK32];
+#pragma unroll
+    for (int q = 0; q < HEAD_MAXK32; ++q) acc[q] = 0.f;
+    for (int v = 0; v < V; ++v) {
+      float d = __shfl_sync(0xffffffffu, v < 32 ? d0 : d1, v & 31);
+      const float* wr = w + (int64_t)v * K;
+#pragma unroll
+      for (int q = 0; q < HEAD_MAXK32; ++q) {
+        int k = lane + 32 * q;
+        if (q < nk && k < K) acc[q] = fmaf(d, __ldg(wr + k), acc[q]);
+      }
+    }
+    float* o = dh + (int64_t)b * dh_bs + (int64_t)t * dh_rs;
+#pragma unroll
+    for (int q = 0; q < HEAD_MAXK32; ++q) {
+      int k = lane + 32 * q;
+      if (q < nk && k < K) o[k] = acc[q];
+    }
+  }
+  if (db) {
+    if (lane < V) atomicAdd(db + lane, db0);
+    if (lane + 32 < V) atomicAdd(db + lane + 32, db1);
+  }
+}
+
+// ---------------------------------------------------------------- CTC
+__device__ __forceinline__ float logadd(float a, float b) {
+  if (a == -CUDART_INF_F) return b;
+  if (b == -CUDART_INF_F) return a;
+  float m = fmaxf(a, b);
+  return m + log1pf(expf(-fabsf(a - b)));
+}
+
+// one CTA per utterance; threads over the extended label sequence (2S+1 states, blank = 0)
+__global__ void ctc_kernel(const float* __restrict__ logp, int B, int T, int V, const int32_t* __restrict__ targets, int S,
+                           const int64_t* __restrict__ audio_len, int len_div, const int64_t* __restrict__ targets_len,
+                           float* __restrict__ nll_out, float* __restrict__ loss_out, float* __restrict__ dlogits,
+                           float* __restrict__ work) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x;
+  const int Lmax = 2 * S + 1;
+  int Tb = (int)(audio_len[b] / len_div);
+  if (Tb > T) Tb = T;
+  int Sb = (int)targets_len[b];
+  if (Sb > S) Sb = S;
+  const int L = 2 * Sb + 1;
+  float* prev = sm;            // Lmax
+  float* cur = sm + Lmax;      // Lmax
+  int* ext = reinterpret_cast<int*>(sm + 2 * Lmax);
+  float* alpha = work + (int64_t)b * T * Lmax;
+  float* beta = work + (int64_t)B * T * Lmax + (int64_t)b * T * Lmax;
+  const float* lp = logp + (int64_t)b * T * V;
+  const float NEG = -CUDART_INF_F;
+  for (int s = threadIdx.x; s < Lmax; s += blockDim.x) ext[s] = (s < L && (s & 1)) ? targets[(int64_t)b * S + (s >> 1)] : 0;
+  __syncthreads();
+  __shared__ float s_nll;
+  // ---- alpha
+  for (int s = threadIdx.x; s < L; s += blockDim.x) {
+    float a = NEG;
+    if (Tb > 0) {
+      if (s == 0) a = lp[0];
+      else if (s == 1) a = lp[ext[1]];
+    }
+    prev[s] = a;
+    if (Tb > 0) alpha[s] = a;
+  }
+  __syncthreads();
+  for (int t = 1; t < Tb; ++t) {
+    for (int s = threadIdx.x; s < L; s += blockDim.x) {
+      float a = prev[s];
+      if (s >= 1) a = logadd(a, prev[s - 1]);
+      if (s >= 2 && ext[s] != 0 && ext[s] != ext[s - 2]) a = logadd(a, prev[s - 2]);
+      if (a != NEG) a += lp[(int64_t)t * V + ext[s]];
+      cur[s] = a;
+      alpha[(int64_t)t * Lmax + s] = a;
+    }
+    __syncthreads();
+    float* tmp = prev; prev = cur; cur = tmp;
+  }
+  if (threadIdx.x == 0) {
+    float ll = NEG;
+    if (Tb > 0) {
+      ll = prev[L - 1];
+      if (L > 1) ll = logadd(ll, prev[L - 2]);
+    }
+    float nll = -ll;
+    if (nll == CUDART_INF_F || nll != nll) nll = CUDART_INF_F;
+    s_nll = nll;
+    float z = (nll == CUDART_INF_F) ? 0.f : nll;   // zero_infinity=True
+    nll_out[b] = z;
+    if (loss_out && Tb > 0) atomicAdd(loss_out, z / (float)Tb / (float)B);
+  }
+  __syncthreads();
+  if (!dlogits) return;
+  const float nll = s_nll;
+  float* dl = dlogits + (int64_t)b * T * V;
+  if (nll == CUDART_INF_F || Tb == 0) {
+    for (int i = threadIdx.x; i < T * V; i += blockDim.x) dl[i] = 0.f;
+    return;
+  }
+  // ---- beta
+  for (int s = threadIdx.x; s < L; s += blockDim.x) {
+    float bv = NEG;
+    if (s == L - 1) bv = lp[(int64_t)(Tb - 1) * V];
+    else if (s == L - 2) bv = lp[(int64_t)(Tb - 1) * V + ext[L - 2]];
+    prev[s] = bv;
+    beta[(int64_t)(Tb - 1) * Lmax + s] = bv;
+  }
+  __syncthreads();
+  for (int t = Tb - 2; t >= 0; --t) {
+    for (int s = threadIdx.x; s < L; s += blockDim.x) {
+      float bv = prev[s];
+      if (s + 1 < L) bv = logadd(bv, prev[s + 1]);
+      if (s + 2 < L && ext[s + 2] != 0 && ext[s + 2] != ext[s]) bv = logadd(bv, prev[s + 2]);
+      if (bv != NEG) bv += lp[(int64_t)t * V + ext[s]];
+      cur[s] = bv;
+      beta[(int64_t)t * Lmax + s] = bv;
+    }
+    __syncthreads();
+    float* tmp = prev; prev = cur; cur = tmp;
+  }
+  __syncthreads();
+  // ---- gradient wrt logits (log-softmax backward folded in); thread per frame
+  const float scale = 1.f / ((float)Tb * (float)B);
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float* row = dl + (int64_t)t * V;
+    if (t >= Tb) {
+      for (int c = 0; c < V; ++c) row[c] = 0.f;
+      continue;
+    }
+    for (int c = 0; c < V; ++c) row[c] = NEG;
+    for (int s = 0; s < L; ++s) {
+      float ab = alpha[(int64_t)t * Lmax + s] + beta[(int64_t)t * Lmax + s];
+      int c = ext[s];
+      row[c] = logadd(row[c], ab);
+    }
+    for (int c = 0; c < V; ++c) {
+      float l = lp[(int64_t)t * V + c];
+      float occ = (row[c] == NEG) ? 0.f : expf(row[c] + nll - l);
+      row[c] = (expf(l) - occ) * scale;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- greedy decode + PER
+__global__ void greedy_per_kernel(const float* __restrict__ logp, int B, int T, int V, const int64_t* __restrict__ audio_len,
+                                  int len_div, const int32_t* __restrict__ targets, int S,
+                                  const int64_t* __restrict__ targets_len, const int32_t* __restrict__ lut,
+                                  int32_t* __restrict__ hyp, int32_t* __restrict__ hyp_len, int32_t* __restrict__ dist,
+                                  double* __restrict__ per, int32_t* __restrict__ work) {
+  extern __shared__ int smi[];
+  int* best = smi;              // T
+  int* hy = best + T;           // T
+  int* ref = hy + T;            // S
+  int* d0 = ref + S;            // S+1  (three anti-diagonals)
+  int* d1 = d0 + S + 1;
+  int* d2 = d1 + S + 1;
+  __shared__ int s_n, s_m;
+  const int b = blockIdx.x;
+  int Tb = (int)(audio_len[b] / len_div);
+  if (Tb > T) Tb = T;
+  const float* lp = logp + (int64_t)b * T * V;
+  for (int t = threadIdx.x; t < Tb; t += blockDim.x) {
+    const float* row = lp + (int64_t)t * V;
+    float bv = row[0];
+    int bi = 0;
+    for (int c = 1; c < V; ++c) {
+      float v = row[c];
+      if (v > bv) { bv = v; bi = c; }     // strict > keeps the first maximum, like torch.argmax
+    }
+    best[t] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0, prev = -1;
+    for (int t = 0; t < Tb; ++t) {
+      int c = best[t];
+      if (c != prev && c != 0) {
+        int f = lut ? lut[c] : c;
+        if (f != 0) hy[n++] = f;
+      }
+      prev = c;
+    }
+    s_n = n;
+    int m = 0;
+    int tl = (int)targets_len[b];
+    if (tl > S) tl = S;
+    for (int j = 0; j < tl; ++j) {
+      int c = targets[(int64_t)b * S + j];
+      int f = lut ? lut[c] : c;
+      if (f != 0) ref[m++] = f;
+    }
+    s_m = m;
+    hyp_len[b] = n;
+  }
+  __syncthreads();
+  const int n = s_n, m = s_m;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) hyp[(int64_t)b * T + t] = t < n ? hy[t] : 0;
+  // Levenshtein over anti-diagonals k = i + j; cell (i, j) lives at index j of diagonal k.
+  // dk[j] = min(d(k-1)[j] + 1 [delete hyp i], d(k-1)[j-1] + 1 [insert ref j], d(k-2)[j-1] + (hy[i-1] != ref[j-1]))
+  int* pm2 = d0; int* pm1 = d1; int* cur = d2;
+  for (int k = 0; k <= n + m; ++k) {
+    int jlo = max(0, k - n), jhi = min(m, k);
+    for (int j = jlo + threadIdx.x; j <= jhi; j += blockDim.x) {
+      int i = k - j;
+      int v;
+      if (i == 0) v = j;
+      else if (j == 0) v = i;
+      else {
+        int sub = pm2[j - 1] + (hy[i - 1] != ref[j - 1] ? 1 : 0);
+        int del = pm1[j] + 1;
+        int ins = pm1[j - 1] + 1;
+        v = min(sub, min(del, ins));
+      }
+      cur[j] = v;
+    }
+    __syncthreads();
+    int* tmp = pm2; pm2 = pm1; pm1 = cur; cur = tmp;
+  }
+  if (threadIdx.x == 0) {
+    dist[b] = pm1[m];       // after the last swap pm1 holds diagonal n+m
+    __threadfence();
+    int ticket = atomicAdd(work, 1);
+    if (ticket == B - 1) {   // last utterance finished: sequential fp64 mean, deterministic order
+      __threadfence();
+      double acc = 0.0;
+      for (int i = 0; i < B; ++i) {
+        int d = *((volatile int32_t*)dist + i);
+        acc += (double)d / (double)targets_len[i];
+      }
+      per[0] = acc / (double)B;
+      reinterpret_cast<float*>(per + 1)[0] = (float)(acc / (double)B);
+      *work = 0;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int nbasr_head_fwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B, int T, int K, int V, const float* w,
+                   const float* bias, float* logits, float* logp, void* stream) {
+  NBASR_REQUIRE(V <= 64 && K <= 32 * HEAD_MAXK32, "head shape");
+  int64_t rows = (int64_t)B * T;
+  if (rows == 0) return 0;
+  int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 8);
+  head_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(h_dtype, h, h_bs, h_rs, B, T, K, V, w, bias, logits, logp);
+  NBASR_CHECK_LAUNCH();
+  return 0;
+}
+
+int nbasr_head_bwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B, int T, int K, int V, const float* w,
+                   const float* dlogits, float* dh, int64_t dh_bs, int64_t dh_rs, float* dw, float* db, void* stream) {
+  NBASR_REQUIRE(V <= 64 && K <= 32 * HEAD_MAXK32, "head shape");
+  int64_t rows = (int64_t)B * T;
+  if (rows == 0) return 0;
+  int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 4);
+  head_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(B, T, K, V, w, dlogits, dh, dh_bs, dh_rs, db);
+  NBASR_CHECK_LAUNCH();
+  if (dw) {
+    // dW[v, k] += sum_{b,t} dl[b,t,v] * h[b,t,k]
+    SimtGemmArgs a{};
+    a.a = dlogits; a.a_dtype = NBASR_F32; a.a_ib = 0; a.a_ir = 1; a.a_kb = (int64_t)T * V; a.a_kr = V;
+    a.nib = 1; a.nir = V;
+    a.b = h; a.b_dtype = h_dtype; a.b_j = 1; a.b_kb = h_bs; a.b_kr = h_rs;
+    a.nkb = B; a.nkr = T; a.N = K;
+    a.o_r0 = 0; a.o_bs = 0; a.o_rs = 1;
+    a.epi.out = dw; a.epi.out_dtype = NBASR_F32; a.epi.ld_out = K; a.epi.accumulate = 1;
+    return simt_gemm_launch(a, as_stream(stream));
+  }
+  return 0;
+}
+
+int nbasr_ctc(const float* logp, int B, int T, int V, const int32_t* targets, int S, const int64_t* audio_len, int len_div,
+              const int64_t* targets_len, float* nll, float* loss, float* dlogits, float* work, void* stream) {
+  if (B == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (loss) cudaMemsetAsync(loss, 0, sizeof(float), st);
+  int Lmax = 2 * S + 1;
+  int threads = std::min(1024, std::max(64, ((Lmax + 31) / 32) * 32));
+  size_t sm = sizeof(float) * 3 * Lmax;
+  ctc_kernel<<<B, threads, sm, st>>>(logp, B, T, V, targets, S, audio_len, len_div, targets_len, nll, loss, dlogits, work);
+  NBASR_CHECK_LAUNCH();
+  return 0;
+}
+
+int nbasr_greedy_per(const float* logp, int B, int T, int V, const int64_t* audio_len, int len_div, const int32_t* targets,
+                     int S, const int64_t* targets_len, const int32_t* lut, int32_t* hyp, int32_t* hyp_len, int32_t* dist,
+                     double* per, int32_t* work, void* stream) {
+  if (B == 0) return 0;
+  size_t sm = sizeof(int) * ((size_t)2 * T + S + 3 * (S + 1));
+  NBASR_REQUIRE(sm <= 200 * 1024, "sequence too long for the decode kernel");
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(greedy_per_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  greedy_per_kernel<<<B, 256, sm, as_stream(stream)>>>(logp, B, T, V, audio_len, len_div, targets, S, targets_len, lut, hyp,
+                                                       hyp_len, dist, per, work);
+  NBASR_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,643 @@
+"""Plan-based executor of the candidate model on libnbasr (forward + backward + optimiser tail).
+
+One Engine per ASRModel.  It
+  * re-homes all parameters (and their .grad) into two flat fp32 buffers (the time-reduction
+    conv weights are stored tap-major (C_out, k, C_in) -- the GEMM layout -- and exposed to torch
+    as permuted views with the reference shape (C_out, C_in, k), so state_dict round-trips);
+  * keeps bf16 operand copies (plain / transposed / tap-flipped) of the GEMM weights;
+  * builds, per input shape (B, T), a static plan: zero-padded channels-last activation buffers
+    and a list of C-ABI calls with pre-filled argument structs (one list for forward, one for
+    backward), replayed on torch's current stream (CUDA-graph capturable: no allocation, no sync).
+
+Forward semantics follow ASRModel.forward (model.py:116-131), SearchCell/Node (model.py:13-59),
+PadConvRelu/Linear (ops.py:7-50); backward is the hand-derived adjoint (there is no autograd
+inside the engine).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, PAD_L, PAD_R, Epilogue, GConv, Gemm, Wgrad
+from .model import CELLS_PER_BLOCK, CONV_EDGES, FEATURES, FILTERS, HIDDEN, TR_STRIDES, PadConvRelu, pad_rule
+
+HP = 512  # padded LSTM hidden width of the h_seq buffer (TMA-friendly row pitch)
+
+
+def _ptr(t, off_elems=0):
+    return t.data_ptr() + off_elems * t.element_size()
+
+
+class _Geo:
+    """Padded channels-last geometry of one encoder block: (B, Tp, C), frame t at row b*Tp+PAD_L+t."""
+
+    def __init__(self, B, T, C):
+        self.B, self.T, self.C = B, T, C
+        tp = T + PAD_L + PAD_R
+        self.Tp = tp + (tp & 1)          # even, so strided (stride-2) row views nest exactly
+        self.rows = B * self.Tp + 8      # tail slack: taps may reach 8 rows past the last utterance
+        self.mw = (C + 31) // 32         # mask words per row
+
+
+class _Plan:
+    pass
+
+
+class Engine:
+    def __init__(self, model, precision='bf16'):
+        assert precision in ('bf16', 'fp32')
+        self.model = model
+        self.precision = precision
+        self.dt = BF16 if precision == 'bf16' else F32
+        self.tdt = torch.bfloat16 if precision == 'bf16' else torch.float32
+        self.lib = _lib.load()
+        self.params = list(model.parameters())
+        self.names = [n for n, _ in model.named_parameters()]
+        self.plans = {}
+        self.flat_p = None
+        self._pack_version = None
+        self._bound_ptr = None
+        self.training_drop = float(model.dropout_rate)
+        self.launches = 0
+
+    # ------------------------------------------------------------------ parameter binding
+    def _is_dense_conv_w(self, name):
+        return name.endswith('.conv.weight') and name.count('.') == 3   # model.{i}.conv.weight
+
+    def bind(self):
+        p0 = self.params[0]
+        if self.flat_p is not None and self._bound_ptr == (p0.data_ptr(), p0.device):
+            return
+        dev = p0.device
+        if dev.type != 'cuda':
+            raise RuntimeError('nb_asr_b200 needs the model on a CUDA device (no CPU fallback)')
+        self.device = dev
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 63) // 64 * 64
+        flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.slices = {}
+        with torch.no_grad():
+            for name, p, off in zip(self.names, self.params, offs):
+                n = p.numel()
+                dst, gdst = flat_p[off:off + n], flat_g[off:off + n]
+                if self._is_dense_conv_w(name):
+                    co, ci, k = p.shape
+                    dst.view(co, k, ci).copy_(p.detach().to(dev).permute(0, 2, 1))
+                    p.data = dst.view(co, k, ci).permute(0, 2, 1)
+                    p.grad = gdst.view(co, k, ci).permute(0, 2, 1)
+                else:
+                    dst.view(p.shape).copy_(p.detach().to(dev))
+                    p.data = dst.view(p.shape)
+                    p.grad = gdst.view(p.shape)
+                self.slices[name] = (off, n)
+        self.flat_p, self.flat_g = flat_p, flat_g
+        self.n_flat = total
+        self.adam_m = torch.zeros_like(flat_p)
+        self.adam_v = torch.zeros_like(flat_p)
+        reg = [self.slices[n] for n in self.names if n.endswith('.conv.weight')]
+        self.seg_off = torch.tensor([o for o, _ in reg], dtype=torch.int64, device=dev)
+        self.seg_len = torch.tensor([l for _, l in reg], dtype=torch.int64, device=dev)
+        self.opt_state = torch.zeros(8 + len(reg), dtype=torch.float32, device=dev)
+        self.drop_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._bound_ptr = (self.params[0].data_ptr(), dev)
+        self._build_packs()
+        self.plans = {}
+        self._pack_version = None
+
+    def P(self, name):
+        off, _ = self.slices[name]
+        return self.flat_p.data_ptr() + 4 * off
+
+    def G(self, name):
+        off, _ = self.slices[name]
+        return self.flat_g.data_ptr() + 4 * off
+
+    # ------------------------------------------------------------------ operand copies
+    def _build_packs(self):
+        """Describe every derived weight buffer; (re)filled by refresh_packs()."""
+        m = self.model
+        dev, tdt = self.device, self.tdt
+        self.pack_ops = []     # (cfunc, args) without stream
+        self.wf, self.wd, self.wt = {}, {}, {}
+        lib = self.lib
+        idx = 0
+        self.block_conv, self.block_ln, self.block_cells = [], [], []
+        for i in range(4):
+            cin = FEATURES if i == 0 else FILTERS[i - 1]
+            cout = FILTERS[i]
+            name = f'model.{idx}.conv'
+            self.block_conv.append(name)
+            n = cout * 8 * cin
+            if self.dt == BF16:
+                buf = torch.empty(n, dtype=tdt, device=dev)
+                self.pack_ops.append((lib.nbasr_convert, (self.P(name + '.weight'), buf.data_ptr(), BF16, n)))
+                self.wf[name] = buf
+            else:
+                self.wf[name] = None   # flat fp32 master is already (C_out, 8*C_in)
+            if i > 0:
+                if TR_STRIDES[i] == 1:
+                    specs = [(8, 7, -1)]
+                else:
+                    specs = [(4, 7, -2), (4, 6, -2)]
+                bufs = []
+                for nq, t0, ts in specs:
+                    b = torch.empty(cin * nq * cout, dtype=tdt, device=dev)
+                    # out[n=ci][q*Cout + co] = w[co][t0+q*ts][ci]
+                    self.pack_ops.append((lib.nbasr_pack_weight, (self.P(name + '.weight'), b.data_ptr(), self.dt, cout, cin,
+                                                                   nq, t0, ts, 8 * cin, 1, cin)))
+                    bufs.append(b)
+                self.wd[name] = bufs
+            idx += 1
+            self.block_ln.append(f'model.{idx}')
+            idx += 1
+            cells = []
+            for _ in range(CELLS_PER_BLOCK[i]):
+                cells.append(f'model.{idx}')
+                for nn_, node in enumerate(m.arch_desc):
+                    op = node[0]
+                    pn = f'model.{idx}.nodes.{nn_}.op'
+                    if op == 'linear':
+                        n = cout * cout
+                        if self.dt == BF16:
+                            b = torch.empty(n, dtype=tdt, device=dev)
+                            self.pack_ops.append((lib.nbasr_convert, (self.P(pn + '.linear.weight'), b.data_ptr(), BF16, n)))
+                            self.wf[pn] = b
+                        else:
+                            self.wf[pn] = None
+                        bt = torch.empty(n, dtype=tdt, device=dev)
+                        self.pack_ops.append((lib.nbasr_pack_weight, (self.P(pn + '.linear.weight'), bt.data_ptr(), self.dt,
+                                                                       cout, cout, 1, 0, 0, cout, 1, 0)))
+                        self.wt[pn] = bt
+                    elif op in CONV_EDGES:
+                        k, _ = CONV_EDGES[op]
+                        cpg = cout // 100
+                        bt = torch.empty(cout * cpg * k, dtype=torch.float32, device=dev)
+                        self.pack_ops.append((lib.nbasr_pack_gconv_dgrad, (self.P(pn + '.conv.weight'), bt.data_ptr(), cout, cpg, k)))
+                        self.wt[pn] = bt
+                idx += 1
+            self.block_cells.append(cells)
+        if m.use_rnn:
+            idx += 1
+            self.lstm_name = f'model.{idx}'
+            ln = self.lstm_name
+            n = 4 * HIDDEN * FILTERS[-1]
+            if self.dt == BF16:
+                b = torch.empty(n, dtype=tdt, device=dev)
+                self.pack_ops.append((lib.nbasr_convert, (self.P(ln + '.weight_ih_l0'), b.data_ptr(), BF16, n)))
+                self.wf[ln] = b
+            else:
+                self.wf[ln] = None
+            bt = torch.empty(n, dtype=tdt, device=dev)
+            self.pack_ops.append((lib.nbasr_pack_weight, (self.P(ln + '.weight_ih_l0'), bt.data_ptr(), self.dt, 4 * HIDDEN,
+                                                           FILTERS[-1], 1, 0, 0, FILTERS[-1], 1, 0)))
+            self.wt[ln] = bt
+            self.lstm_bias = torch.zeros(4 * HIDDEN, dtype=torch.float32, device=dev)
+            idx += 1
+        self.head_name = f'model.{idx}'
+
+    def _param_version(self):
+        return sum(p._version for p in self.params)
+
+    def refresh_packs(self, force=False):
+        v = self._param_version()
+        if not force and v == self._pack_version:
+            return
+        st = torch.cuda.current_stream().cuda_stream
+        for fn, args in self.pack_ops:
+            _lib.check(fn(*args, st), 'pack')
+        if self.model.use_rnn:
+            off_i, n = self.slices[self.lstm_name + '.bias_ih_l0']
+            off_h, _ = self.slices[self.lstm_name + '.bias_hh_l0']
+            torch.add(self.flat_p[off_i:off_i + n], self.flat_p[off_h:off_h + n], out=self.lstm_bias)
+        self._pack_version = v
+
+    # ------------------------------------------------------------------ plan construction
+    def _epi(self, ld, bias=0, relu=0, drop_p=0.0, salt=0, adds=(), out=0, out_dtype=None, mask_out=0, out2=0,
+             mask2=0, scale2=1.0, ld_mask=0, accumulate=0):
+        e = Epilogue()
+        e.bias = bias or None
+        e.relu20 = relu
+        e.drop_p = drop_p
+        e.drop_seed = salt
+        e.drop_step = self.drop_step.data_ptr() if drop_p > 0 else None
+        e.n_add = len(adds)
+        for i, a in enumerate(adds):
+            e.add[i] = a
+        e.add_dtype = self.dt
+        e.out = out or None
+        e.out_dtype = self.dt if out_dtype is None else out_dtype
+        e.ld_out = ld
+        e.mask_out = mask_out or None
+        e.out2 = out2 or None
+        e.out2_dtype = self.dt
+        e.mask2 = mask2 or None
+        e.scale2 = scale2
+        e.ld_mask = ld_mask
+        e.accumulate = accumulate
+        return e
+
+    def plan(self, B, T, training):
+        key = (B, T, bool(training))
+        if key not in self.plans:
+            self.plans[key] = self._build_plan(B, T, bool(training))
+        return self.plans[key]
+
+    def _build_plan(self, B, T, training):
+        self.bind()
+        m, lib, dev, dt, tdt = self.model, self.lib, self.device, self.dt, self.tdt
+        es = 2 if dt == BF16 else 4
+        pl = _Plan()
+        pl.B, pl.T, pl.training = B, T, training
+        pl.keep = []       # keeps ctypes structs / tensors alive
+        fwd, bwd_rev = [], []   # bwd_rev: groups appended in forward order, executed reversed
+        drop_p = self.training_drop if training else 0.0
+        dscale = 1.0 / (1.0 - drop_p) if drop_p > 0 else 1.0
+        salt = [1]
+
+        def next_salt():
+            salt[0] += 1
+            return salt[0] * 0x9E3779B1
+
+        def zbuf(rows, cols, dtype=None):
+            t = torch.zeros((rows, cols), dtype=tdt if dtype is None else dtype, device=dev)
+            pl.keep.append(t)
+            return t
+
+        def call(lst, fn, *args):
+            pl.keep.append(args)
+            lst.append((fn, args))
+
+        def gemm(lst, a_ptr, a_bs, a_rs, nb, nr, K, N, w_ptr, ldw, o_r0, o_bs, o_rs, epi, dtype=None):
+            g = Gemm()
+            g.dtype = dt if dtype is None else dtype
+            g.a, g.a_bs, g.a_rs, g.nb, g.nr, g.K, g.N = a_ptr, a_bs, a_rs, nb, nr, K, N
+            g.w, g.ldw, g.o_r0, g.o_bs, g.o_rs, g.epi = w_ptr, ldw, o_r0, o_bs, o_rs, epi
+            call(lst, lib.nbasr_gemm_tn, C.byref(g))
+            pl.keep.append(g)
+
+        def wgrad(lst, dy_ptr, dy_bs, dy_rs, x_ptr, x_bs, x_rs, nb, nr, M, N, dw_ptr, ldw, dtype=None):
+            w = Wgrad()
+            w.dtype = dt if dtype is None else dtype
+            w.dy, w.dy_bs, w.dy_rs, w.x, w.x_bs, w.x_rs = dy_ptr, dy_bs, dy_rs, x_ptr, x_bs, x_rs
+            w.nb, w.nr, w.M, w.N, w.dw, w.ldw = nb, nr, M, N, dw_ptr, ldw
+            call(lst, lib.nbasr_gemm_wgrad, C.byref(w))
+            pl.keep.append(w)
+
+        # ---- input
+        pl.audio = torch.zeros((B, FEATURES, T), dtype=torch.float32, device=dev)
+        g_in = _Geo(B, T, FEATURES)
+        x_in = zbuf(g_in.rows, FEATURES)
+        call(fwd, lib.nbasr_transpose_in, pl.audio.data_ptr(), x_in.data_ptr(), dt, B, FEATURES, T, g_in.Tp)
+
+        prev, pg = x_in, g_in
+        Tcur = T
+        arch = m.arch_desc
+        pl.block_geo = []
+        # backward bookkeeping: per block a pool of gradient buffers
+        gpools = []
+        block_records = []
+        for i in range(4):
+            s = TR_STRIDES[i]
+            Ti = Tcur if s == 1 else (Tcur + 1) // 2
+            geo = _Geo(B, Ti, FILTERS[i])
+            pl.block_geo.append(geo)
+            Cc, Tp, mw = geo.C, geo.Tp, geo.mw
+            cname = self.block_conv[i]
+            lpad, _ = pad_rule(8, 1, s)
+            K = 8 * pg.C
+            z = zbuf(geo.rows, Cc)
+            zmask = zbuf(geo.rows, mw, torch.int32)
+            wf_ptr = self.wf[cname].data_ptr() if self.wf[cname] is not None else self.P(cname + '.weight')
+            a_ptr = _ptr(prev, (PAD_L - lpad) * pg.C)
+            epi = self._epi(Cc, bias=self.P(cname + '.bias'), relu=1, out=z.data_ptr(), mask_out=zmask.data_ptr(), ld_mask=mw)
+            gemm(fwd, a_ptr, pg.Tp * pg.C, s * pg.C, B, Ti, K, Cc, wf_ptr, K, PAD_L, Tp, 1, epi)
+            y = zbuf(geo.rows, Cc)
+            mean0 = zbuf(geo.rows, 1, torch.float32)
+            rstd0 = zbuf(geo.rows, 1, torch.float32)
+            lname = self.block_ln[i]
+            call(fwd, lib.nbasr_layernorm_fwd, dt, z.data_ptr(), y.data_ptr(), B, Ti, Tp, Cc, self.P(lname + '.weight'),
+                 self.P(lname + '.bias'), 1e-3, mean0.data_ptr(), rstd0.data_ptr())
+            rec = dict(i=i, geo=geo, prev=prev, pg=pg, z=z, zmask=zmask, y=y, mean=mean0, rstd=rstd0, cells=[],
+                       a_ptr=a_ptr, K=K, s=s, lpad=lpad)
+            cur = y
+            for cellname in self.block_cells[i]:
+                outs = [cur]
+                crec = dict(name=cellname, outs=outs, masks=[], nodes=[])
+                for n, node in enumerate(arch):
+                    op, branches = node[0], node[1:]
+                    src = outs[-1]
+                    skips = [outs[k] for k, bit in enumerate(branches) if bit]
+                    o = zbuf(geo.rows, Cc)
+                    pn = f'{cellname}.nodes.{n}.op'
+                    nrec = dict(op=op, branches=list(branches), pn=pn, mask=None, salt=0)
+                    adds = [t.data_ptr() for t in skips]
+                    if op == 'zero':
+                        epi = self._epi(Cc, adds=adds, out=o.data_ptr())
+                        call(fwd, lib.nbasr_eltwise, dt, None, Cc, B, Ti, Tp, Cc, C.byref(epi))
+                        pl.keep.append(epi)
+                    else:
+                        mask = zbuf(geo.rows, mw, torch.int32)
+                        nrec['mask'] = mask
+                        sl = next_salt()
+                        if op == 'linear':
+                            epi = self._epi(Cc, bias=self.P(pn + '.linear.bias'), relu=1, drop_p=drop_p, salt=sl, adds=adds,
+                                            out=o.data_ptr(), mask_out=mask.data_ptr(), ld_mask=mw)
+                            w_ptr = self.wf[pn].data_ptr() if self.wf[pn] is not None else self.P(pn + '.linear.weight')
+                            gemm(fwd, _ptr(src, PAD_L * Cc), Tp * Cc, Cc, B, Ti, Cc, Cc, w_ptr, Cc, PAD_L, Tp, 1, epi)
+                        else:
+                            k, d = CONV_EDGES[op]
+                            lp, _ = pad_rule(k, d, 1)
+                            gc = GConv()
+                            gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = dt, src.data_ptr(), B, Ti, Tp, Cc, Cc // 100
+                            gc.ktaps, gc.off0, gc.dstep, gc.w = k, -lp, d, self.P(pn + '.conv.weight')
+                            gc.epi = self._epi(Cc, bias=self.P(pn + '.conv.bias'), relu=1, drop_p=drop_p, salt=sl, adds=adds,
+                                               out=o.data_ptr(), mask_out=mask.data_ptr(), ld_mask=mw)
+                            call(fwd, lib.nbasr_gconv_fwd, C.byref(gc))
+                            pl.keep.append(gc)
+                            nrec.update(k=k, d=d, lp=lp)
+                    crec['nodes'].append(nrec)
+                    outs.append(o)
+                if m.use_norm:
+                    co = zbuf(geo.rows, Cc)
+                    mean = zbuf(geo.rows, 1, torch.float32)
+                    rstd = zbuf(geo.rows, 1, torch.float32)
+                    call(fwd, lib.nbasr_layernorm_fwd, dt, outs[-1].data_ptr(), co.data_ptr(), B, Ti, Tp, Cc,
+                         self.P(cellname + '.norm_layer.weight'), self.P(cellname + '.norm_layer.bias'), 1e-3,
+                         mean.data_ptr(), rstd.data_ptr())
+                    crec.update(mean=mean, rstd=rstd, out=co)
+                    cur = co
+                else:
+                    crec.update(out=outs[-1])
+                    cur = outs[-1]
+                rec['cells'].append(crec)
+            block_records.append(rec)
+            prev, pg, Tcur = cur, geo, Ti
+
+        # ---- head
+        geo3 = pl.block_geo[-1]
+        Tq, Tp3, C3 = geo3.T, geo3.Tp, geo3.C
+        pl.Tq = Tq
+        V = m.num_classes + 1
+        pl.V = V
+        pl.logits = torch.zeros((B, Tq, V), dtype=torch.float32, device=dev)
+        pl.logp = torch.zeros((B, Tq, V), dtype=torch.float32, device=dev)
+        hn = self.head_name
+        head = dict()
+        if m.use_rnn:
+            ln = self.lstm_name
+            if drop_p > 0:
+                lin = zbuf(geo3.rows, C3)
+                dmask = zbuf(geo3.rows, geo3.mw, torch.int32)
+                epi = self._epi(C3, drop_p=drop_p, salt=next_salt(), out=lin.data_ptr(), mask_out=dmask.data_ptr(), ld_mask=geo3.mw)
+                call(fwd, lib.nbasr_eltwise, dt, prev.data_ptr(), C3, B, Tq, Tp3, C3, C.byref(epi))
+                pl.keep.append(epi)
+            else:
+                lin, dmask = prev, None
+            H4 = 4 * HIDDEN
+            gx = zbuf(B * Tq, H4, torch.float32)
+            wih = self.wf[ln].data_ptr() if self.wf[ln] is not None else self.P(ln + '.weight_ih_l0')
+            epi = self._epi(H4, bias=self.lstm_bias.data_ptr(), out=gx.data_ptr(), out_dtype=F32)
+            gemm(fwd, _ptr(lin, PAD_L * C3), Tp3 * C3, C3, B, Tq, C3, H4, wih, C3, 0, Tq, 1, epi)
+            gh = _Geo(B, Tq, HP)
+            hseq = zbuf(gh.rows, HP)
+            gates = zbuf(B * Tq, H4, torch.float32)
+            cst = zbuf(B * Tq, HIDDEN, torch.float32)
+            work = zbuf(1, 2 * B * HIDDEN + 256, torch.float32)
+            call(fwd, lib.nbasr_lstm_fwd, gx.data_ptr(), self.P(ln + '.weight_hh_l0'), Tq, B, HIDDEN, _ptr(hseq, PAD_L * HP), dt,
+                 gh.Tp * HP, HP, HP, gates.data_ptr(), cst.data_ptr(), None, work.data_ptr())
+            call(fwd, lib.nbasr_head_fwd, dt, _ptr(hseq, PAD_L * HP), gh.Tp * HP, HP, B, Tq, HIDDEN, V, self.P(hn + '.weight'),
+                 self.P(hn + '.bias'), pl.logits.data_ptr(), pl.logp.data_ptr())
+            head.update(lin=lin, dmask=dmask, gx=gx, hseq=hseq, gh=gh, gates=gates, cst=cst, work=work)
+        else:
+            call(fwd, lib.nbasr_head_fwd, dt, _ptr(prev, PAD_L * C3), Tp3 * C3, C3, B, Tq, C3, V, self.P(hn + '.weight'),
+                 self.P(hn + '.bias'), pl.logits.data_ptr(), pl.logp.data_ptr())
+        pl.fwd = fwd
+        pl.final = prev
+
+        # =========================================================== backward plan
+        bwd = []
+        pl.dlogits = torch.zeros((B, Tq, V), dtype=torch.float32, device=dev)
+        # gradient wrt the last cell output of block 3 (act dtype, padded geometry)
+        pools = []
+        for geo in pl.block_geo:
+            pools.append([zbuf(geo.rows, geo.C) for _ in range(5)])
+        dzs = [[zbuf(geo.rows, geo.C) for _ in range(2)] for geo in pl.block_geo]
+
+        gout = pools[3].pop()
+        if m.use_rnn:
+            ln = self.lstm_name
+            H4 = 4 * HIDDEN
+            dh = zbuf(B * Tq, HIDDEN, torch.float32)
+            call(bwd, lib.nbasr_head_bwd, dt, _ptr(head['hseq'], PAD_L * HP), head['gh'].Tp * HP, HP, B, Tq, HIDDEN, V,
+                 self.P(hn + '.weight'), pl.dlogits.data_ptr(), dh.data_ptr(), Tq * HIDDEN, HIDDEN, self.G(hn + '.weight'),
+                 self.G(hn + '.bias'))
+            dgx = zbuf(B * Tq, H4, torch.float32)
+            call(bwd, lib.nbasr_lstm_bwd, dh.data_ptr(), Tq * HIDDEN, HIDDEN, HIDDEN, self.P(ln + '.weight_hh_l0'),
+                 head['gates'].data_ptr(), head['cst'].data_ptr(), Tq, B, HIDDEN, dgx.data_ptr(), head['work'].data_ptr())
+            if dt == BF16:
+                dgx_a = zbuf(B * Tq, H4)
+                call(bwd, lib.nbasr_convert, dgx.data_ptr(), dgx_a.data_ptr(), BF16, B * Tq * H4)
+            else:
+                dgx_a = dgx
+            # biases: column sums of dgx (B*Tq rows, unpadded) -> both bias vectors
+            for bn in ('.bias_ih_l0', '.bias_hh_l0'):
+                call(bwd, lib.nbasr_colsum, F32, dgx.data_ptr() - PAD_L * H4 * 4, 1, B * Tq, B * Tq, H4, self.G(ln + bn))
+            # dW_ih += dgx^T X ; dW_hh += dgx^T H_{t-1} (h_seq shifted one row up; row -1 is a zero pad row)
+            wgrad(bwd, dgx_a.data_ptr(), Tq * H4, H4, _ptr(head['lin'], PAD_L * C3), Tp3 * C3, C3, B, Tq, H4, C3,
+                  self.G(ln + '.weight_ih_l0'), C3)
+            wgrad(bwd, dgx_a.data_ptr(), Tq * H4, H4, _ptr(head['hseq'], (PAD_L - 1) * HP), head['gh'].Tp * HP, HP, B, Tq, H4,
+                  HIDDEN, self.G(ln + '.weight_hh_l0'), HIDDEN)
+            # dX = dgx W_ih  (through the input dropout mask if any)
+            if head['dmask'] is not None:
+                epi = self._epi(C3, out2=gout.data_ptr(), mask2=head['dmask'].data_ptr(), scale2=dscale, ld_mask=geo3.mw)
+            else:
+                epi = self._epi(C3, out=gout.data_ptr())
+            gemm(bwd, dgx_a.data_ptr(), Tq * H4, H4, B, Tq, H4, C3, self.wt[ln].data_ptr(), H4, PAD_L, Tp3, 1, epi)
+        else:
+            dhp = zbuf(geo3.rows, C3, torch.float32)
+            call(bwd, lib.nbasr_head_bwd, dt, _ptr(prev, PAD_L * C3), Tp3 * C3, C3, B, Tq, C3, V, self.P(hn + '.weight'),
+                 pl.dlogits.data_ptr(), _ptr(dhp, PAD_L * C3), Tp3 * C3, C3, self.G(hn + '.weight'), self.G(hn + '.bias'))
+            epi = self._epi(C3, out=gout.data_ptr())
+            call(bwd, lib.nbasr_eltwise, F32, dhp.data_ptr(), C3, B, Tq, Tp3, C3, C.byref(epi))
+            pl.keep.append(epi)
+
+        for i in (3, 2, 1, 0):
+            rec = block_records[i]
+            geo = rec['geo']
+            Cc, Ti, Tp, mw = geo.C, geo.T, geo.Tp, geo.mw
+            pool = pools[i]
+            dz = dzs[i]
+            for crec in reversed(rec['cells']):
+                outs, nodes = crec['outs'], crec['nodes']
+                nn_ = len(nodes)
+                g = [None] * (nn_ + 1)
+                dzb = [None] * nn_
+                last = nodes[nn_ - 1]
+                # gradient wrt the pre-norm cell output o_n
+                if m.use_norm:
+                    g[nn_] = pool.pop()
+                    dz_t = None
+                    if last['op'] != 'zero':
+                        dz_t = dz[(nn_ - 1) & 1]
+                        dzb[nn_ - 1] = dz_t
+                    call(bwd, lib.nbasr_layernorm_bwd, dt, gout.data_ptr(), outs[nn_].data_ptr(), crec['mean'].data_ptr(),
+                         crec['rstd'].data_ptr(), self.P(crec['name'] + '.norm_layer.weight'), B, Ti, Tp, Cc,
+                         g[nn_].data_ptr(), dz_t.data_ptr() if dz_t is not None else None,
+                         last['mask'].data_ptr() if dz_t is not None else None, dscale, mw,
+                         self.G(crec['name'] + '.norm_layer.weight'), self.G(crec['name'] + '.norm_layer.bias'))
+                    pool.append(gout)
+                else:
+                    g[nn_] = gout
+                    if last['op'] != 'zero':
+                        dz_t = dz[(nn_ - 1) & 1]
+                        dzb[nn_ - 1] = dz_t
+                        epi = self._epi(Cc, out2=dz_t.data_ptr(), mask2=last['mask'].data_ptr(), scale2=dscale, ld_mask=mw)
+                        call(bwd, lib.nbasr_eltwise, dt, gout.data_ptr(), Cc, B, Ti, Tp, Cc, C.byref(epi))
+                        pl.keep.append(epi)
+                for j in range(nn_ - 1, -1, -1):
+                    nrec = nodes[j]
+                    op, pn = nrec['op'], nrec['pn']
+                    src = outs[j]
+                    # contributions of later nodes' skip connections onto outs[j]
+                    adds = [g[k + 1].data_ptr() for k in range(j, nn_) if nodes[k]['branches'][j]]
+                    g[j] = pool.pop()
+                    # the epilogue that produces g[j] also emits dZ_{j-1} = g[j] * mask_{j-1}
+                    o2, m2 = 0, 0
+                    if j >= 1 and nodes[j - 1]['op'] != 'zero':
+                        dzb[j - 1] = dz[(j - 1) & 1]
+                        o2, m2 = dzb[j - 1].data_ptr(), nodes[j - 1]['mask'].data_ptr()
+                    epi = self._epi(Cc, adds=adds, out=g[j].data_ptr(), out2=o2, mask2=m2, scale2=dscale, ld_mask=mw)
+                    if op == 'zero':
+                        call(bwd, lib.nbasr_eltwise, dt, None, Cc, B, Ti, Tp, Cc, C.byref(epi))
+                        pl.keep.append(epi)
+                    elif op == 'linear':
+                        d = dzb[j]
+                        wgrad(bwd, _ptr(d, PAD_L * Cc), Tp * Cc, Cc, _ptr(src, PAD_L * Cc), Tp * Cc, Cc, B, Ti, Cc, Cc,
+                              self.G(pn + '.linear.weight'), Cc)
+                        call(bwd, lib.nbasr_colsum, dt, d.data_ptr(), B, Ti, Tp, Cc, self.G(pn + '.linear.bias'))
+                        gemm(bwd, _ptr(d, PAD_L * Cc), Tp * Cc, Cc, B, Ti, Cc, Cc, self.wt[pn].data_ptr(), Cc, PAD_L, Tp, 1, epi)
+                    else:
+                        d = dzb[j]
+                        k, dd, lp = nrec['k'], nrec['d'], nrec['lp']
+                        call(bwd, lib.nbasr_gconv_wgrad, dt, d.data_ptr(), src.data_ptr(), B, Ti, Tp, Cc, Cc // 100, k, -lp, dd,
+                             self.G(pn + '.conv.weight'))
+                        call(bwd, lib.nbasr_colsum, dt, d.data_ptr(), B, Ti, Tp, Cc, self.G(pn + '.conv.bias'))
+                        gc = GConv()
+                        gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = dt, d.data_ptr(), B, Ti, Tp, Cc, Cc // 100
+                        gc.ktaps, gc.off0, gc.dstep, gc.w = k, lp - (k - 1) * dd, dd, self.wt[pn].data_ptr()
+                        gc.epi = epi
+                        call(bwd, lib.nbasr_gconv_fwd, C.byref(gc))
+                        pl.keep.append(gc)
+                for k in range(1, nn_ + 1):   # (without norm, g[nn_] is the consumed incoming buffer)
+                    pool.append(g[k])
+                gout = g[0]
+            # ---- top of the block: LayerNorm bwd -> dZ of the time-reduction conv
+            dzc = dz[0]
+            lname, cname = self.block_ln[i], self.block_conv[i]
+            call(bwd, lib.nbasr_layernorm_bwd, dt, gout.data_ptr(), rec['z'].data_ptr(), rec['mean'].data_ptr(),
+                 rec['rstd'].data_ptr(), self.P(lname + '.weight'), B, Ti, Tp, Cc, None, dzc.data_ptr(), rec['zmask'].data_ptr(),
+                 1.0, mw, self.G(lname + '.weight'), self.G(lname + '.bias'))
+            pool.append(gout)
+            pgeo, s = rec['pg'], rec['s']
+            wgrad(bwd, _ptr(dzc, PAD_L * Cc), Tp * Cc, Cc, rec['a_ptr'], pgeo.Tp * pgeo.C, s * pgeo.C, B, Ti, Cc, rec['K'],
+                  self.G(cname + '.weight'), rec['K'])
+            call(bwd, lib.nbasr_colsum, dt, dzc.data_ptr(), B, Ti, Tp, Cc, self.G(cname + '.bias'))
+            if i > 0:
+                gout = pools[i - 1].pop()
+                Cin, Tin = pgeo.C, pgeo.T
+                if s == 1:
+                    epi = self._epi(Cin, out=gout.data_ptr())
+                    gemm(bwd, _ptr(dzc, (PAD_L - 4) * Cc), Tp * Cc, Cc, B, Tin, 8 * Cc, Cin, self.wd[cname][0].data_ptr(), 8 * Cc,
+                         PAD_L, pgeo.Tp, 1, epi)
+                else:
+                    for par in (0, 1):
+                        nrp = (Tin - par + 1) // 2
+                        epi = self._epi(Cin, out=gout.data_ptr())
+                        gemm(bwd, _ptr(dzc, (PAD_L - 1 + par) * Cc), Tp * Cc, Cc, B, nrp, 4 * Cc, Cin,
+                             self.wd[cname][par].data_ptr(), 4 * Cc, PAD_L + par, pgeo.Tp, 2, epi)
+        pl.bwd = bwd
+        return pl
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, ops):
+        st = torch.cuda.current_stream().cuda_stream
+        for fn, args in ops:
+            rc = fn(*args, st)
+            if rc != 0:
+                raise _lib.NbasrError(f'{fn.__name__}: {self.lib.nbasr_last_error().decode()}')
+        self.launches += len(ops)
+
+    def forward(self, audio, training=None):
+        """audio (B, 80, T) fp32 cuda -> plan (holds logits / logp buffers)."""
+        self.bind()
+        training = self.model.training if training is None else training
+        B, F, T = audio.shape
+        assert F == FEATURES
+        pl = self.plan(B, T, training)
+        self.refresh_packs()
+        pl.audio.copy_(audio, non_blocking=True)
+        if training and self.training_drop > 0:
+            self.drop_step.add_(1)
+        self._run(pl.fwd)
+        return pl
+
+    def backward(self, pl, dlogits=None, zero_grad=True):
+        if dlogits is not None:
+            pl.dlogits.copy_(dlogits)
+        if zero_grad:
+            self.flat_g.zero_()
+        self._run(pl.bwd)
+
+    def attach_grads(self):
+        """Re-point p.grad at the flat gradient buffer (torch's zero_grad(set_to_none=True) drops it)."""
+        for name, p in zip(self.names, self.params):
+            off, n = self.slices[name]
+            if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * off:
+                gv = self.flat_g[off:off + n]
+                if self._is_dense_conv_w(name):
+                    co, ci, k = p.shape
+                    p.grad = gv.view(co, k, ci).permute(0, 2, 1)
+                else:
+                    p.grad = gv.view(p.shape)
+
+    def optimizer_step(self, lr, reg_coef=0.01, max_norm=5.0, betas=(0.9, 0.999), eps=1e-7):
+        if getattr(self, '_lr_host', None) != lr:   # device copy only when the schedule changes lr
+            self.opt_state[1:2].fill_(lr)
+            self._lr_host = lr
+        self._optimizer_launch(reg_coef, max_norm, betas, eps)
+
+    def _optimizer_launch(self, reg_coef=0.01, max_norm=5.0, betas=(0.9, 0.999), eps=1e-7):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.nbasr_optim_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.adam_m.data_ptr(),
+                                             self.adam_v.data_ptr(), self.n_flat, self.seg_off.data_ptr(),
+                                             self.seg_len.data_ptr(), int(self.seg_off.numel()), reg_coef, max_norm,
+                                             betas[0], betas[1], eps, self.opt_state.data_ptr(), st), 'optim')
+        self.refresh_packs(force=True)
+
+
+class ModelFunction(torch.autograd.Function):
+    """Whole-model autograd node: forward/backward are engine plans, gradients land in the flat buffer."""
+
+    @staticmethod
+    def forward(ctx, model, audio, *params):
+        eng = model.engine
+        pl = eng.forward(audio.contiguous().float())
+        ctx.eng, ctx.pl = eng, pl
+        return pl.logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        eng, pl = ctx.eng, ctx.pl
+        # accumulate like autograd: grads of this call are added to whatever .grad holds
+        had = any(p.grad is not None for p in eng.params)
+        saved = eng.flat_g.clone() if had else None
+        eng.backward(pl, dlogits.contiguous(), zero_grad=True)
+        if had:
+            eng.flat_g.add_(saved)
+        eng.attach_grads()
+        # gradients were written in place into p.grad (views of the flat buffer)
+        return (None, None) + tuple(None for _ in eng.params)

@@ -1,0 +1,369 @@
+"""Train / eval step on the B200 engine behind the reference Trainer API.
+
+Mirrors nasbench_asr/training/torch/trainer.py: get_loss (:36-44), Trainer.step (:208-227),
+Trainer.decode (:229-247, with the greedy decoder of tf/metrics/ctc.py:76-81 in place of the
+third-party beam search, as BASELINE.json's north_star asks), train (:80-206), save/load
+(:249-258), remember_best/recall_best (:260-264), AvgMeter (:16-33).
+
+Differences that are deliberate: the step is one fused pipeline (forward plan -> CTC kernel ->
+backward plan -> [NCCL all-reduce] -> regulariser+clip+Adam kernel) with no autograd graph and
+no host synchronisation; data-parallel training is one process per GPU (torch.distributed)
+instead of single-process nn.DataParallel (:91-92).
+"""
+import pathlib
+import collections.abc as cabc
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import PadConvRelu, print_model_summary
+
+
+class AvgMeter:
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.avg = 0
+        self.n = 0
+
+    def update(self, a):
+        if not self.n:
+            self.avg, self.n = a, 1
+        else:
+            self.avg = self.avg * (self.n / (self.n + 1)) + (a / (self.n + 1))
+            self.n += 1
+
+    def get(self):
+        return self.avg
+
+
+class _CtcWorkspace:
+    def __init__(self):
+        self.key = None
+
+    def get(self, dev, B, T, V, S):
+        key = (str(dev), B, T, V, S)
+        if key != self.key:
+            L = 2 * S + 1
+            self.work = torch.empty(2 * B * T * L + 16, dtype=torch.float32, device=dev)
+            self.nll = torch.zeros(B, dtype=torch.float32, device=dev)
+            self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.dlogits = torch.zeros((B, T, V), dtype=torch.float32, device=dev)
+            self.hyp = torch.zeros((B, T), dtype=torch.int32, device=dev)
+            self.hyp_len = torch.zeros(B, dtype=torch.int32, device=dev)
+            self.dist = torch.zeros(B, dtype=torch.int32, device=dev)
+            self.per = torch.zeros(2, dtype=torch.float64, device=dev)
+            self.iwork = torch.zeros(B * (S + 2) + 16, dtype=torch.int32, device=dev)
+            self.key = key
+        return self
+
+
+_ws = _CtcWorkspace()
+
+
+def ctc_loss_cuda(logp, output_len_src, len_div, targets, targets_len, dlogits=None):
+    """CTC NLL / output_len, batch mean (zero_infinity) on libnbasr; optional d/dlogits."""
+    lib = _lib.load()
+    B, T, V = logp.shape
+    S = targets.shape[1]
+    ws = _ws.get(logp.device, B, T, V, S)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.nbasr_ctc(logp.data_ptr(), B, T, V, targets.data_ptr(), S, output_len_src.data_ptr(), len_div,
+                             targets_len.data_ptr(), ws.nll.data_ptr(), ws.loss.data_ptr(),
+                             dlogits.data_ptr() if dlogits is not None else None, ws.work.data_ptr(), st), 'ctc')
+    return ws.loss, ws.nll
+
+
+class _CtcLossFn(torch.autograd.Function):
+    """Differentiable wrapper for users who call loss() on a tensor that requires grad."""
+
+    @staticmethod
+    def forward(ctx, output, output_len, targets, targets_len):
+        out = output.detach().contiguous().float()
+        olen = output_len.to(out.device, torch.int64).contiguous()
+        d = torch.empty_like(out)
+        loss, nll = ctc_loss_cuda(out, olen, 1, targets.to(out.device, torch.int32).contiguous(),
+                                  targets_len.to(out.device, torch.int64).contiguous(), dlogits=d)
+        # the kernel emits d/dlogits = (softmax - occupancy) * s with s = 1/(B*len); the gradient wrt the
+        # log-probs themselves is -occupancy * s = d - softmax * s on active rows, 0 elsewhere.
+        B, T, _ = out.shape
+        s = 1.0 / (olen.clamp(min=1).float() * B)
+        active = (torch.arange(T, device=out.device)[None, :] < olen[:, None]) & (nll > 0)[:, None]
+        ctx.save_for_backward((d - out.exp() * s[:, None, None]) * active[:, :, None])
+        return loss.clone().squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogp,) = ctx.saved_tensors
+        return dlogp * g, None, None, None
+
+
+def get_loss():
+    """loss(output (B,T',49) log-probs, output_len, targets, targets_len) -> scalar (trainer.py:36-44)."""
+    def loss(output, output_len, targets, targets_len):
+        if not output.is_cuda:
+            raise RuntimeError('nb_asr_b200 loss runs on a CUDA device only (no CPU fallback)')
+        if output.requires_grad and torch.is_grad_enabled():
+            return _CtcLossFn.apply(output, output_len, targets, targets_len)
+        out = output.detach().contiguous().float()
+        l, _ = ctc_loss_cuda(out, output_len.to(out.device, torch.int64).contiguous(), 1,
+                             targets.to(out.device, torch.int32).contiguous(),
+                             targets_len.to(out.device, torch.int64).contiguous())
+        return l.clone().squeeze(0)
+    return loss
+
+
+class FusedAdam:
+    """Handle on the engine-resident Adam state with a torch.optim.Adam-shaped state_dict."""
+
+    def __init__(self, model, lr, eps=1e-7, betas=(0.9, 0.999)):
+        self.model, self.eps, self.betas = model, eps, betas
+        self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False)]
+
+    @property
+    def lr(self):
+        return self.param_groups[0]['lr']
+
+    def zero_grad(self, set_to_none=False):
+        self.model.engine.bind()
+        self.model.engine.flat_g.zero_()
+
+    def _views(self, flat):
+        eng = self.model.engine
+        out = []
+        for name, p in zip(eng.names, eng.params):
+            off, n = eng.slices[name]
+            v = flat[off:off + n]
+            if eng._is_dense_conv_w(name):
+                co, ci, k = p.shape
+                out.append(v.view(co, k, ci).permute(0, 2, 1))
+            else:
+                out.append(v.view(p.shape))
+        return out
+
+    def state_dict(self):
+        eng = self.model.engine
+        eng.bind()
+        step = float(eng.opt_state[0].item())
+        m, v = self._views(eng.adam_m), self._views(eng.adam_v)
+        state = {i: dict(step=torch.tensor(step), exp_avg=m[i].contiguous().clone(), exp_avg_sq=v[i].contiguous().clone())
+                 for i in range(len(m))} if step > 0 else {}
+        groups = [dict(self.param_groups[0], params=list(range(len(m))))]
+        return dict(state=state, param_groups=groups)
+
+    def load_state_dict(self, sd):
+        eng = self.model.engine
+        eng.bind()
+        m, v = self._views(eng.adam_m), self._views(eng.adam_v)
+        step = 0.0
+        for i, s in sd.get('state', {}).items():
+            m[int(i)].copy_(s['exp_avg'])
+            v[int(i)].copy_(s['exp_avg_sq'])
+            step = float(s['step'])
+        eng.opt_state[0:1].fill_(step)
+        if sd.get('param_groups'):
+            self.param_groups[0]['lr'] = sd['param_groups'][0]['lr']
+
+
+class ExponentialLR:
+    def __init__(self, optimizer, gamma):
+        self.optimizer, self.gamma = optimizer, gamma
+
+    def step(self):
+        self.optimizer.param_groups[0]['lr'] *= self.gamma
+
+
+def set_time_limit(loader, time_limit):
+    """training/torch/timit.py:116-119 when the loader exposes the same hooks; otherwise a no-op."""
+    db = getattr(loader, 'dataset', None)
+    sampler = getattr(loader, 'sampler', None)
+    if db is not None and sampler is not None and hasattr(db, 'get_indices_shorter_than'):
+        sampler.indices = db.get_indices_shorter_than(time_limit)
+
+
+class Trainer:
+    def __init__(self, dataloaders, loss, gpus=None, save_dir=None, verbose=True):
+        encoder, train_load, valid_load, test_load = dataloaders
+        self.encoder = encoder
+        self.train_load, self.valid_load, self.test_load = train_load, valid_load, test_load
+        self.gpus = gpus
+        self.save_dir = pathlib.Path(save_dir) if save_dir else save_dir
+        if self.save_dir:
+            self.save_dir.mkdir(exist_ok=True, parents=True)
+        self.verbose = verbose
+        self.loss = loss
+        if self.gpus is not None and (not isinstance(self.gpus, cabc.Sequence) or bool(self.gpus)):
+            if not isinstance(gpus, cabc.Sequence):
+                self.gpus = [self.gpus]
+            self.device = torch.device(f'cuda:{self.gpus[0]}')
+        else:
+            raise RuntimeError('the b200 backend needs gpus=[device index]: there is no CPU execution path')
+        self.fold_to = 39
+        lut = encoder.fold_lut(self.fold_to) if encoder is not None and hasattr(encoder, 'fold_lut') else None
+        self._lut = torch.as_tensor(lut, dtype=torch.int32, device=self.device) if lut is not None else None
+        self.model = None
+        self._model = None
+        self.lr = None
+        self.optimizer = None
+        self.scheduler = None
+        self._best_weights = None
+        self.last_hyp = None
+
+    # ---------------------------------------------------------------- the unit of work
+    def step(self, inputs, training):
+        """((audio (B,80,T) f32, audio_len (B,)), (targets (B,S) i32, targets_len (B,))) ->
+        (loss w/o regulariser, log-probs (B,T',49), output_len), all detached (trainer.py:208-227)."""
+        (audio, audio_len), (targets, targets_len) = inputs
+        dev = self.device
+        audio = audio.to(device=dev, dtype=torch.float32, non_blocking=True)
+        audio_len = audio_len.to(device=dev, dtype=torch.int64, non_blocking=True)
+        targets = targets.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+        targets_len = targets_len.to(device=dev, dtype=torch.int64, non_blocking=True)
+        model = self._model
+        eng = model.engine
+        pl = eng.forward(audio, training=model.training)
+        B, S = targets.shape
+        ws = _ws.get(dev, B, pl.Tq, pl.V, S)
+        lib = eng.lib
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.nbasr_ctc(pl.logp.data_ptr(), B, pl.Tq, pl.V, targets.data_ptr(), S, audio_len.data_ptr(), 4,
+                                 targets_len.data_ptr(), ws.nll.data_ptr(), ws.loss.data_ptr(),
+                                 pl.dlogits.data_ptr() if training else None, ws.work.data_ptr(), st), 'ctc')
+        if training:
+            eng.backward(pl)
+            self._allreduce_grads(eng)
+            lr = self.optimizer.param_groups[0]['lr'] if self.optimizer is not None else (self.lr or 1e-4)
+            eng.optimizer_step(lr)
+        output_len = audio_len // 4
+        return ws.loss[0].clone(), pl.logp.clone(), output_len
+
+    def _allreduce_grads(self, eng):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(eng.flat_g, op=dist.ReduceOp.SUM)
+            eng.flat_g.mul_(1.0 / dist.get_world_size())
+
+    def decode(self, output, output_len, val_inputs):
+        """Greedy CTC decode + 48->39 fold + PER (batch mean of edit_distance / ref_len)."""
+        _, (targets, targets_len) = val_inputs
+        dev = self.device
+        targets = targets.to(device=dev, dtype=torch.int32).contiguous()
+        targets_len = targets_len.to(device=dev, dtype=torch.int64)
+        output = output.contiguous().float()
+        output_len = output_len.to(device=dev, dtype=torch.int64)
+        B, T, V = output.shape
+        S = targets.shape[1]
+        ws = _ws.get(dev, B, T, V, S)
+        lib = _lib.load()
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.nbasr_greedy_per(output.data_ptr(), B, T, V, output_len.data_ptr(), 1, targets.data_ptr(), S,
+                                        targets_len.data_ptr(), self._lut.data_ptr() if self._lut is not None else None,
+                                        ws.hyp.data_ptr(), ws.hyp_len.data_ptr(), ws.dist.data_ptr(), ws.per.data_ptr(),
+                                        ws.iwork.data_ptr(), st), 'greedy_per')
+        self.last_hyp = (ws.hyp, ws.hyp_len, ws.dist)
+        return ws.per[0].clone()
+
+    # ---------------------------------------------------------------- epoch loop (trainer.py:80-206)
+    def train(self, model, epochs=40, lr=0.0001, reset=False, model_name=None):
+        self.model = model
+        self._model = model
+        self.lr = lr
+        model.to(device=self.device)
+        self.optimizer = FusedAdam(model, lr=lr, eps=1e-07)
+        self.scheduler = ExponentialLR(self.optimizer, 0.9)
+        if self.verbose:
+            print_model_summary(model)
+        epoch, best_val, val_scores = 0, None, []
+        latest_ckpt = best_ckpt = None
+        if self.save_dir:
+            d = pathlib.Path(self.save_dir)
+            if model_name is not None:
+                d = d / str(model_name)
+            d.mkdir(exist_ok=True, parents=True)
+            latest_ckpt, best_ckpt = d / 'latest.ckpt', d / 'best.ckpt'
+            if best_ckpt.exists():
+                if reset:
+                    best_ckpt.unlink()
+                else:
+                    self.load(best_ckpt)
+                    self.remember_best()
+            if latest_ckpt.exists():
+                if reset:
+                    latest_ckpt.unlink()
+                else:
+                    self.load(latest_ckpt)
+        loss_tracker, per_tracker = AvgMeter(), AvgMeter()
+        warmup_limits = [1.0, 1.0, 2.0, 2.0]
+        warmup = 0
+        while epoch < epochs:
+            set_time_limit(self.train_load, warmup_limits[warmup] if warmup < len(warmup_limits) else None)
+            loss_tracker.reset()
+            model.train()
+            losses = []
+            for batch in self.train_load:
+                loss, *_ = self.step(batch, training=True)
+                losses.append(loss)          # no per-batch host sync; reduce once per epoch
+            for l in torch.stack(losses).tolist() if losses else []:
+                loss_tracker.update(l)
+            if self.verbose:
+                tag = f'Warmup epoch {warmup + 1}' if warmup < len(warmup_limits) else f'Epoch {epoch + 1}'
+                print(f'{tag}: average loss: {loss_tracker.get():.4f}')
+            if warmup < len(warmup_limits):
+                warmup += 1
+                continue
+            val_loss, val_per = self._evaluate(self.valid_load)
+            val_scores.append((val_loss, val_per))
+            if self.verbose:
+                print(f'Epoch {epoch + 1}: average val loss: {val_loss:.4f}, average val per: {val_per:.4f}')
+            epoch += 1
+            is_best = best_val is None or val_per < best_val
+            if is_best:
+                best_val = val_per
+                self.remember_best()
+            if epoch >= 5:
+                self.scheduler.step()
+            if self.save_dir:
+                self.save(latest_ckpt)
+                if is_best:
+                    self.save(best_ckpt)
+        self.recall_best()
+        test_loss, test_per = self._evaluate(self.test_load)
+        self.model = self._model = self.lr = self.optimizer = self.scheduler = self._best_weights = None
+        return val_scores, test_loss, test_per
+
+    def _evaluate(self, loader):
+        lt, pt = AvgMeter(), AvgMeter()
+        self._model.eval()
+        res = []
+        for batch in loader:
+            loss, logp, out_len = self.step(batch, training=False)
+            per = self.decode(logp, out_len, batch)
+            res.append(torch.stack([loss.double(), per.double()]))
+        for l, p in (torch.stack(res).tolist() if res else []):
+            lt.update(l)
+            pt.update(p)
+        return lt.get(), pt.get()
+
+    # ---------------------------------------------------------------- checkpoints (trainer.py:249-264)
+    def save(self, ckpt_name):
+        torch.save({'model': {k: v.contiguous() for k, v in self._model.state_dict().items()},
+                    'optim': self.optimizer.state_dict()}, str(ckpt_name))
+
+    def load(self, ckpt_name):
+        state = torch.load(str(ckpt_name), map_location=self.device)
+        self._model.load_state_dict(state['model'])
+        self.optimizer.load_state_dict(state['optim'])
+
+    def remember_best(self):
+        # a real copy (the reference keeps aliases of the live tensors, trainer.py:260-261)
+        self._best_weights = {k: v.detach().clone() for k, v in self._model.state_dict().items()}
+
+    def recall_best(self):
+        if self._best_weights is not None:
+            self._model.load_state_dict(self._best_weights)
+
+
+def get_trainer(*args, **kwargs):
+    return Trainer(*args, **kwargs)

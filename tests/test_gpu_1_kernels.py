@@ -1,0 +1,372 @@
+"""-m gpu: every non-tensor-core kernel of libnbasr against torch-fp32 / the numpy oracle (through the C ABI)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from nb_asr_b200 import _lib  # noqa: E402
+from nb_asr_b200._lib import BF16, F32, PAD_L, GConv  # noqa: E402
+from nb_asr_b200.model import pad_rule  # noqa: E402
+from oracle import decode_np as D  # noqa: E402
+from oracle import model_ref as M  # noqa: E402
+import gpu_utils as U  # noqa: E402
+
+
+def _dense_conv_ref(x, w, b, stride):
+    # x (B,T,Cin) ; w (Cout,Cin,8) reference layout
+    return M.pad_conv_relu(x.permute(0, 2, 1), w, b, 8, 1, stride, 1).permute(0, 2, 1)
+
+
+@pytest.mark.parametrize('stride', [1, 2])
+def test_simt_dense_conv_as_gemm(stride):
+    torch.manual_seed(0)
+    B, T, Cin, Cout = 2, 37, 24, 40
+    x = torch.randn(B, T, Cin)
+    w = torch.randn(Cout, Cin, 8) * 0.2
+    bias = torch.randn(Cout)
+    skip = torch.randn(B, (T + stride - 1) // stride, Cout)
+    ref = _dense_conv_ref(x, w, bias, stride) + skip
+    To = ref.shape[1]
+    xb = U.to_padded(x, F32)
+    wp = w.permute(0, 2, 1).contiguous().view(Cout, 8 * Cin).to(U.DEV)       # (Cout, k, Cin)
+    out = U.empty_padded(B, To, Cout, F32)
+    sk = U.to_padded(skip, F32)
+    mask = torch.zeros(out.shape[0], (Cout + 31) // 32, dtype=torch.int32, device=U.DEV)
+    lpad, _ = pad_rule(8, 1, stride)
+    epi = U.epilogue(F32, Cout, bias=bias.to(U.DEV), relu=1, adds=[sk], out=out, mask_out=mask, ld_mask=mask.shape[1])
+    U.run_gemm(F32, U.ptr(xb, (PAD_L - lpad) * Cin), U.geo(T) * Cin, stride * Cin, B, To, 8 * Cin, Cout, wp, 8 * Cin,
+               PAD_L, U.geo(To), 1, epi)
+    got = U.from_padded(out, B, To).cpu()
+    assert U.relerr(got, ref) < 1e-5
+    z = F.conv1d(F.pad(x.permute(0, 2, 1), pad_rule(8, 1, stride)), w, bias, stride=stride).permute(0, 2, 1)
+    m = U.unpack_mask(mask, B, To, Cout).cpu()
+    assert torch.equal(m, (z > 0) & (z <= 20))
+    # pad rows untouched
+    assert float(out[:PAD_L].abs().sum()) == 0.0
+
+
+def test_simt_wgrad_and_dgrad():
+    torch.manual_seed(1)
+    B, T, Cin, Cout = 2, 29, 16, 24
+    x = torch.randn(B, T, Cin, requires_grad=True)
+    w = (torch.randn(Cout, Cin, 8) * 0.2).requires_grad_(True)
+    for stride in (1, 2):
+        y = F.conv1d(F.pad(x.permute(0, 2, 1), pad_rule(8, 1, stride)), w, None, stride=stride).permute(0, 2, 1)
+        To = y.shape[1]
+        dy = torch.randn_like(y)
+        gx, gw = torch.autograd.grad(y, (x, w), dy)
+        xb, dyb = U.to_padded(x.detach(), F32), U.to_padded(dy, F32)
+        lpad, _ = pad_rule(8, 1, stride)
+        dw = torch.zeros(Cout, 8 * Cin, device=U.DEV)
+        U.run_wgrad(F32, U.ptr(dyb, PAD_L * Cout), U.geo(To) * Cout, Cout, U.ptr(xb, (PAD_L - lpad) * Cin), U.geo(T) * Cin,
+                    stride * Cin, B, To, Cout, 8 * Cin, dw, 8 * Cin)
+        got_w = dw.view(Cout, 8, Cin).permute(0, 2, 1).cpu()
+        assert U.relerr(got_w, gw) < 1e-5
+        # dgrad through packed weights
+        lib = _lib.load()
+        wp = w.detach().permute(0, 2, 1).contiguous().to(U.DEV)       # (Cout, 8, Cin)
+        dx = U.empty_padded(B, T, Cin, F32)
+        specs = [(8, 7, -1, 4, 0, T, 1)] if stride == 1 else [(4, 7, -2, 1, 0, (T + 1) // 2, 2), (4, 6, -2, 0, 1, T // 2, 2)]
+        for nq, t0, ts, back, par, nr, ors in specs:
+            wd = torch.empty(Cin, nq * Cout, device=U.DEV)
+            _lib.check(lib.nbasr_pack_weight(wp.data_ptr(), wd.data_ptr(), F32, Cout, Cin, nq, t0, ts, 8 * Cin, 1, Cin, U.stream()))
+            epi = U.epilogue(F32, Cin, out=dx)
+            U.run_gemm(F32, U.ptr(dyb, (PAD_L - back) * Cout), U.geo(To) * Cout, Cout, B, nr, nq * Cout, Cin, wd, nq * Cout,
+                       PAD_L + par, U.geo(T), ors, epi)
+        assert U.relerr(U.from_padded(dx, B, T).cpu(), gx) < 1e-5
+
+
+@pytest.mark.parametrize('dt', [F32, BF16])
+@pytest.mark.parametrize('op', ['conv5', 'conv5d2', 'conv7', 'conv7d2'])
+@pytest.mark.parametrize('Cc', [600, 800, 1000, 1200])
+def test_gconv_fwd_bwd(dt, op, Cc):
+    if dt == BF16 and Cc not in (600, 1000):
+        pytest.skip('bf16 variant sampled on two widths')
+    torch.manual_seed(2)
+    k, d = M.CONV_EDGE[op]
+    B, T, cpg = 2, 70, Cc // 100
+    rnd = (lambda t: t.bfloat16().float()) if dt == BF16 else (lambda t: t)
+    x = rnd(torch.randn(B, T, Cc)).requires_grad_(True)
+    w = (torch.randn(Cc, cpg, k) * 0.3).requires_grad_(True)
+    bias = torch.randn(Cc) * 0.1
+    skip = rnd(torch.randn(B, T, Cc))
+    lp, rp = pad_rule(k, d, 1)
+    z = F.conv1d(F.pad(x.permute(0, 2, 1), (lp, rp)), w, bias, dilation=d, groups=100).permute(0, 2, 1)
+    ref = M.relu20(z) + skip
+    lib = _lib.load()
+    xb, sk = U.to_padded(x.detach(), dt), U.to_padded(skip, dt)
+    out = U.empty_padded(B, T, Cc, dt)
+    mw = (Cc + 31) // 32
+    mask = torch.zeros(out.shape[0], mw, dtype=torch.int32, device=U.DEV)
+    wg, bg = w.detach().to(U.DEV), bias.to(U.DEV)
+    gc = GConv()
+    gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg, gc.ktaps, gc.off0, gc.dstep = dt, xb.data_ptr(), B, T, U.geo(T), Cc, cpg, k, -lp, d
+    gc.w = wg.data_ptr()
+    gc.epi = U.epilogue(dt, Cc, bias=bg, relu=1, adds=[sk], out=out, mask_out=mask, ld_mask=mw)
+    _lib.check(lib.nbasr_gconv_fwd(C.byref(gc), U.stream()), 'gconv')
+    torch.cuda.synchronize()
+    tol = 1e-5 if dt == F32 else 6e-3
+    assert U.relerr(U.from_padded(out, B, T).cpu(), ref) < tol
+    if dt == F32:
+        assert torch.equal(U.unpack_mask(mask, B, T, Cc).cpu(), (z > 0) & (z <= 20))
+    # backward: dz given
+    dz = rnd(torch.randn(B, T, Cc))
+    gx, gw = torch.autograd.grad(z, (x, w), dz)
+    dzb = U.to_padded(dz, dt)
+    dw = torch.zeros(Cc, cpg, k, device=U.DEV)
+    _lib.check(lib.nbasr_gconv_wgrad(dt, dzb.data_ptr(), xb.data_ptr(), B, T, U.geo(T), Cc, cpg, k, -lp, d, dw.data_ptr(), U.stream()))
+    wt = torch.empty_like(wg)
+    _lib.check(lib.nbasr_pack_gconv_dgrad(wg.data_ptr(), wt.data_ptr(), Cc, cpg, k, U.stream()))
+    dx = U.empty_padded(B, T, Cc, dt)
+    gc2 = GConv()
+    gc2.dtype, gc2.x, gc2.B, gc2.T, gc2.Tp, gc2.C, gc2.cpg, gc2.ktaps, gc2.dstep = dt, dzb.data_ptr(), B, T, U.geo(T), Cc, cpg, k, d
+    gc2.off0 = lp - (k - 1) * d
+    gc2.w = wt.data_ptr()
+    gc2.epi = U.epilogue(dt, Cc, out=dx)
+    _lib.check(lib.nbasr_gconv_fwd(C.byref(gc2), U.stream()), 'gconv dgrad')
+    torch.cuda.synchronize()
+    assert U.relerr(dw.cpu(), gw) < (1e-4 if dt == F32 else 1e-2)
+    assert U.relerr(U.from_padded(dx, B, T).cpu(), gx) < tol
+    db = torch.zeros(Cc, device=U.DEV)
+    _lib.check(lib.nbasr_colsum(dt, dzb.data_ptr(), B, T, U.geo(T), Cc, db.data_ptr(), U.stream()))
+    assert U.relerr(db.cpu(), dz.sum((0, 1))) < 1e-4
+
+
+@pytest.mark.parametrize('dt', [F32, BF16])
+@pytest.mark.parametrize('Cc', [600, 1200])
+def test_layernorm_fwd_bwd(dt, Cc):
+    torch.manual_seed(3)
+    B, T = 3, 41
+    rnd = (lambda t: t.bfloat16().float()) if dt == BF16 else (lambda t: t)
+    x = rnd(torch.randn(B, T, Cc) * 2 + 0.5).requires_grad_(True)
+    g = (torch.randn(Cc) * 0.2 + 1).requires_grad_(True)
+    b = (torch.randn(Cc) * 0.1).requires_grad_(True)
+    y = F.layer_norm(x, (Cc,), g, b, 1e-3)
+    dy = rnd(torch.randn_like(y))
+    gx, gg, gb = torch.autograd.grad(y, (x, g, b), dy)
+    lib = _lib.load()
+    xb, yb = U.to_padded(x.detach(), dt), U.empty_padded(B, T, Cc, dt)
+    mean = torch.zeros(xb.shape[0], device=U.DEV)
+    rstd = torch.zeros(xb.shape[0], device=U.DEV)
+    gd, bd = g.detach().to(U.DEV), b.detach().to(U.DEV)
+    _lib.check(lib.nbasr_layernorm_fwd(dt, xb.data_ptr(), yb.data_ptr(), B, T, U.geo(T), Cc, gd.data_ptr(), bd.data_ptr(), 1e-3,
+                                       mean.data_ptr(), rstd.data_ptr(), U.stream()))
+    tol = 2e-6 if dt == F32 else 4e-3
+    assert U.relerr(U.from_padded(yb, B, T).cpu(), y.detach()) < tol
+    dyb, dxb = U.to_padded(dy, dt), U.empty_padded(B, T, Cc, dt)
+    dg, db = torch.zeros(Cc, device=U.DEV), torch.zeros(Cc, device=U.DEV)
+    _lib.check(lib.nbasr_layernorm_bwd(dt, dyb.data_ptr(), xb.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gd.data_ptr(), B, T,
+                                       U.geo(T), Cc, dxb.data_ptr(), None, None, 1.0, 0, dg.data_ptr(), db.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    assert U.relerr(U.from_padded(dxb, B, T).cpu(), gx) < (1e-4 if dt == F32 else 8e-3)
+    assert U.relerr(dg.cpu(), gg) < 1e-4 and U.relerr(db.cpu(), gb) < 1e-4
+
+
+def test_layernorm_degenerate_rows():
+    # all-zero input (all-`zero` no-skip cell): var = 0 -> y = beta, no NaN
+    B, T, Cc = 1, 5, 600
+    lib = _lib.load()
+    xb, yb = U.empty_padded(B, T, Cc, F32), U.empty_padded(B, T, Cc, F32)
+    g = torch.ones(Cc, device=U.DEV)
+    b = torch.full((Cc,), 0.25, device=U.DEV)
+    _lib.check(lib.nbasr_layernorm_fwd(F32, xb.data_ptr(), yb.data_ptr(), B, T, U.geo(T), Cc, g.data_ptr(), b.data_ptr(), 1e-3,
+                                       None, None, U.stream()))
+    assert torch.allclose(U.from_padded(yb, B, T), torch.full((B, T, Cc), 0.25, device=U.DEV))
+
+
+@pytest.mark.parametrize('B,T', [(3, 9), (20, 6), (64, 4)])
+def test_lstm_fwd_bwd(B, T):
+    torch.manual_seed(4)
+    H, I = 500, 64
+    x = torch.randn(B, T, I)
+    w_ih = (torch.randn(4 * H, I) * 0.2).requires_grad_(True)
+    w_hh = (torch.randn(4 * H, H) * 0.08).requires_grad_(True)
+    b_ih = torch.randn(4 * H) * 0.1
+    b_hh = torch.randn(4 * H) * 0.1
+    gx = (x @ w_ih.t() + b_ih + b_hh)
+    gx_leaf = gx.detach().clone().requires_grad_(True)
+    # reference recurrence on the precomputed projection
+    h = torch.zeros(B, H)
+    c = torch.zeros(B, H)
+    outs = []
+    for t in range(T):
+        g = gx_leaf[:, t] + h @ w_hh.t()
+        i, f, gg, o = g.split(H, 1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        outs.append(h)
+    hs = torch.stack(outs, 1)
+    dh = torch.randn_like(hs)
+    ggx, gwhh = torch.autograd.grad(hs, (gx_leaf, w_hh), dh)
+    lib = _lib.load()
+    gxd = gx.detach().contiguous().to(U.DEV)
+    whh = w_hh.detach().to(U.DEV)
+    hseq = torch.zeros(B, T, 512, device=U.DEV)
+    gates = torch.zeros(B * T, 4 * H, device=U.DEV)
+    cst = torch.zeros(B * T, H, device=U.DEV)
+    work = torch.zeros(2 * B * H + 256, device=U.DEV)
+    _lib.check(lib.nbasr_lstm_fwd(gxd.data_ptr(), whh.data_ptr(), T, B, H, hseq.data_ptr(), F32, T * 512, 512, 512, gates.data_ptr(),
+                                  cst.data_ptr(), None, work.data_ptr(), U.stream()), 'lstm_fwd')
+    torch.cuda.synchronize()
+    assert U.relerr(hseq[:, :, :H].cpu(), hs.detach()) < 2e-5
+    dhd = dh.contiguous().to(U.DEV)
+    dgx = torch.zeros(B * T, 4 * H, device=U.DEV)
+    _lib.check(lib.nbasr_lstm_bwd(dhd.data_ptr(), T * H, H, H, whh.data_ptr(), gates.data_ptr(), cst.data_ptr(), T, B, H, dgx.data_ptr(),
+                                  work.data_ptr(), U.stream()), 'lstm_bwd')
+    torch.cuda.synchronize()
+    assert U.relerr(dgx.view(B, T, 4 * H).cpu(), ggx) < 5e-5
+    # dW_hh = dgx^T h_{t-1} via the SIMT wgrad over a row-shifted view of h_seq
+    hp = torch.zeros(B, T + 1, 512, device=U.DEV)
+    hp[:, 1:] = hseq
+    dw = torch.zeros(4 * H, H, device=U.DEV)
+    U.run_wgrad(F32, dgx.data_ptr(), T * 4 * H, 4 * H, hp.data_ptr(), (T + 1) * 512, 512, B, T, 4 * H, H, dw, H)
+    assert U.relerr(dw.cpu(), gwhh) < 5e-5
+
+
+def test_head_ctc_greedy_per():
+    torch.manual_seed(5)
+    B, T, K, V, S = 5, 23, 500, 49, 9
+    h = torch.randn(B, T, K) * 0.5
+    w = (torch.randn(V, K) * 0.1).requires_grad_(True)
+    bias = (torch.randn(V) * 0.1).requires_grad_(True)
+    hq = h.clone().requires_grad_(True)
+    logits = hq @ w.t() + bias
+    logp = F.log_softmax(logits, 2)
+    alen = torch.tensor([92, 60, 95, 20, 77])          # // 4 -> 23, 15, 23, 5, 19
+    tl = torch.tensor([9, 4, 7, 8, 5])                  # utt 3: 8 labels in 5 frames -> infeasible
+    tg = torch.randint(1, V, (B, S), dtype=torch.int32)
+    for b in range(B):
+        tg[b, int(tl[b]):] = 0
+    out_len = alen // 4
+    loss = M.ctc_loss_ref(logp, out_len, tg, tl)
+    gh, gw, gb = torch.autograd.grad(loss, (hq, w, bias))
+    lib = _lib.load()
+    hd, wd, bd = h.to(U.DEV), w.detach().to(U.DEV), bias.detach().to(U.DEV)
+    lg = torch.zeros(B, T, V, device=U.DEV)
+    lp = torch.zeros(B, T, V, device=U.DEV)
+    _lib.check(lib.nbasr_head_fwd(F32, hd.data_ptr(), T * K, K, B, T, K, V, wd.data_ptr(), bd.data_ptr(), lg.data_ptr(), lp.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    assert U.relerr(lg.cpu(), logits.detach()) < 1e-5 and U.relerr(lp.cpu(), logp.detach()) < 1e-5
+    nll = torch.zeros(B, device=U.DEV)
+    lossd = torch.zeros(1, device=U.DEV)
+    dl = torch.zeros(B, T, V, device=U.DEV)
+    work = torch.zeros(2 * B * T * (2 * S + 1) + 16, device=U.DEV)
+    _lib.check(lib.nbasr_ctc(lp.data_ptr(), B, T, V, tg.to(U.DEV).data_ptr(), S, alen.to(U.DEV).data_ptr(), 4, tl.to(U.DEV).data_ptr(),
+                             nll.data_ptr(), lossd.data_ptr(), dl.data_ptr(), work.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    assert abs(lossd.item() - loss.item()) < 1e-5 * abs(loss.item())
+    assert nll[3].item() == 0.0                          # zero_infinity
+    ref64 = D.ctc_nll(logp.detach().numpy(), out_len.numpy(), tg.numpy(), tl.numpy())
+    assert np.allclose(nll.cpu().numpy()[[0, 1, 2, 4]], ref64[[0, 1, 2, 4]], rtol=1e-5)
+    # backward through head
+    dh = torch.zeros(B, T, K, device=U.DEV)
+    dw = torch.zeros(V, K, device=U.DEV)
+    db = torch.zeros(V, device=U.DEV)
+    _lib.check(lib.nbasr_head_bwd(F32, hd.data_ptr(), T * K, K, B, T, K, V, wd.data_ptr(), dl.data_ptr(), dh.data_ptr(), T * K, K,
+                                  dw.data_ptr(), db.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    assert U.relerr(dh.cpu(), gh) < 2e-4 and U.relerr(dw.cpu(), gw) < 2e-4 and U.relerr(db.cpu(), gb) < 2e-4
+    # greedy + fold + PER: bit exact against the numpy oracle on the SAME log-probs
+    lut = torch.as_tensor(D.FOLD_LUT, dtype=torch.int32, device=U.DEV)
+    hyp = torch.zeros(B, T, dtype=torch.int32, device=U.DEV)
+    hl = torch.zeros(B, dtype=torch.int32, device=U.DEV)
+    dist = torch.zeros(B, dtype=torch.int32, device=U.DEV)
+    per = torch.zeros(2, dtype=torch.float64, device=U.DEV)
+    iw = torch.zeros(B * (S + 2) + 16, dtype=torch.int32, device=U.DEV)
+    _lib.check(lib.nbasr_greedy_per(lp.data_ptr(), B, T, V, alen.to(U.DEV).data_ptr(), 4, tg.to(U.DEV).data_ptr(), S,
+                                    tl.to(U.DEV).data_ptr(), lut.data_ptr(), hyp.data_ptr(), hl.data_ptr(), dist.data_ptr(),
+                                    per.data_ptr(), iw.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    rper, rd, _, rh = D.per_batch(lp.cpu().numpy(), out_len.numpy(), tg.numpy(), tl.numpy())
+    assert dist.cpu().tolist() == rd.tolist()
+    assert per[0].item() == rper
+    for b in range(B):
+        assert hyp[b, :int(hl[b])].cpu().tolist() == rh[b].tolist()
+
+
+def test_levenshtein_edge_cases():
+    lib = _lib.load()
+    V = 49
+    cases = [([], [1, 2]), ([11, 9, 20, 20, 5, 14], [19, 9, 20, 20, 9, 14, 7]), ([3, 4, 5], [3, 4, 5]), ([7] * 1, [8] * 12)]
+    B, T, S = len(cases), 16, 12
+    lp = torch.full((B, T, V), -10.0)
+    alen = torch.zeros(B, dtype=torch.int64)
+    tg = torch.zeros(B, S, dtype=torch.int32)
+    tl = torch.zeros(B, dtype=torch.int64)
+    for b, (h, r) in enumerate(cases):
+        # frames: label, blank, label, blank ... so greedy reproduces h exactly (incl. repeats)
+        seq = []
+        for s in h:
+            seq += [s, 0]
+        for t, s in enumerate(seq):
+            lp[b, t, s] = 0.0
+        alen[b] = max(len(seq), 1)
+        if not seq:
+            lp[b, 0, 0] = 0.0
+        tg[b, :len(r)] = torch.tensor(r, dtype=torch.int32)
+        tl[b] = len(r)
+    d = [t.to(U.DEV) for t in (lp, alen, tg, tl)]
+    hyp = torch.zeros(B, T, dtype=torch.int32, device=U.DEV)
+    hl = torch.zeros(B, dtype=torch.int32, device=U.DEV)
+    dist = torch.zeros(B, dtype=torch.int32, device=U.DEV)
+    per = torch.zeros(2, dtype=torch.float64, device=U.DEV)
+    iw = torch.zeros(64, dtype=torch.int32, device=U.DEV)
+    _lib.check(lib.nbasr_greedy_per(d[0].data_ptr(), B, T, V, d[1].data_ptr(), 1, d[2].data_ptr(), S, d[3].data_ptr(), None,
+                                    hyp.data_ptr(), hl.data_ptr(), dist.data_ptr(), per.data_ptr(), iw.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    assert dist.cpu().tolist() == [2, 3, 0, 12]
+    assert dist.cpu().tolist() == [D.levenshtein(h, r) for h, r in cases]
+
+
+def test_optim_step_matches_reference_formulas():
+    torch.manual_seed(6)
+    n = 5000
+    p = torch.randn(n)
+    g = torch.randn(n) * 3
+    segs = [(0, 1000), (1024, 2000)]
+    lib = _lib.load()
+    pd, gd = p.clone().to(U.DEV), g.clone().to(U.DEV)
+    m, v = torch.zeros(n, device=U.DEV), torch.zeros(n, device=U.DEV)
+    so = torch.tensor([s[0] for s in segs], dtype=torch.int64, device=U.DEV)
+    sl = torch.tensor([s[1] for s in segs], dtype=torch.int64, device=U.DEV)
+    state = torch.zeros(16, device=U.DEV)
+    state[1] = 1e-3
+    pr, mr, vr = p.clone(), torch.zeros(n), torch.zeros(n)
+    for step in range(1, 4):
+        gr = g.clone() * step
+        gd.copy_(gr)
+        for o, l in segs:
+            gr[o:o + l] += 0.01 * pr[o:o + l] / pr[o:o + l].norm()
+        coef = min(1.0, 5.0 / (float(gr.norm()) + 1e-6))
+        gr = gr * coef
+        mr = 0.9 * mr + 0.1 * gr
+        vr = 0.999 * vr + 0.001 * gr * gr
+        pr = pr - (1e-3 / (1 - 0.9 ** step)) * mr / (vr.sqrt() / math.sqrt(1 - 0.999 ** step) + 1e-7)
+        _lib.check(lib.nbasr_optim_step(pd.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, so.data_ptr(), sl.data_ptr(), 2,
+                                        0.01, 5.0, 0.9, 0.999, 1e-7, state.data_ptr(), U.stream()))
+        torch.cuda.synchronize()
+        assert U.relerr(pd.cpu(), pr) < 1e-6
+        assert abs(state[3].item() - coef) < 1e-5 * coef
+    assert state[0].item() == 3.0
+
+
+def test_dropout_statistics_and_mask_consistency():
+    B, T, Cc, p = 2, 50, 608, 0.2
+    lib = _lib.load()
+    src = U.to_padded(torch.ones(B, T, Cc), F32)
+    out = U.empty_padded(B, T, Cc, F32)
+    mw = (Cc + 31) // 32
+    mask = torch.zeros(out.shape[0], mw, dtype=torch.int32, device=U.DEV)
+    epi = U.epilogue(F32, Cc, drop_p=p, salt=1234, out=out, mask_out=mask, ld_mask=mw)
+    _lib.check(lib.nbasr_eltwise(F32, src.data_ptr(), Cc, B, T, U.geo(T), Cc, C.byref(epi), U.stream()))
+    torch.cuda.synchronize()
+    o = U.from_padded(out, B, T)
+    keep = (o != 0)
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    assert torch.allclose(o[keep], torch.full_like(o[keep], 1 / (1 - p)))
+    assert torch.equal(U.unpack_mask(mask, B, T, Cc), keep)

@@ -1,0 +1,181 @@
+"""-m gpu: the whole candidate train/eval step on the engine against golden fixtures of the REAL reference
+(tests/golden, oracle/make_golden.py) and against the CPU oracle on the same seeded inputs."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import nb_asr_b200 as nb  # noqa: E402
+from conftest import golden_path  # noqa: E402
+from oracle import decode_np as D  # noqa: E402
+from oracle import model_ref as M  # noqa: E402
+
+DEV = 'cuda:0'
+SMALL = ['default', 'c7d2_skips', 'linear_skips', 'mixed', 'zero_mix', 'c5_c7']
+
+
+def rel64(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def build(arch, precision, dropout=0.0):
+    nb.set_seed(1235)
+    return nb.get_model(arch, use_rnn=True, dropout_rate=dropout, gpu=0, precision=precision)
+
+
+def trainer(model):
+    tr = nb.get_trainer((nb.PhonemeEncoder(48), None, None, None), nb.get_loss(), gpus=[0], save_dir=None, verbose=False)
+    tr.model = tr._model = model
+    tr.lr = 1e-4
+    return tr
+
+
+@pytest.mark.parametrize('name', SMALL)
+def test_fp32_forward_matches_reference(name, golden_meta):
+    meta = golden_meta[f'small_{name}']
+    g = np.load(golden_path(f'eval_small_{name}.npz'))
+    model = build(meta['arch'], 'fp32').eval()
+    (audio, alen), (tg, tl) = nb.data.make_batch(meta['B'], meta['T'], seed=0, min_len=meta['T'] // 2)
+    with torch.no_grad():
+        logits = model(audio.to(DEV))
+    ref = torch.from_numpy(g['logits'])
+    assert rel64(logits, ref) < 1e-4, rel64(logits, ref)       # north_star: 1e-4 relative in fp32
+    tr = trainer(model)
+    loss, logp, out_len = tr.step(((audio, alen), (tg, tl)), training=False)
+    assert abs(loss.item() - float(g['loss'])) < 1e-4 * abs(float(g['loss']))
+    assert out_len.cpu().tolist() == g['out_len'].tolist()
+    # decode on OUR log-probs: kernel vs numpy oracle, bit exact
+    per = tr.decode(logp, out_len, ((audio, alen), (tg, tl)))
+    rper, rd, _, rh = D.per_batch(logp.cpu().numpy(), out_len.cpu().numpy(), tg.numpy(), tl.numpy())
+    hyp, hl, dist = tr.last_hyp
+    assert dist.cpu().tolist() == rd.tolist()
+    assert per.item() == rper
+    for b in range(meta['B']):
+        assert hyp[b, :int(hl[b])].cpu().tolist() == rh[b].tolist()
+
+
+def test_fp32_survey_fixture_kat(golden_meta):
+    meta = golden_meta['survey_c7d2_skips']
+    g = np.load(golden_path('eval_survey_c7d2_skips.npz'))
+    model = build(meta['arch'], 'fp32').eval()
+    batch = nb.data.make_batch(8, 500, seed=0, min_len=250)
+    tr = trainer(model)
+    loss, logp, out_len = tr.step(batch, training=False)
+    assert abs(loss.item() - 3.168433) < 2e-4
+    with torch.no_grad():
+        assert rel64(model(batch[0][0].to(DEV)), torch.from_numpy(g['logits'])) < 1e-4
+    per = tr.decode(logp, out_len, batch)
+    assert abs(per.item() - 4.490172) < 1e-6               # SURVEY.md §8c KAT: labels/PER bit-exact
+    hyp, hl, _ = tr.last_hyp
+    assert hl.cpu().tolist() == [109, 86, 58, 71, 89, 88, 96, 100]
+
+
+@pytest.mark.parametrize('name', ['c7d2_skips', 'linear_skips', 'mixed', 'zero_mix', 'c5_c7', 'default'])
+def test_fp32_train_step_matches_reference(name, golden_meta):
+    meta = golden_meta[f'train_{name}']
+    arch = meta['arch']
+    model = build(arch, 'fp32').train()
+    batch = nb.data.make_batch(meta['B'], meta['T'], seed=0, min_len=meta['T'] // 2)
+    tr = trainer(model)
+    tr.optimizer = nb.trainer.FusedAdam(model, lr=1e-4)
+    # oracle gradients (CPU autograd over the restated forward)
+    sd0 = M.build_state_dict(arch, seed=1235)
+    (audio, alen), (tg, tl) = batch
+    _, _, raw, total, sd1, _, _ = M.train_step(sd0, arch, audio, alen, tg, tl, None)
+    eng = model.engine
+    loss0, _, _ = tr.step(batch, training=True)
+    assert abs(loss0.item() - meta['loss0']) < 1e-4 * abs(meta['loss0'])
+    # flat_g now holds raw grads + regulariser (what clip_grad_norm_ saw); compare per-parameter
+    coef = eng.opt_state[3].item()
+    assert abs(coef - min(1.0, 5.0 / (total + 1e-6))) < 1e-3 * coef
+    worst = 0.0
+    for k, p in model.named_parameters():
+        gref = raw[k].double()
+        got = p.grad.double().cpu()
+        denom = max(float(gref.norm()), 1e-12 * max(1.0, total))
+        err = float((got - gref).norm()) / denom
+        worst = max(worst, err)
+        assert err < 2e-3 or float((got - gref).norm()) < 1e-7 * total, (k, err)
+    # parameters after Adam vs the REAL reference
+    sd = model.state_dict()
+    for k, s in meta['params0'].items():
+        v = sd[k].double().cpu()
+        assert abs(float(v.sum()) - s['sum']) <= 2e-4 * abs(s['sum']) + 2e-3, k
+        assert np.allclose(v.flatten()[:8].numpy(), s['head'], rtol=2e-4, atol=2e-6), k
+    loss1, _, _ = tr.step(batch, training=True)
+    assert abs(loss1.item() - meta['loss1']) < 2e-3 * abs(meta['loss1'])
+
+
+@pytest.mark.parametrize('name', ['c7d2_skips', 'linear_skips', 'mixed', 'c5_c7'])
+def test_bf16_forward_within_tolerance(name, golden_meta):
+    meta = golden_meta[f'small_{name}']
+    g = np.load(golden_path(f'eval_small_{name}.npz'))
+    model = build(meta['arch'], 'bf16').eval()
+    (audio, alen), (tg, tl) = nb.data.make_batch(meta['B'], meta['T'], seed=0, min_len=meta['T'] // 2)
+    with torch.no_grad():
+        logits = model(audio.to(DEV))
+    ref = torch.from_numpy(g['logits'])
+    assert rel64(logits, ref) < 2e-2, rel64(logits, ref)       # north_star: 2e-2 relative in bf16
+    tr = trainer(model)
+    loss, logp, out_len = tr.step(((audio, alen), (tg, tl)), training=False)
+    assert abs(loss.item() - float(g['loss'])) < 2e-2 * abs(float(g['loss']))
+    per = tr.decode(logp, out_len, ((audio, alen), (tg, tl)))
+    rper, rd, _, _ = D.per_batch(logp.cpu().numpy(), out_len.cpu().numpy(), tg.numpy(), tl.numpy())
+    assert per.item() == rper and tr.last_hyp[2].cpu().tolist() == rd.tolist()
+
+
+def test_bf16_train_step_close_to_fp32(golden_meta):
+    meta = golden_meta['train_mixed']
+    model = build(meta['arch'], 'bf16').train()
+    batch = nb.data.make_batch(meta['B'], meta['T'], seed=0, min_len=meta['T'] // 2)
+    tr = trainer(model)
+    tr.optimizer = nb.trainer.FusedAdam(model, lr=1e-4)
+    l0, _, _ = tr.step(batch, training=True)
+    l1, _, _ = tr.step(batch, training=True)
+    assert abs(l0.item() - meta['loss0']) < 2e-2 * abs(meta['loss0'])
+    assert abs(l1.item() - meta['loss1']) < 5e-2 * abs(meta['loss1'])
+
+
+def test_autograd_path_and_state_dict_roundtrip(golden_meta, tmp_path):
+    arch = golden_meta['small_mixed']['arch']
+    model = build(arch, 'fp32').train()
+    (audio, alen), (tg, tl) = nb.data.make_batch(3, 70, seed=0, min_len=35)
+    logits = model(audio.to(DEV))
+    logp = torch.log_softmax(logits, 2)
+    loss = nb.get_loss()(logp, (alen // 4).to(DEV), tg.to(DEV), tl.to(DEV))
+    loss.backward()
+    sd0 = M.build_state_dict(arch, seed=1235)
+    p = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    lr = M.ctc_loss_ref(torch.log_softmax(M.forward(p, arch, audio), 2), alen // 4, tg, tl)
+    lr.backward()
+    assert abs(loss.item() - lr.item()) < 1e-4 * abs(lr.item())
+    for k, q in model.named_parameters():
+        ref = p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])
+        assert float((q.grad.cpu().double() - ref.double()).norm()) <= 2e-3 * float(ref.double().norm()) + 1e-9, k
+    # checkpoint interchange: reference-shaped keys and shapes
+    tr = trainer(model)
+    tr.optimizer = nb.trainer.FusedAdam(model, lr=1e-4)
+    tr.save(tmp_path / 'x.ckpt')
+    st = torch.load(tmp_path / 'x.ckpt', map_location='cpu')
+    assert list(st['model'].keys()) == list(sd0.keys())
+    assert all(st['model'][k].shape == sd0[k].shape for k in sd0)
+    for k in sd0:
+        assert torch.equal(st['model'][k], sd0[k]), k
+
+
+def test_dropout_training_runs_and_differs():
+    model = build([[0, 1], [2, 1, 0], [5, 1, 0, 1]], 'bf16', dropout=0.2).train()
+    batch = nb.data.make_batch(2, 64, seed=1, min_len=40)
+    tr = trainer(model)
+    tr.optimizer = nb.trainer.FusedAdam(model, lr=1e-4)
+    l0, lp0, _ = tr.step(batch, training=True)
+    l1, lp1, _ = tr.step(batch, training=True)
+    assert torch.isfinite(l0) and torch.isfinite(l1)
+    model.eval()
+    a, b, _ = tr.step(batch, training=False)
+    c, d, _ = tr.step(batch, training=False)
+    assert torch.equal(b, d)                                   # eval is deterministic (no dropout)

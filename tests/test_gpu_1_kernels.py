@@ -252,11 +252,12 @@ def test_head_ctc_greedy_per():
     _lib.check(lib.nbasr_head_fwd(F32, hd.data_ptr(), T * K, K, B, T, K, V, wd.data_ptr(), bd.data_ptr(), lg.data_ptr(), lp.data_ptr(), U.stream()))
     torch.cuda.synchronize()
     assert U.relerr(lg.cpu(), logits.detach()) < 1e-5 and U.relerr(lp.cpu(), logp.detach()) < 1e-5
+    tgd, alend, tld = tg.to(U.DEV), alen.to(U.DEV), tl.to(U.DEV)     # keep device copies alive across the calls
     nll = torch.zeros(B, device=U.DEV)
     lossd = torch.zeros(1, device=U.DEV)
     dl = torch.zeros(B, T, V, device=U.DEV)
     work = torch.zeros(2 * B * T * (2 * S + 1) + 16, device=U.DEV)
-    _lib.check(lib.nbasr_ctc(lp.data_ptr(), B, T, V, tg.to(U.DEV).data_ptr(), S, alen.to(U.DEV).data_ptr(), 4, tl.to(U.DEV).data_ptr(),
+    _lib.check(lib.nbasr_ctc(lp.data_ptr(), B, T, V, tgd.data_ptr(), S, alend.data_ptr(), 4, tld.data_ptr(),
                              nll.data_ptr(), lossd.data_ptr(), dl.data_ptr(), work.data_ptr(), U.stream()))
     torch.cuda.synchronize()
     assert abs(lossd.item() - loss.item()) < 1e-5 * abs(loss.item())
@@ -278,8 +279,8 @@ def test_head_ctc_greedy_per():
     dist = torch.zeros(B, dtype=torch.int32, device=U.DEV)
     per = torch.zeros(2, dtype=torch.float64, device=U.DEV)
     iw = torch.zeros(B * (S + 2) + 16, dtype=torch.int32, device=U.DEV)
-    _lib.check(lib.nbasr_greedy_per(lp.data_ptr(), B, T, V, alen.to(U.DEV).data_ptr(), 4, tg.to(U.DEV).data_ptr(), S,
-                                    tl.to(U.DEV).data_ptr(), lut.data_ptr(), hyp.data_ptr(), hl.data_ptr(), dist.data_ptr(),
+    _lib.check(lib.nbasr_greedy_per(lp.data_ptr(), B, T, V, alend.data_ptr(), 4, tgd.data_ptr(), S,
+                                    tld.data_ptr(), lut.data_ptr(), hyp.data_ptr(), hl.data_ptr(), dist.data_ptr(),
                                     per.data_ptr(), iw.data_ptr(), U.stream()))
     torch.cuda.synchronize()
     rper, rd, _, rh = D.per_batch(lp.cpu().numpy(), out_len.numpy(), tg.numpy(), tl.numpy())

@@ -59,18 +59,20 @@ def test_gemm_tn_conv_epilogue(stride):
     assert (m != exp).float().mean() < 1e-4                    # accumulation-order ties at z ~ 0 only
 
 
-@pytest.mark.parametrize('nb,nr,M_,N', [(1, 64, 128, 256), (2, 100, 64, 64), (4, 500, 600, 640), (3, 125, 2000, 500)])
-def test_gemm_wgrad(nb, nr, M_, N):
+@pytest.mark.parametrize('nb,nr,M_,N,ldx', [(1, 64, 128, 256, 256), (2, 100, 64, 64, 64), (4, 500, 600, 640, 640),
+                                             (3, 125, 2000, 500, 512)])
+def test_gemm_wgrad(nb, nr, M_, N, ldx):
+    # ldx > N: the LSTM h_seq buffer keeps 500 hidden units in rows of 512 (16-byte aligned pitch for TMA)
     torch.manual_seed(12)
     dy = _bf(torch.randn(nb, nr, M_))
-    x = _bf(torch.randn(nb, nr, N))
-    ref = torch.einsum('brm,brn->mn', dy, x)
+    x = _bf(torch.randn(nb, nr, ldx))
+    ref = torch.einsum('brm,brn->mn', dy, x[:, :, :N])
     dyb, xb = U.to_padded(dy, BF16), U.to_padded(x, BF16)
     dw = torch.zeros(M_, N, device=U.DEV)
-    U.run_wgrad(BF16, U.ptr(dyb, PAD_L * M_), U.geo(nr) * M_, M_, U.ptr(xb, PAD_L * N), U.geo(nr) * N, N, nb, nr, M_, N, dw, N)
+    args = (BF16, U.ptr(dyb, PAD_L * M_), U.geo(nr) * M_, M_, U.ptr(xb, PAD_L * ldx), U.geo(nr) * ldx, ldx, nb, nr, M_, N, dw, N)
+    U.run_wgrad(*args)
     assert U.relerr(dw.cpu(), ref) < 1e-5, U.relerr(dw.cpu(), ref)
-    # accumulates (+=)
-    U.run_wgrad(BF16, U.ptr(dyb, PAD_L * M_), U.geo(nr) * M_, M_, U.ptr(xb, PAD_L * N), U.geo(nr) * N, N, nb, nr, M_, N, dw, N)
+    U.run_wgrad(*args)                                      # accumulates (+=)
     assert U.relerr(dw.cpu(), 2 * ref) < 1e-5
 
 

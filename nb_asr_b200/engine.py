@@ -209,6 +209,7 @@ class Engine:
         st = torch.cuda.current_stream().cuda_stream
         for fn, args in self.pack_ops:
             _lib.check(fn(*args, st), 'pack')
+        self.launches += len(self.pack_ops)
         if self.model.use_rnn:
             off_i, n = self.slices[self.lstm_name + '.bias_ih_l0']
             off_h, _ = self.slices[self.lstm_name + '.bias_hh_l0']
@@ -565,11 +566,13 @@ class Engine:
     # ------------------------------------------------------------------ execution
     def _run(self, ops):
         st = torch.cuda.current_stream().cuda_stream
+        n = 0
         for fn, args in ops:
             rc = fn(*args, st)
             if rc != 0:
                 raise _lib.NbasrError(f'{fn.__name__}: {self.lib.nbasr_last_error().decode()}')
-        self.launches += len(ops)
+            n += 2 if fn.__name__ == 'nbasr_head_bwd' else 1
+        self.launches += n     # kernels launched (every C-ABI call launches >= 1 kernel of libnbasr)
 
     def forward(self, audio, training=None):
         """audio (B, 80, T) fp32 cuda -> plan (holds logits / logp buffers)."""
@@ -604,11 +607,22 @@ class Engine:
                 else:
                     p.grad = gv.view(p.shape)
 
-    def optimizer_step(self, lr, reg_coef=0.01, max_norm=5.0, betas=(0.9, 0.999), eps=1e-7):
-        if getattr(self, '_lr_host', None) != lr:   # device copy only when the schedule changes lr
+    def set_lr(self, lr):
+        if getattr(self, '_lr_host', None) != lr:   # device write only when the schedule changes lr
             self.opt_state[1:2].fill_(lr)
             self._lr_host = lr
+
+    def optimizer_step(self, lr, reg_coef=0.01, max_norm=5.0, betas=(0.9, 0.999), eps=1e-7):
+        self.set_lr(lr)
         self._optimizer_launch(reg_coef, max_norm, betas, eps)
+
+    def snapshot_state(self):
+        return (self.flat_p.clone(), self.adam_m.clone(), self.adam_v.clone(), self.opt_state.clone(), self.drop_step.clone())
+
+    def restore_state(self, st):
+        self.flat_p.copy_(st[0]); self.adam_m.copy_(st[1]); self.adam_v.copy_(st[2]); self.opt_state.copy_(st[3])
+        self.drop_step.copy_(st[4])
+        self.refresh_packs(force=True)
 
     def _optimizer_launch(self, reg_coef=0.01, max_norm=5.0, betas=(0.9, 0.999), eps=1e-7):
         st = torch.cuda.current_stream().cuda_stream
@@ -616,6 +630,7 @@ class Engine:
                                              self.adam_v.data_ptr(), self.n_flat, self.seg_off.data_ptr(),
                                              self.seg_len.data_ptr(), int(self.seg_off.numel()), reg_coef, max_norm,
                                              betas[0], betas[1], eps, self.opt_state.data_ptr(), st), 'optim')
+        self.launches += 5 if self.seg_off.numel() else 3
         self.refresh_packs(force=True)
 
 

@@ -1,0 +1,97 @@
+"""Per-launch timing of an engine plan with CUDA events (on the launching stream) + algorithmic work model.
+
+Used by bench.py for the live roofline figure and by tools/ for optimisation work.  Algorithmic
+FLOPs / bytes follow SURVEY.md §8(d) / DESIGN.md "Kernels and rooflines".
+"""
+import collections
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, GConv, Gemm, Wgrad
+
+
+def _struct_of(arg, typ):
+    # ctypes.byref objects keep the referenced struct in ._obj
+    obj = getattr(arg, '_obj', None)
+    return obj if isinstance(obj, typ) else None
+
+
+def op_work(fn_name, args, es):
+    """(class tag, algorithmic flops, algorithmic bytes) of one plan entry. es = activation element size."""
+    if fn_name == 'nbasr_gemm_tn':
+        g = _struct_of(args[0], Gemm)
+        rows = g.nb * g.nr
+        flops = 2.0 * rows * g.K * g.N
+        a_cols = min(g.K, g.a_rs) if g.a_rs > 0 else g.K      # overlapping rows are read once
+        byts = rows * a_cols * es + g.N * g.K * es + rows * g.N * es * (1 + g.epi.n_add)
+        return f'gemm_tn K={g.K} N={g.N}', flops, byts
+    if fn_name == 'nbasr_gemm_wgrad':
+        w = _struct_of(args[0], Wgrad)
+        rows = w.nb * w.nr
+        flops = 2.0 * rows * w.M * w.N
+        x_cols = min(w.N, w.x_rs)
+        byts = rows * (w.M + x_cols) * es + 4.0 * w.M * w.N * 2
+        return f'gemm_wgrad M={w.M} N={w.N}', flops, byts
+    if fn_name == 'nbasr_gconv_fwd':
+        g = _struct_of(args[0], GConv)
+        el = g.B * g.T * g.C
+        return f'gconv C={g.C} k={g.ktaps} d={g.dstep}', 2.0 * el * g.cpg * g.ktaps, el * es * (2 + g.epi.n_add)
+    if fn_name == 'nbasr_gconv_wgrad':
+        dt, dz, x, B, T, Tp, Cc, cpg, k = args[:9]
+        el = B * T * Cc
+        return f'gconv_wgrad C={Cc} k={k}', 2.0 * el * cpg * k, el * es * 2
+    if fn_name in ('nbasr_layernorm_fwd', 'nbasr_layernorm_bwd'):
+        if fn_name.endswith('fwd'):
+            B, T, Tp, Cc = args[3:7]
+            return f'ln_fwd C={Cc}', 0.0, B * T * Cc * es * 2
+        B, T, Tp, Cc = args[6:10]
+        n_out = (1 if args[10] else 0) + (1 if args[11] else 0)
+        return f'ln_bwd C={Cc}', 0.0, B * T * Cc * es * (2 + n_out)
+    if fn_name == 'nbasr_eltwise':
+        B, T, Tp, Cc = args[3:7]
+        return f'eltwise C={Cc}', 0.0, B * T * Cc * es * 2
+    if fn_name == 'nbasr_colsum':
+        B, T, Tp, Cc = args[2:6]
+        return f'colsum C={Cc}', 0.0, B * T * Cc * (2 if args[0] == BF16 else 4)
+    return fn_name.replace('nbasr_', ''), 0.0, 0.0
+
+
+def profile_ops(engine, ops, iters=3):
+    """Time every entry of a plan op list. Returns {tag: dict(n, ms, flops, bytes)} averaged over iters."""
+    st = torch.cuda.current_stream()
+    es = 2 if engine.dt == BF16 else 4
+    n = len(ops)
+    acc = collections.OrderedDict()
+    for it in range(iters + 1):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        evs[0].record(st)
+        for i, (fn, args) in enumerate(ops):
+            _lib.check(fn(*args, st.cuda_stream), fn.__name__)
+            evs[i + 1].record(st)
+        torch.cuda.synchronize()
+        if it == 0:
+            continue   # warm-up pass
+        for i, (fn, args) in enumerate(ops):
+            tag, fl, by = op_work(fn.__name__, args, es)
+            d = acc.setdefault(tag, dict(n=0, ms=0.0, flops=0.0, bytes=0.0))
+            d['n'] += 1
+            d['ms'] += evs[i].elapsed_time(evs[i + 1])
+            d['flops'] += fl
+            d['bytes'] += by
+    for d in acc.values():
+        for k in d:
+            d[k] /= iters
+    return acc
+
+
+def format_profile(acc, top=40):
+    tot = sum(d['ms'] for d in acc.values())
+    lines = [f'{"class":38s} {"n":>4s} {"ms":>8s} {"%":>6s} {"TFLOP/s":>8s} {"GB/s":>8s}']
+    for tag, d in sorted(acc.items(), key=lambda kv: -kv[1]['ms'])[:top]:
+        tf = d['flops'] / d['ms'] / 1e9 if d['ms'] > 0 else 0
+        gb = d['bytes'] / d['ms'] / 1e6 if d['ms'] > 0 else 0
+        lines.append(f'{tag:38s} {d["n"]:4.0f} {d["ms"]:8.3f} {100 * d["ms"] / tot:6.1f} {tf:8.1f} {gb:8.0f}')
+    lines.append(f'{"total":38s} {"":4s} {tot:8.3f}')
+    return '\n'.join(lines)

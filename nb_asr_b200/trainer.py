@@ -39,25 +39,33 @@ class AvgMeter:
         return self.avg
 
 
+class _Ws:
+    pass
+
+
 class _CtcWorkspace:
+    """Per-shape scratch buffers; never freed, so pointers captured in CUDA graphs stay valid."""
+
     def __init__(self):
-        self.key = None
+        self.cache = {}
 
     def get(self, dev, B, T, V, S):
         key = (str(dev), B, T, V, S)
-        if key != self.key:
+        w = self.cache.get(key)
+        if w is None:
             L = 2 * S + 1
-            self.work = torch.empty(2 * B * T * L + 16, dtype=torch.float32, device=dev)
-            self.nll = torch.zeros(B, dtype=torch.float32, device=dev)
-            self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
-            self.dlogits = torch.zeros((B, T, V), dtype=torch.float32, device=dev)
-            self.hyp = torch.zeros((B, T), dtype=torch.int32, device=dev)
-            self.hyp_len = torch.zeros(B, dtype=torch.int32, device=dev)
-            self.dist = torch.zeros(B, dtype=torch.int32, device=dev)
-            self.per = torch.zeros(2, dtype=torch.float64, device=dev)
-            self.iwork = torch.zeros(B * (S + 2) + 16, dtype=torch.int32, device=dev)
-            self.key = key
-        return self
+            w = _Ws()
+            w.work = torch.empty(2 * B * T * L + 16, dtype=torch.float32, device=dev)
+            w.nll = torch.zeros(B, dtype=torch.float32, device=dev)
+            w.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+            w.dlogits = torch.zeros((B, T, V), dtype=torch.float32, device=dev)
+            w.hyp = torch.zeros((B, T), dtype=torch.int32, device=dev)
+            w.hyp_len = torch.zeros(B, dtype=torch.int32, device=dev)
+            w.dist = torch.zeros(B, dtype=torch.int32, device=dev)
+            w.per = torch.zeros(2, dtype=torch.float64, device=dev)
+            w.iwork = torch.zeros(B * (S + 2) + 16, dtype=torch.int32, device=dev)
+            self.cache[key] = w
+        return w
 
 
 _ws = _CtcWorkspace()
@@ -113,6 +121,10 @@ def get_loss():
                              targets_len.to(out.device, torch.int64).contiguous())
         return l.clone().squeeze(0)
     return loss
+
+
+class _GraphCaptureError(RuntimeError):
+    pass
 
 
 class FusedAdam:
@@ -221,23 +233,114 @@ class Trainer:
         audio_len = audio_len.to(device=dev, dtype=torch.int64, non_blocking=True)
         targets = targets.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
         targets_len = targets_len.to(device=dev, dtype=torch.int64, non_blocking=True)
+        if getattr(self, 'use_graph', False):
+            try:
+                return self._step_graph(audio, audio_len, targets, targets_len, training)
+            except _GraphCaptureError as e:       # eager launches of the same kernels; still GPU-only
+                import sys
+                sys.stderr.write(f'[nb_asr_b200] CUDA graph capture unavailable ({e}); running eagerly\n')
+                self.use_graph = False
+        return self._step_eager(audio, audio_len, targets, targets_len, training)
+
+    def _lr(self):
+        return self.optimizer.param_groups[0]['lr'] if self.optimizer is not None else (self.lr or 1e-4)
+
+    def _ctc(self, eng, pl, targets, audio_len, targets_len, training, ws):
+        B, S = targets.shape
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(eng.lib.nbasr_ctc(pl.logp.data_ptr(), B, pl.Tq, pl.V, targets.data_ptr(), S, audio_len.data_ptr(), 4,
+                                     targets_len.data_ptr(), ws.nll.data_ptr(), ws.loss.data_ptr(),
+                                     pl.dlogits.data_ptr() if training else None, ws.work.data_ptr(), st), 'ctc')
+        eng.launches += 1
+
+    def _step_eager(self, audio, audio_len, targets, targets_len, training):
         model = self._model
         eng = model.engine
         pl = eng.forward(audio, training=model.training)
         B, S = targets.shape
-        ws = _ws.get(dev, B, pl.Tq, pl.V, S)
-        lib = eng.lib
-        st = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.nbasr_ctc(pl.logp.data_ptr(), B, pl.Tq, pl.V, targets.data_ptr(), S, audio_len.data_ptr(), 4,
-                                 targets_len.data_ptr(), ws.nll.data_ptr(), ws.loss.data_ptr(),
-                                 pl.dlogits.data_ptr() if training else None, ws.work.data_ptr(), st), 'ctc')
+        ws = _ws.get(self.device, B, pl.Tq, pl.V, S)
+        self._ctc(eng, pl, targets, audio_len, targets_len, training, ws)
         if training:
             eng.backward(pl)
             self._allreduce_grads(eng)
-            lr = self.optimizer.param_groups[0]['lr'] if self.optimizer is not None else (self.lr or 1e-4)
-            eng.optimizer_step(lr)
-        output_len = audio_len // 4
-        return ws.loss[0].clone(), pl.logp.clone(), output_len
+            eng.optimizer_step(self._lr())
+        return ws.loss[0].clone(), pl.logp.clone(), audio_len // 4
+
+    def _step_graph(self, audio, audio_len, targets, targets_len, training):
+        """Same launches as _step_eager, replayed from CUDA graphs (static buffers, no per-launch host cost)."""
+        import torch.distributed as dist
+        model = self._model
+        eng = model.engine
+        eng.bind()
+        B, _, T = audio.shape
+        S = targets.shape[1]
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        key = (id(eng), B, T, S, bool(training), bool(model.training), multi)
+        if not hasattr(self, '_graphs'):
+            self._graphs = {}
+        ent = self._graphs.get(key)
+        pl = eng.plan(B, T, model.training)
+        ws = _ws.get(self.device, B, pl.Tq, pl.V, S)
+        eng.refresh_packs()
+        if training:
+            eng.set_lr(self._lr())
+        if ent is None:
+            ent = dict(alen=torch.zeros_like(audio_len), tg=torch.zeros_like(targets), tl=torch.zeros_like(targets_len), ws=ws)
+            ent['alen'].copy_(audio_len); ent['tg'].copy_(targets); ent['tl'].copy_(targets_len)
+            pl.audio.copy_(audio)
+
+            def body_main():
+                if model.training and eng.training_drop > 0:
+                    eng.drop_step.add_(1)
+                eng._run(pl.fwd)
+                self._ctc(eng, pl, ent['tg'], ent['alen'], ent['tl'], training, ws)
+                if training:
+                    eng.flat_g.zero_()
+                    eng._run(pl.bwd)
+                    if not multi:
+                        eng._optimizer_launch()
+
+            # eager warm-up run on a side stream (sets function attributes, fills the tensor-map cache)
+            state = eng.snapshot_state() if training else None
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body_main()
+                if training and multi:
+                    eng._optimizer_launch()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if state is not None:
+                eng.restore_state(state)
+            n0 = eng.launches
+            try:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    body_main()
+                ent['g1'] = g1
+                ent['n1'] = eng.launches - n0
+                if training and multi:
+                    n0 = eng.launches
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2):
+                        eng._optimizer_launch()
+                    ent['g2'] = g2
+                    ent['n2'] = eng.launches - n0
+            except Exception as e:  # noqa: BLE001
+                torch.cuda.synchronize()
+                raise _GraphCaptureError(str(e)) from e
+            self._graphs[key] = ent
+        ent['alen'].copy_(audio_len, non_blocking=True)
+        ent['tg'].copy_(targets, non_blocking=True)
+        ent['tl'].copy_(targets_len, non_blocking=True)
+        pl.audio.copy_(audio, non_blocking=True)
+        ent['g1'].replay()
+        eng.launches += ent['n1']
+        if training and multi:
+            self._allreduce_grads(eng)
+            ent['g2'].replay()
+            eng.launches += ent['n2']
+        return ws.loss[0].clone(), pl.logp.clone(), audio_len // 4
 
     def _allreduce_grads(self, eng):
         import torch.distributed as dist

@@ -110,12 +110,19 @@ typedef struct nbasr_gconv {
   int32_t dtype;
   const void* x;          /* (B, Tp, C) padded activation, pointer to row 0 of the buffer */
   int32_t B, T, Tp, C, cpg, ktaps, off0, dstep;
-  const float* w;
+  const void* w;          /* w_packed = 0: fp32 (C, cpg, ktaps)  -> SIMT kernel (any dtype)
+                             w_packed = 1: bf16 block-diagonal pack of nbasr_pack_gconv_mma -> tcgen05 kernel (BF16) */
+  int32_t w_packed;
   nbasr_epilogue epi;     /* rows rho = b*Tp + PAD_L + t */
 } nbasr_gconv;
 
 int nbasr_gconv_fwd(const nbasr_gconv* p, void* stream);
 int nbasr_pack_gconv_dgrad(const float* w, float* wt, int C, int cpg, int ktaps, void* stream);
+/* bf16 block-diagonal operand for the tcgen05 grouped-conv kernel: [slab][tap][48][64], slabs of 48 (cpg 6/8/12)
+ * or 40 (cpg 10) channels; transposed = 1 gives the input-gradient operand (group-transposed, taps flipped).
+ * nbasr_gconv_mma_pack_elems returns the number of bf16 elements of the pack. */
+int nbasr_pack_gconv_mma(const float* w, void* out, int C, int cpg, int ktaps, int transposed, void* stream);
+int64_t nbasr_gconv_mma_pack_elems(int C, int cpg, int ktaps);
 /* dw[c_out][i][j] += sum_{b,t} dz[b,t,c_out] * x[b, t+off0+j*dstep, g*cpg+i];  db[c] += sum dz */
 int nbasr_gconv_wgrad(int dtype, const void* dz, const void* x, int B, int T, int Tp, int C, int cpg,
                       int ktaps, int off0, int dstep, float* dw, void* stream);

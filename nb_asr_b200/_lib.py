@@ -31,7 +31,7 @@ class Wgrad(C.Structure):
 
 class GConv(C.Structure):
     _fields_ = [('dtype', _i32), ('x', _vp), ('B', _i32), ('T', _i32), ('Tp', _i32), ('C', _i32), ('cpg', _i32),
-                ('ktaps', _i32), ('off0', _i32), ('dstep', _i32), ('w', _vp), ('epi', Epilogue)]
+                ('ktaps', _i32), ('off0', _i32), ('dstep', _i32), ('w', _vp), ('w_packed', _i32), ('epi', Epilogue)]
 
 
 _SIGS = {
@@ -39,6 +39,8 @@ _SIGS = {
     'nbasr_gemm_wgrad': [C.POINTER(Wgrad), _vp],
     'nbasr_gconv_fwd': [C.POINTER(GConv), _vp],
     'nbasr_pack_gconv_dgrad': [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp],
+    'nbasr_pack_gconv_mma': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    'nbasr_gconv_mma_pack_elems': [C.c_int, C.c_int, C.c_int],
     'nbasr_gconv_wgrad': [C.c_int, _vp, _vp] + [C.c_int] * 8 + [_vp, _vp],
     'nbasr_eltwise': [C.c_int, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), _vp],
     'nbasr_colsum': [C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
@@ -91,6 +93,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.nbasr_gconv_mma_pack_elems.restype = C.c_int64
     lib.nbasr_last_error.restype = C.c_char_p
     lib.nbasr_last_error.argtypes = []
     _lib = lib

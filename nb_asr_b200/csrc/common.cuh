@@ -95,25 +95,33 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused output stage on one (row, 32-column chunk). v[32] holds the accumulator values.
-// ncol = number of valid columns in the tensor (row pitches must keep 16-byte alignment).
+// Fused output stage on one row and NV (multiple of 8) consecutive columns starting at c0 (multiple
+// of 8).  v[NV] holds the accumulator values; nvalid = number of valid columns (<= NV).  Masks are
+// bit arrays addressed by BYTE (8 columns per byte; row pitch ld_mask is given in 32-bit words), so
+// any 8-aligned column range can be produced by one thread without touching its neighbours' bits.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk(const nbasr_epilogue& e, int64_t rho, int c0, int ncol,
-                                               float* v) {
-  const int nvalid = min(32, ncol - c0);
-  uint32_t m = 0xffffffffu;
+template <int NV>
+__device__ __forceinline__ void epilogue_cols(const nbasr_epilogue& e, int64_t rho, int c0, int nvalid, float* v) {
+  constexpr int NG = NV / 8;
+  uint32_t m[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) m[g] = 0xffu;
   if (e.bias) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
+    for (int i = 0; i < NV; ++i)
       if (i < nvalid) v[i] += __ldg(e.bias + c0 + i);
   }
   if (e.relu20) {
-    m = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float z = v[i];
-      if (z > 0.f && z <= 20.f) m |= (1u << i);
-      v[i] = fminf(fmaxf(z, 0.f), 20.f);
+    for (int g = 0; g < NG; ++g) {
+      uint32_t mm = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float z = v[g * 8 + i];
+        if (z > 0.f && z <= 20.f) mm |= (1u << i);
+        v[g * 8 + i] = fminf(fmaxf(z, 0.f), 20.f);
+      }
+      m[g] = mm;
     }
   }
   if (e.drop_p > 0.f) {
@@ -121,16 +129,16 @@ __device__ __forceinline__ void epilogue_chunk(const nbasr_epilogue& e, int64_t 
     const uint32_t thr = static_cast<uint32_t>(e.drop_p * 4294967296.0);
     const uint64_t seed = e.drop_seed + (e.drop_step ? __ldg(e.drop_step) * 0xD1B54A32D192ED03ull : 0ull);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < NV; ++i) {
       uint32_t h = hash_u32(seed, static_cast<uint64_t>(rho) * 4096ull + c0 + i);
       bool keep = h >= thr;
-      if (!keep) m &= ~(1u << i);
+      if (!keep) m[i >> 3] &= ~(1u << (i & 7));
       v[i] = keep ? v[i] * scale : 0.f;
     }
   }
   for (int a = 0; a < e.n_add; ++a) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g) {
       if (g * 8 < nvalid) {
         float t[8];
         load8_dt_n(e.add[a], e.add_dtype, rho * e.ld_out + c0 + g * 8, t, nvalid - g * 8);
@@ -143,27 +151,38 @@ __device__ __forceinline__ void epilogue_chunk(const nbasr_epilogue& e, int64_t 
     if (e.accumulate) {
       float* o = reinterpret_cast<float*>(e.out) + rho * e.ld_out + c0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
+      for (int i = 0; i < NV; ++i)
         if (i < nvalid) o[i] += v[i];
     } else {
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < NG; ++g)
         if (g * 8 < nvalid) store8_dt_n(e.out, e.out_dtype, rho * e.ld_out + c0 + g * 8, v + g * 8, nvalid - g * 8);
     }
   }
-  if (e.mask_out) e.mask_out[rho * e.ld_mask + (c0 >> 5)] = m;
-  if (e.out2) {
-    uint32_t w = e.mask2 ? e.mask2[rho * e.ld_mask + (c0 >> 5)] : 0xffffffffu;
+  if (e.mask_out) {
+    uint8_t* mo = reinterpret_cast<uint8_t*>(e.mask_out) + rho * e.ld_mask * 4 + (c0 >> 3);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g)
+      if (g * 8 < nvalid) mo[g] = static_cast<uint8_t>(m[g]);
+  }
+  if (e.out2) {
+    const uint8_t* mi = e.mask2 ? reinterpret_cast<const uint8_t*>(e.mask2) + rho * e.ld_mask * 4 + (c0 >> 3) : nullptr;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
       if (g * 8 < nvalid) {
+        uint32_t w = mi ? mi[g] : 0xffu;
         float t[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = ((w >> (g * 8 + i)) & 1u) ? v[g * 8 + i] * e.scale2 : 0.f;
+        for (int i = 0; i < 8; ++i) t[i] = ((w >> i) & 1u) ? v[g * 8 + i] * e.scale2 : 0.f;
         store8_dt_n(e.out2, e.out2_dtype, rho * e.ld_out + c0 + g * 8, t, nvalid - g * 8);
       }
     }
   }
+}
+
+// one (row, aligned 32-column chunk); ncol = number of valid columns of the tensor
+__device__ __forceinline__ void epilogue_chunk(const nbasr_epilogue& e, int64_t rho, int c0, int ncol, float* v) {
+  epilogue_cols<32>(e, rho, c0, min(32, ncol - c0), v);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -1,0 +1,104 @@
+// Micro-experiment kernel (test-only entry point): does a UMMA shared-memory descriptor whose start
+// address is shifted by whole 128-byte rows inside a 128B-swizzled tile address the right data?
+// mode 0: K-major A tile of (128+pad) rows x 64 bf16; D[m][n] = sum_k A[m+shift][k] * B[n][k]
+// mode 1: MN-major: D[m][n] = sum_{k<64} Y[k][m] * X[k+shift][n]   (Y: 64 x 128, X: (64+pad) x 64)
+// bo_mode 0: base_offset field = 0; 1: base_offset = (start_addr >> 7) & 7.
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int PADROWS = 16;
+
+__global__ void __launch_bounds__(128, 1)
+dbg_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* D, int mode, int shift,
+                 int bo_mode) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sa = base;                    // up to 144 rows x 128 B = 18 KB  (mode 1: Y, 2 boxes of 64x64)
+  const uint32_t sb = base + 32768;            // B / X tile
+  const uint32_t bar = base + 65536;
+  const uint32_t tbar = bar + 8;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(al + 65536 + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(tbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tptr), 64);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tm = *tptr;
+  if (threadIdx.x == 0) {
+    if (mode == 0) {
+      mbar_expect_tx(bar, (128 + PADROWS) * 128 + 64 * 128);
+      tma_load_2d(sa, &tmA, bar, 0, 0);
+      tma_load_2d(sb, &tmB, bar, 0, 0);
+    } else {
+      mbar_expect_tx(bar, 2 * 64 * 128 + (64 + PADROWS) * 128);
+      tma_load_2d(sa, &tmA, bar, 0, 0);
+      tma_load_2d(sa + 8192, &tmA, bar, 64, 0);
+      tma_load_2d(sb, &tmB, bar, 0, 0);
+    }
+    mbar_wait(bar, 0);
+    tcgen05_fence_after();
+    for (int k = 0; k < 4; ++k) {
+      uint64_t ad, bd;
+      if (mode == 0) {
+        uint32_t a0 = sa + shift * 128 + k * 32;
+        ad = make_smem_desc(a0, 16, 1024, bo_mode ? (a0 >> 7) & 7 : 0);
+        bd = make_smem_desc(sb + k * 32, 16, 1024);
+      } else {
+        uint32_t b0 = sb + shift * 128 + k * 2048;
+        ad = make_smem_desc(sa + k * 2048, 8192, 1024);
+        bd = make_smem_desc(b0, 8192, 1024, bo_mode ? (b0 >> 7) & 7 : 0);
+      }
+      umma_bf16(tm, ad, bd, make_idesc(128, 64, mode, mode), k != 0);
+    }
+    umma_commit(tbar);
+  }
+  mbar_wait(tbar, 0);
+  tcgen05_fence_after();
+  for (int c = 0; c < 64; c += 32) {
+    float v[32];
+    tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c, v);
+    for (int i = 0; i < 32; ++i) D[(warp * 32 + lane) * 64 + c + i] = v[i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 64);
+}
+
+}  // namespace
+
+extern "C" int nbasr_dbg_shift(const void* A, const void* B, float* D, int mode, int shift, int bo_mode, void* stream) {
+  CUtensorMap tmA, tmB;
+  if (mode == 0) {
+    uint64_t da[2] = {64, 128 + PADROWS};
+    int64_t sa[2] = {1, 64};
+    uint32_t ba[2] = {64, 128 + PADROWS};
+    if (sm100_get_map(A, 2, da, sa, ba, &tmA)) return 1;
+    uint64_t db[2] = {64, 64};
+    uint32_t bb[2] = {64, 64};
+    if (sm100_get_map(B, 2, db, sa, bb, &tmB)) return 1;
+  } else {
+    uint64_t da[2] = {128, 64};
+    int64_t sa[2] = {1, 128};
+    uint32_t ba[2] = {64, 64};
+    if (sm100_get_map(A, 2, da, sa, ba, &tmA)) return 1;
+    uint64_t db[2] = {64, 64 + PADROWS};
+    int64_t sb[2] = {1, 64};
+    uint32_t bb[2] = {64, 64 + PADROWS};
+    if (sm100_get_map(B, 2, db, sb, bb, &tmB)) return 1;
+  }
+  cudaFuncSetAttribute(dbg_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024);
+  dbg_shift_kernel<<<1, 128, 70 * 1024, as_stream(stream)>>>(tmA, tmB, D, mode, shift, bo_mode);
+  NBASR_CHECK_LAUNCH();
+  return 0;
+}

@@ -67,28 +67,25 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
   }
 }
 
+// Backward: per-warp rows, dgamma/dbeta partials live in warp-private shared memory (layout [i][group] so
+// that the 32 lanes of a warp hit 32 different banks), which keeps registers low enough for 16 warps / SM.
 template <typename T>
-__global__ void __launch_bounds__(256, 1) layernorm_bwd_kernel(
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
     const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean_i,
     const float* __restrict__ rstd_i, const float* __restrict__ gamma, int B, int Tt, int Tp, int C,
     T* __restrict__ dx, T* __restrict__ dx2, const uint32_t* __restrict__ mask2, float scale2, int64_t ld_mask,
     float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ float red[];  // 2*C floats
-  const int lane = threadIdx.x & 31;
+  extern __shared__ float red[];  // 8 warps x 2 x (8 x GP) floats, GP = padded group count
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int ngroups = C >> 3;
+  const int GP = 32 * LN_MAXG;
   const int64_t nrows = (int64_t)B * Tt;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  float dg[LN_MAXG][8], db[LN_MAXG][8], ga[LN_MAXG][8];
-#pragma unroll
-  for (int q = 0; q < LN_MAXG; ++q) {
-    int g = lane + 32 * q;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dg[q][i] = db[q][i] = ga[q][i] = 0.f;
-    if (g < ngroups) load8(gamma + g * 8, ga[q]);
-  }
+  float* my_dg = red + (size_t)wib * 2 * 8 * GP;
+  float* my_db = my_dg + 8 * GP;
+  for (int i = lane; i < 2 * 8 * GP; i += 32) my_dg[i] = 0.f;
+  __syncwarp();
   for (int64_t r = warp; r < nrows; r += nwarps) {
     int b = (int)(r / Tt), t = (int)(r % Tt);
     int64_t rho = (int64_t)b * Tp + NBASR_PAD_L + t;
@@ -99,15 +96,16 @@ __global__ void __launch_bounds__(256, 1) layernorm_bwd_kernel(
     for (int q = 0; q < LN_MAXG; ++q) {
       int g = lane + 32 * q;
       if (g < ngroups) {
-        float xv[8], dv[8];
+        float xv[8], dv[8], ga[8];
         load8(x + rho * C + g * 8, xv);
         load8(dy + rho * C + g * 8, dv);
+        load8(gamma + g * 8, ga);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           xh[q][i] = (xv[i] - mean) * rstd;
-          dg[q][i] += dv[i] * xh[q][i];
-          db[q][i] += dv[i];
-          gy[q][i] = dv[i] * ga[q][i];
+          my_dg[i * GP + g] += dv[i] * xh[q][i];
+          my_db[i * GP + g] += dv[i];
+          gy[q][i] = dv[i] * ga[i];
           s1 += gy[q][i];
           s2 += gy[q][i] * xh[q][i];
         }
@@ -133,21 +131,18 @@ __global__ void __launch_bounds__(256, 1) layernorm_bwd_kernel(
       }
     }
   }
-#pragma unroll
-  for (int q = 0; q < LN_MAXG; ++q) {
-    int g = lane + 32 * q;
-    if (g < ngroups) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(&red[g * 8 + i], dg[q][i]);
-        atomicAdd(&red[C + g * 8 + i], db[q][i]);
-      }
-    }
-  }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(dgamma + i, red[i]);
-    atomicAdd(dbeta + i, red[C + i]);
+  // block reduction over the 8 warps, then one atomic per channel per block
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c >> 3, i = c & 7;
+    float a = 0.f, bsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += red[(size_t)w * 2 * 8 * GP + i * GP + g];
+      bsum += red[(size_t)w * 2 * 8 * GP + 8 * GP + i * GP + g];
+    }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, bsum);
   }
 }
 
@@ -175,26 +170,48 @@ __global__ void eltwise_kernel(int src_dtype, const void* __restrict__ src, int6
   epilogue_chunk(e, rho, c0, C, v);
 }
 
+constexpr int CS_MAXG = 8;  // C <= 2048
+
+// column sums: warp per row (16-byte vector loads, fully coalesced), register partials, block reduce, atomics
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ x, int B, int Tt, int Tp, int C, float* __restrict__ out) {
-  __shared__ float red[8][33];
-  int c = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  int64_t nrows = (int64_t)B * Tt;
-  if (c < C) {
-    for (int64_t r = blockIdx.y * 8 + threadIdx.y; r < nrows; r += (int64_t)gridDim.y * 8) {
-      int b = (int)(r / Tt), t = (int)(r % Tt);
-      s += static_cast<float>(x[((int64_t)b * Tp + NBASR_PAD_L + t) * C + c]);
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int B, int Tt, int Tp, int C, float* __restrict__ out) {
+  extern __shared__ float red[];  // C floats
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int ngroups = C >> 3;
+  const int64_t nrows = (int64_t)B * Tt;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float acc[CS_MAXG][8];
+#pragma unroll
+  for (int q = 0; q < CS_MAXG; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[q][i] = 0.f;
+  for (int64_t r = warp; r < nrows; r += nwarps) {
+    int b = (int)(r / Tt), t = (int)(r % Tt);
+    const T* xr = x + ((int64_t)b * Tp + NBASR_PAD_L + t) * C;
+#pragma unroll
+    for (int q = 0; q < CS_MAXG; ++q) {
+      int g = lane + 32 * q;
+      if (g < ngroups) {
+        float v[8];
+        load8(xr + g * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[q][i] += v[i];
+      }
     }
   }
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    atomicAdd(out + c, t);
+  for (int q = 0; q < CS_MAXG; ++q) {
+    int g = lane + 32 * q;
+    if (g < ngroups) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&red[g * 8 + i], acc[q][i]);
+    }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + i, red[i]);
 }
 
 template <typename T>
@@ -261,7 +278,13 @@ int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* m
   int64_t rows = (int64_t)B * T;
   int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 2);
   if (blocks < 1) return 0;
-  size_t sm = 2 * C * sizeof(float);
+  size_t sm = (size_t)8 * 2 * 8 * 32 * LN_MAXG * sizeof(float);   // 80 KB
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layernorm_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
   if (dtype == NBASR_BF16)
     layernorm_bwd_kernel<bf16><<<blocks, 256, sm, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, B, T, Tp, C, (bf16*)dx, (bf16*)dx2, mask2, scale2, ld_mask, dgamma, dbeta);
   else
@@ -280,9 +303,13 @@ int nbasr_eltwise(int src_dtype, const void* src, int64_t ld_src, int B, int T, 
 }
 
 int nbasr_colsum(int dtype, const void* x, int B, int T, int Tp, int C, float* out, void* stream) {
-  dim3 grid((C + 31) / 32, 64), block(32, 8);
-  if (dtype == NBASR_BF16) colsum_kernel<bf16><<<grid, block, 0, as_stream(stream)>>>((const bf16*)x, B, T, Tp, C, out);
-  else colsum_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)x, B, T, Tp, C, out);
+  NBASR_REQUIRE(C % 8 == 0 && C <= 8 * 32 * CS_MAXG, "C");
+  int64_t rows = (int64_t)B * T;
+  if (rows < 1) return 0;
+  int grid = (int)std::min<int64_t>((rows + 7) / 8, 148 * 4);
+  size_t sm = C * sizeof(float);
+  if (dtype == NBASR_BF16) colsum_kernel<bf16><<<grid, 256, sm, as_stream(stream)>>>((const bf16*)x, B, T, Tp, C, out);
+  else colsum_kernel<float><<<grid, 256, sm, as_stream(stream)>>>((const float*)x, B, T, Tp, C, out);
   NBASR_CHECK_LAUNCH();
   return 0;
 }

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(G_NT) gconv_fwd_kernel(nbasr_gconv p) {
   // stage weights of the slab: w[(c_lo+co)][i][j]
   for (int idx = tid; idx < cs * p.cpg * p.ktaps; idx += G_NT) {
     int co = idx / (p.cpg * p.ktaps), rem = idx % (p.cpg * p.ktaps);
-    ws[co * WP + rem] = p.w[(int64_t)(c_lo + co) * p.cpg * p.ktaps + rem];
+    ws[co * WP + rem] = reinterpret_cast<const float*>(p.w)[(int64_t)(c_lo + co) * p.cpg * p.ktaps + rem];
   }
   // stage input rows t0+off0 .. t0+off0+G_TT+halo-1 (zero outside [0,T))
   const int nrow = G_TT + halo;
@@ -223,6 +223,11 @@ extern "C" {
 
 int nbasr_gconv_fwd(const nbasr_gconv* p, void* stream) {
   NBASR_REQUIRE(p->C % p->cpg == 0 && p->C % 8 == 0, "channels");
+  if (p->B <= 0 || p->T <= 0) return 0;
+  if (p->w_packed) {
+    NBASR_REQUIRE(p->dtype == NBASR_BF16, "packed grouped-conv weights need bf16 activations");
+    return sm100_gconv_fwd(p, as_stream(stream));
+  }
   NBASR_REQUIRE(p->ktaps <= 7 && (p->dstep == 1 || p->dstep == 2), "taps");
   NBASR_REQUIRE(p->cpg == 6 || p->cpg == 8 || p->cpg == 10 || p->cpg == 12, "cpg (slab must stay 8-aligned)");
   int CS = slab_channels(p->cpg);
@@ -252,6 +257,9 @@ int nbasr_gconv_wgrad(int dtype, const void* dz, const void* x, int B, int T, in
                       int off0, int dstep, float* dw, void* stream) {
   NBASR_REQUIRE(cpg == 6 || cpg == 8 || cpg == 10 || cpg == 12, "cpg");
   NBASR_REQUIRE(ktaps <= 7 && (dstep == 1 || dstep == 2), "taps");
+  if (B <= 0 || T <= 0) return 0;
+  if (dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT"))
+    return sm100_gconv_wgrad(dz, x, B, T, Tp, C, cpg, ktaps, off0, dstep, dw, as_stream(stream));
   int CS = slab_channels(cpg);
   dim3 grid((C + CS - 1) / CS, B);
   size_t sm = wgrad_smem(cpg);

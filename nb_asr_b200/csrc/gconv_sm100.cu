@@ -1,0 +1,379 @@
+// Grouped conv edges (ops.py:73-76, groups=100, cpg = C/100 in {6,8,10,12}) on tcgen05 tensor cores.
+//
+// A grouped conv is HBM-bound (15-42 FLOP/B in bf16) but CUDA-core FMA cannot reach the HBM roofline
+// (SURVEY.md 7.3), so the groups are evaluated as BLOCK-DIAGONAL MMAs: a slab of OUT = 48 (40 for
+// cpg = 10) consecutive channels = 8/6/4/4 whole groups is one 128 x 48 x 48 MMA per tap whose weight
+// tile is zero outside the diagonal blocks (8x..4x redundant tensor FLOPs, still far below the HBM time).
+//
+//  * The input tile (128 frames + halo) x 64 channels is TMA-loaded ONCE per (frame tile, slab) in the
+//    128B-swizzled K-major layout; every (dilated) tap is the SAME tile addressed through a UMMA
+//    descriptor whose start address is advanced by whole 128-byte rows (swizzle is a function of the
+//    absolute smem address, verified on B200 with csrc/dbg.cu) -- no im2col, no per-tap reload.
+//  * A CTA keeps one slab's block-diagonal weights (<= 7 taps x 6 KB) in smem and walks frame tiles;
+//    2 CTAs / SM, 3-stage TMA ring, 4 TMEM accumulator stages, warp roles as in gemm_sm100.cu.
+//  * Forward and input-gradient share the kernel (different weight pack / tap offsets); the fused
+//    epilogue (bias, ReLU20, dropout, skip-sum, gradient mask) works on 8-column groups because slab
+//    boundaries are only 8-aligned.
+//  * Weight gradient: dW_j[co][ci] = sum_t dZ[t][co] X[t+off_j][ci], both operands MN-major (frames
+//    are the reduction index).  Two taps share one M=128 MMA: the A descriptor's "leading byte offset"
+//    makes rows 64..127 the same dZ tile shifted by `dstep` frames, so rows 0-63 give tap j+1 and rows
+//    64-127 tap j.  Diagonal blocks are extracted from TMEM and atomically added to the fp32 gradient.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int GT = 128;                    // frames per tile
+constexpr int AROWS = 144;                 // 128 + max halo 12, multiple of 8
+constexpr int A_BYTES = AROWS * 128;       // 18432
+constexpr int NW = 48;                     // MMA N (and K window) of a slab
+constexpr int WTAP_BYTES = NW * 128;       // 6144
+constexpr int MAXTAPS = 7;
+constexpr int NSTAGE = 3;
+constexpr int NACC = 4;
+constexpr int GC_THREADS = 192;
+constexpr int FWD_SMEM = MAXTAPS * WTAP_BYTES + NSTAGE * A_BYTES + 1024 + 256;
+
+__host__ __device__ inline int slab_out(int cpg) { return cpg == 10 ? 40 : 48; }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GcFwdArgs {
+  int B, T, C, OUT, ktaps, dstep, off0;
+  int nslabs, ntiles, tiles_per_utt, nlanes;
+  nbasr_epilogue epi;
+  int64_t Tp;
+};
+
+__global__ void __launch_bounds__(GC_THREADS, 2)
+gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const GcFwdArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t wsm = base;
+  const uint32_t asm0 = base + MAXTAPS * WTAP_BYTES;
+  const uint32_t bar0 = asm0 + NSTAGE * A_BYTES;
+  const uint32_t wbar = bar0;
+  auto full_bar = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (1 + NSTAGE + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (1 + 2 * NSTAGE + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (1 + 2 * NSTAGE + NACC + s); };
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(al + MAXTAPS * WTAP_BYTES + NSTAGE * A_BYTES + 8 * (1 + 2 * NSTAGE + 2 * NACC));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slab = blockIdx.x % p.nslabs;
+  const int lane_id = blockIdx.x / p.nslabs;
+  const int c0 = slab * p.OUT;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmW);
+    mbar_init(wbar, 1);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tptr), 256);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tm = *tptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wbar, p.ktaps * WTAP_BYTES);
+      for (int j = 0; j < p.ktaps; ++j) tma_load_2d(wsm + j * WTAP_BYTES, &tmW, wbar, 0, (slab * p.ktaps + j) * NW);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes) {
+        const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * GT;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_expect_tx(full_bar(stage), A_BYTES);
+        tma_load_3d(asm0 + stage * A_BYTES, &tmX, full_bar(stage), c0, NBASR_PAD_L + t0 + p.off0, b);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, NW, 0, 0);
+      mbar_wait(wbar, 0);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes, ++it) {
+        const int as = it % NACC;
+        const uint32_t aphase = (it / NACC) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        const uint32_t sa = asm0 + stage * A_BYTES;
+        for (int j = 0; j < p.ktaps; ++j) {
+#pragma unroll
+          for (int k = 0; k < NW / 16; ++k) {
+            uint64_t ad = make_smem_desc(sa + (j * p.dstep) * 128 + k * 32, 16, 1024);
+            uint64_t bd = make_smem_desc(wsm + j * WTAP_BYTES + k * 32, 16, 1024);
+            umma_bf16(tm + as * 64, ad, bd, idesc, (j | k) != 0);
+          }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(as));
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int nvalid = min(p.C, c0 + p.OUT) - c0;
+    int it = 0;
+    for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes, ++it) {
+      const int as = it % NACC;
+      const uint32_t aphase = (it / NACC) & 1;
+      const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * GT;
+      const int t = t0 + q * 32 + lane;
+      mbar_wait(tfull_bar(as), aphase);
+      tcgen05_fence_after();
+      float v[48];
+      const uint32_t ta = tm + ((uint32_t)(q * 32) << 16) + as * 64;
+      tmem_ld32(ta, v);
+      tmem_ld16(ta + 32, v + 32);
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar(as));       // accumulator is in registers: release the TMEM stage early
+      if (t < p.T) {
+        const int64_t rho = (int64_t)b * p.Tp + NBASR_PAD_L + t;
+        epilogue_cols<48>(p.epi, rho, c0, nvalid, v);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tm, 256);
+  }
+}
+
+// ---------------------------------------------------------------- weight gradient
+constexpr int DZROWS = 136;                       // 128 + dstep(<=2), multiple of 8
+constexpr int DZ_BYTES = DZROWS * 128;            // 17408
+constexpr int WG_STAGE = DZ_BYTES + A_BYTES;      // 35840
+constexpr int WG_SMEM = NSTAGE * WG_STAGE + 1024 + 256;
+
+struct GcWgArgs {
+  int B, T, C, cpg, OUT, ktaps, dstep, off0;
+  int nslabs, nchunks, nunits, nlanes;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(GC_THREADS, 2)
+gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmX, const GcWgArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + NSTAGE * WG_STAGE;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+  const uint32_t tfull = bar0 + 8u * (2 * NSTAGE);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(al + NSTAGE * WG_STAGE + 8 * (2 * NSTAGE + 2));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slab = blockIdx.x % p.nslabs;
+  const int lane_id = blockIdx.x / p.nslabs;
+  const int c0 = slab * p.OUT;
+  const int npairs = (p.ktaps + 1) / 2;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmDZ);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tptr), 256);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tm = *tptr;
+  const bool has_work = lane_id < p.nunits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = lane_id; u < p.nunits; u += p.nlanes) {
+        const int b = u / p.nchunks, t0 = (u % p.nchunks) * GT;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_expect_tx(full_bar(stage), DZ_BYTES + A_BYTES);
+        const uint32_t sa = base + stage * WG_STAGE;
+        tma_load_3d(sa, &tmDZ, full_bar(stage), c0, NBASR_PAD_L + t0 - p.dstep, b);
+        tma_load_3d(sa + DZ_BYTES, &tmX, full_bar(stage), c0, NBASR_PAD_L + t0 + p.off0, b);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      const uint32_t idesc = make_idesc(128, NW, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int u = lane_id; u < p.nunits; u += p.nlanes) {
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        const uint32_t sa = base + stage * WG_STAGE;
+        const uint32_t sb = sa + DZ_BYTES;
+        for (int pr = 0; pr < npairs; ++pr) {
+          const int j = 2 * pr;     // rows 64..127 -> tap j (dZ shifted by dstep rows), rows 0..63 -> tap j+1
+#pragma unroll
+          for (int k = 0; k < GT / 16; ++k) {
+            uint64_t ad = make_smem_desc(sa + k * 2048, (uint32_t)p.dstep * 128u, 1024);
+            uint64_t bd = make_smem_desc(sb + (j * p.dstep) * 128 + k * 2048, 8192, 1024);
+            umma_bf16(tm + pr * 64, ad, bd, idesc, (!first || k > 0) ? 1u : 0u);
+          }
+        }
+        first = false;
+        umma_commit(empty_bar(stage));
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull);
+    }
+  } else if (has_work) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int half = m >> 6, co_l = m & 63;
+    const int co = c0 + co_l;
+    const bool row_ok = co_l < p.OUT && co < p.C;
+    const int g_l = co_l / p.cpg;
+    mbar_wait(tfull, 0);
+    tcgen05_fence_after();
+    for (int pr = 0; pr < npairs; ++pr) {
+      float v[48];
+      const uint32_t ta = tm + ((uint32_t)(q * 32) << 16) + pr * 64;
+      tmem_ld32(ta, v);
+      tmem_ld16(ta + 32, v + 32);
+      const int tap = half ? 2 * pr : 2 * pr + 1;
+      if (row_ok && tap < p.ktaps) {
+        float* dst = p.dw + ((int64_t)co * p.cpg) * p.ktaps + tap;
+#pragma unroll
+        for (int i = 0; i < 48; ++i) {
+          const int il = i - g_l * p.cpg;
+          if (il >= 0 && il < p.cpg) atomicAdd(dst + il * p.ktaps, v[i]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tm, 256);
+  }
+}
+
+// ---------------------------------------------------------------- weight packs (fp32 master -> bf16 block diagonal)
+// out[slab][tap][n (48 rows)][kk (64 cols)], transposed=0: forward  (n = c_out, kk = c_in, tap j)
+//                                            transposed=1: dgrad    (n = c_in, kk = c_out, tap k-1-j)
+__global__ void pack_gconv_mma_kernel(const float* __restrict__ w, bf16* __restrict__ out, int C, int cpg, int ktaps, int OUT,
+                                      int nslabs, int transposed) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)nslabs * ktaps * NW * 64;
+  if (idx >= total) return;
+  int kk = (int)(idx % 64);
+  int n = (int)((idx / 64) % NW);
+  int j = (int)((idx / (64 * NW)) % ktaps);
+  int s = (int)(idx / ((int64_t)64 * NW * ktaps));
+  int c0 = s * OUT;
+  int cn = c0 + n, ck = c0 + kk;
+  float v = 0.f;
+  if (n < OUT && cn < C && ck < C && kk < NW && (cn / cpg) == (ck / cpg)) {
+    if (!transposed) v = w[((int64_t)cn * cpg + (ck % cpg)) * ktaps + j];
+    else v = w[((int64_t)ck * cpg + (cn % cpg)) * ktaps + (ktaps - 1 - j)];
+  }
+  out[idx] = __float2bfloat16(v);
+}
+
+}  // namespace
+
+int sm100_gconv_fwd(const nbasr_gconv* g, cudaStream_t st) {
+  GcFwdArgs a{};
+  a.B = g->B; a.T = g->T; a.Tp = g->Tp; a.C = g->C; a.OUT = slab_out(g->cpg);
+  a.ktaps = g->ktaps; a.dstep = g->dstep; a.off0 = g->off0;
+  NBASR_REQUIRE(a.off0 >= -NBASR_PAD_L && (a.ktaps - 1) * a.dstep <= AROWS - GT, "tap reach");
+  a.nslabs = (g->C + a.OUT - 1) / a.OUT;
+  a.tiles_per_utt = (g->T + GT - 1) / GT;
+  a.ntiles = a.tiles_per_utt * g->B;
+  int slots = 2 * nbasr_sm_count();
+  a.nlanes = std::max(1, std::min(a.ntiles, slots / a.nslabs));
+  a.epi = g->epi;
+  CUtensorMap tmX, tmW;
+  uint64_t dx[3] = {(uint64_t)g->C, (uint64_t)g->Tp, (uint64_t)g->B};
+  int64_t sx[3] = {1, g->C, (int64_t)g->Tp * g->C};
+  uint32_t bx[3] = {64, AROWS, 1};
+  if (sm100_get_map(g->x, 3, dx, sx, bx, &tmX)) return 1;
+  uint64_t dw[2] = {64, (uint64_t)a.nslabs * a.ktaps * NW};
+  int64_t sw[2] = {1, 64};
+  uint32_t bw[2] = {64, NW};
+  if (sm100_get_map(g->w, 2, dw, sw, bw, &tmW)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gconv_mma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    if (e != cudaSuccess) return nbasr_fail("gconv_mma_fwd smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  gconv_mma_fwd_kernel<<<a.nslabs * a.nlanes, GC_THREADS, FWD_SMEM, st>>>(tmX, tmW, a);
+  NBASR_CHECK_LAUNCH();
+  return 0;
+}
+
+int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C, int cpg, int ktaps, int off0, int dstep,
+                      float* dw, cudaStream_t st) {
+  GcWgArgs a{};
+  a.B = B; a.T = T; a.C = C; a.cpg = cpg; a.OUT = slab_out(cpg); a.ktaps = ktaps; a.dstep = dstep; a.off0 = off0;
+  NBASR_REQUIRE(off0 >= -NBASR_PAD_L && (ktaps - 1) * dstep <= AROWS - GT && dstep <= DZROWS - GT, "tap reach");
+  a.nslabs = (C + a.OUT - 1) / a.OUT;
+  a.nchunks = (T + dstep + GT - 1) / GT;
+  a.nunits = a.nchunks * B;
+  int slots = 2 * nbasr_sm_count();
+  a.nlanes = std::max(1, std::min(a.nunits, slots / a.nslabs));
+  a.dw = dw;
+  CUtensorMap tmDZ, tmX;
+  uint64_t dd[3] = {(uint64_t)C, (uint64_t)Tp, (uint64_t)B};
+  int64_t sd[3] = {1, C, (int64_t)Tp * C};
+  uint32_t bz[3] = {64, DZROWS, 1};
+  uint32_t bx[3] = {64, AROWS, 1};
+  if (sm100_get_map(dz, 3, dd, sd, bz, &tmDZ)) return 1;
+  if (sm100_get_map(x, 3, dd, sd, bx, &tmX)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gconv_mma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) return nbasr_fail("gconv_mma_wgrad smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  gconv_mma_wgrad_kernel<<<a.nslabs * a.nlanes, GC_THREADS, WG_SMEM, st>>>(tmDZ, tmX, a);
+  NBASR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int nbasr_pack_gconv_mma(const float* w, void* out, int C, int cpg, int ktaps, int transposed, void* stream) {
+  int OUT = slab_out(cpg);
+  int nslabs = (C + OUT - 1) / OUT;
+  int64_t total = (int64_t)nslabs * ktaps * NW * 64;
+  pack_gconv_mma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(w, (bf16*)out, C, cpg, ktaps, OUT, nslabs,
+                                                                                        transposed);
+  NBASR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int64_t nbasr_gconv_mma_pack_elems(int C, int cpg, int ktaps) {
+  int OUT = slab_out(cpg);
+  return (int64_t)((C + OUT - 1) / OUT) * ktaps * NW * 64;
+}

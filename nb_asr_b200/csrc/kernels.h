@@ -24,3 +24,13 @@ int simt_gemm_launch(const SimtGemmArgs& a, cudaStream_t st);
 // tcgen05 paths (gemm_sm100.cu)
 int sm100_gemm_tn(const nbasr_gemm* p, cudaStream_t st);
 int sm100_gemm_wgrad(const nbasr_wgrad* p, cudaStream_t st);
+
+// cached bf16 TMA descriptor (rank 2/3, 128B swizzle); strides in elements for dims 1..rank-1
+struct CUtensorMap_st;
+int sm100_get_map(const void* base, int rank, const uint64_t* dims, const int64_t* strides_el, const uint32_t* box,
+                  CUtensorMap_st* out);
+
+// tcgen05 grouped conv (gconv_sm100.cu)
+int sm100_gconv_fwd(const nbasr_gconv* p, cudaStream_t st);
+int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C, int cpg, int ktaps, int off0, int dstep,
+                      float* dw, cudaStream_t st);

@@ -175,8 +175,16 @@ class Engine:
                     elif op in CONV_EDGES:
                         k, _ = CONV_EDGES[op]
                         cpg = cout // 100
-                        bt = torch.empty(cout * cpg * k, dtype=torch.float32, device=dev)
-                        self.pack_ops.append((lib.nbasr_pack_gconv_dgrad, (self.P(pn + '.conv.weight'), bt.data_ptr(), cout, cpg, k)))
+                        if self.dt == BF16:
+                            # block-diagonal bf16 operands of the tcgen05 grouped-conv kernel (forward / input-gradient)
+                            ne = int(lib.nbasr_gconv_mma_pack_elems(cout, cpg, k))
+                            bf_, bt = (torch.empty(ne, dtype=tdt, device=dev) for _ in range(2))
+                            for buf, tr_ in ((bf_, 0), (bt, 1)):
+                                self.pack_ops.append((lib.nbasr_pack_gconv_mma, (self.P(pn + '.conv.weight'), buf.data_ptr(), cout, cpg, k, tr_)))
+                            self.wf[pn] = bf_
+                        else:
+                            bt = torch.empty(cout * cpg * k, dtype=torch.float32, device=dev)
+                            self.pack_ops.append((lib.nbasr_pack_gconv_dgrad, (self.P(pn + '.conv.weight'), bt.data_ptr(), cout, cpg, k)))
                         self.wt[pn] = bt
                 idx += 1
             self.block_cells.append(cells)
@@ -354,7 +362,11 @@ class Engine:
                             lp, _ = pad_rule(k, d, 1)
                             gc = GConv()
                             gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = dt, src.data_ptr(), B, Ti, Tp, Cc, Cc // 100
-                            gc.ktaps, gc.off0, gc.dstep, gc.w = k, -lp, d, self.P(pn + '.conv.weight')
+                            gc.ktaps, gc.off0, gc.dstep = k, -lp, d
+                            if dt == BF16:
+                                gc.w, gc.w_packed = self.wf[pn].data_ptr(), 1
+                            else:
+                                gc.w, gc.w_packed = self.P(pn + '.conv.weight'), 0
                             gc.epi = self._epi(Cc, bias=self.P(pn + '.conv.bias'), relu=1, drop_p=drop_p, salt=sl, adds=adds,
                                                out=o.data_ptr(), mask_out=mask.data_ptr(), ld_mask=mw)
                             call(fwd, lib.nbasr_gconv_fwd, C.byref(gc))
@@ -530,6 +542,7 @@ class Engine:
                         gc = GConv()
                         gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = dt, d.data_ptr(), B, Ti, Tp, Cc, Cc // 100
                         gc.ktaps, gc.off0, gc.dstep, gc.w = k, lp - (k - 1) * dd, dd, self.wt[pn].data_ptr()
+                        gc.w_packed = 1 if dt == BF16 else 0
                         gc.epi = epi
                         call(bwd, lib.nbasr_gconv_fwd, C.byref(gc))
                         pl.keep.append(gc)

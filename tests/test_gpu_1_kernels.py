@@ -81,18 +81,22 @@ def test_simt_wgrad_and_dgrad():
         assert U.relerr(U.from_padded(dx, B, T).cpu(), gx) < 1e-5
 
 
-@pytest.mark.parametrize('dt', [F32, BF16])
+@pytest.mark.parametrize('dt', [F32, BF16, 'mma'])
 @pytest.mark.parametrize('op', ['conv5', 'conv5d2', 'conv7', 'conv7d2'])
 @pytest.mark.parametrize('Cc', [600, 800, 1000, 1200])
 def test_gconv_fwd_bwd(dt, op, Cc):
+    """F32 / BF16: SIMT kernels.  'mma': bf16 tcgen05 block-diagonal kernels (the product path in bf16 mode)."""
     if dt == BF16 and Cc not in (600, 1000):
-        pytest.skip('bf16 variant sampled on two widths')
+        pytest.skip('bf16 SIMT variant sampled on two widths')
+    mma = dt == 'mma'
+    if mma:
+        dt = BF16
     torch.manual_seed(2)
     k, d = M.CONV_EDGE[op]
-    B, T, cpg = 2, 70, Cc // 100
+    B, T, cpg = (3, 300, Cc // 100) if mma else (2, 70, Cc // 100)
     rnd = (lambda t: t.bfloat16().float()) if dt == BF16 else (lambda t: t)
     x = rnd(torch.randn(B, T, Cc)).requires_grad_(True)
-    w = (torch.randn(Cc, cpg, k) * 0.3).requires_grad_(True)
+    w = rnd(torch.randn(Cc, cpg, k) * 0.3).requires_grad_(True) if mma else (torch.randn(Cc, cpg, k) * 0.3).requires_grad_(True)
     bias = torch.randn(Cc) * 0.1
     skip = rnd(torch.randn(B, T, Cc))
     lp, rp = pad_rule(k, d, 1)
@@ -107,6 +111,13 @@ def test_gconv_fwd_bwd(dt, op, Cc):
     gc = GConv()
     gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg, gc.ktaps, gc.off0, gc.dstep = dt, xb.data_ptr(), B, T, U.geo(T), Cc, cpg, k, -lp, d
     gc.w = wg.data_ptr()
+    if mma:
+        ne = int(lib.nbasr_gconv_mma_pack_elems(Cc, cpg, k))
+        wpk = torch.zeros(ne, dtype=torch.bfloat16, device=U.DEV)
+        wpk_t = torch.zeros(ne, dtype=torch.bfloat16, device=U.DEV)
+        _lib.check(lib.nbasr_pack_gconv_mma(wg.data_ptr(), wpk.data_ptr(), Cc, cpg, k, 0, U.stream()))
+        _lib.check(lib.nbasr_pack_gconv_mma(wg.data_ptr(), wpk_t.data_ptr(), Cc, cpg, k, 1, U.stream()))
+        gc.w, gc.w_packed = wpk.data_ptr(), 1
     gc.epi = U.epilogue(dt, Cc, bias=bg, relu=1, adds=[sk], out=out, mask_out=mask, ld_mask=mw)
     _lib.check(lib.nbasr_gconv_fwd(C.byref(gc), U.stream()), 'gconv')
     torch.cuda.synchronize()
@@ -127,10 +138,13 @@ def test_gconv_fwd_bwd(dt, op, Cc):
     gc2.dtype, gc2.x, gc2.B, gc2.T, gc2.Tp, gc2.C, gc2.cpg, gc2.ktaps, gc2.dstep = dt, dzb.data_ptr(), B, T, U.geo(T), Cc, cpg, k, d
     gc2.off0 = lp - (k - 1) * d
     gc2.w = wt.data_ptr()
+    if mma:
+        gc2.w, gc2.w_packed = wpk_t.data_ptr(), 1
     gc2.epi = U.epilogue(dt, Cc, out=dx)
     _lib.check(lib.nbasr_gconv_fwd(C.byref(gc2), U.stream()), 'gconv dgrad')
     torch.cuda.synchronize()
-    assert U.relerr(dw.cpu(), gw) < (1e-4 if dt == F32 else 1e-2)
+    assert U.relerr(dw.cpu(), gw) < (1e-4 if dt == F32 else (2e-5 if mma else 1e-2))      # mma: exact bf16 inputs, fp32 accumulate
+    assert float(out[:PAD_L].abs().sum()) == 0.0 and float(dx[:PAD_L].abs().sum()) == 0.0
     assert U.relerr(U.from_padded(dx, B, T).cpu(), gx) < tol
     db = torch.zeros(Cc, device=U.DEV)
     _lib.check(lib.nbasr_colsum(dt, dzb.data_ptr(), B, T, U.geo(T), Cc, db.data_ptr(), U.stream()))

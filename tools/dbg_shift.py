@@ -1,0 +1,32 @@
+"""GPU micro-experiment: row-shifted UMMA descriptors inside a 128B-swizzled tile (see csrc/dbg.cu)."""
+import ctypes as C
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from nb_asr_b200 import _lib
+lib = _lib.load()
+f = lib.nbasr_dbg_shift
+f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+f.restype = C.c_int
+torch.manual_seed(0)
+dev = 'cuda:0'
+for mode in (0, 1):
+    if mode == 0:
+        A = torch.randn(144, 64, device=dev).bfloat16()
+        B = torch.randn(64, 64, device=dev).bfloat16()
+    else:
+        A = torch.randn(64, 128, device=dev).bfloat16()     # Y[k][m]
+        B = torch.randn(80, 64, device=dev).bfloat16()      # X[k][n]
+    for bo in (0, 1):
+        res = []
+        for shift in range(0, 13):
+            D = torch.zeros(128, 64, device=dev)
+            rc = f(A.data_ptr(), B.data_ptr(), D.data_ptr(), mode, shift, bo, None)
+            torch.cuda.synchronize()
+            if mode == 0:
+                ref = A[shift:shift + 128].float() @ B.float().t()
+            else:
+                ref = A.float().t() @ B[shift:shift + 64].float()
+            err = float((D - ref).norm() / ref.norm())
+            res.append(f'{shift}:{err:.1e}')
+        print(f'mode {mode} base_offset_mode {bo}:', ' '.join(res), flush=True)

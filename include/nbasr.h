@@ -98,6 +98,7 @@ typedef struct nbasr_wgrad {
   int32_t nb, nr, M, N;
   float* dw;
   int64_t ldw;
+  float* dbias;           /* optional: dbias[m] += sum_{b,r} dY[(b,r), m] (bias gradient, fused) */
 } nbasr_wgrad;
 
 int nbasr_gemm_wgrad(const nbasr_wgrad* p, void* stream);
@@ -123,9 +124,10 @@ int nbasr_pack_gconv_dgrad(const float* w, float* wt, int C, int cpg, int ktaps,
  * nbasr_gconv_mma_pack_elems returns the number of bf16 elements of the pack. */
 int nbasr_pack_gconv_mma(const float* w, void* out, int C, int cpg, int ktaps, int transposed, void* stream);
 int64_t nbasr_gconv_mma_pack_elems(int C, int cpg, int ktaps);
-/* dw[c_out][i][j] += sum_{b,t} dz[b,t,c_out] * x[b, t+off0+j*dstep, g*cpg+i];  db[c] += sum dz */
+/* dw[c_out][i][j] += sum_{b,t} dz[b,t,c_out] * x[b, t+off0+j*dstep, g*cpg+i];  dbias[c] += sum_{b,t} dz[b,t,c]
+ * (dbias may be NULL). BF16 -> tcgen05 kernel, F32 -> SIMT. */
 int nbasr_gconv_wgrad(int dtype, const void* dz, const void* x, int B, int T, int Tp, int C, int cpg,
-                      int ktaps, int off0, int dstep, float* dw, void* stream);
+                      int ktaps, int off0, int dstep, float* dw, float* dbias, void* stream);
 
 /* Element-wise pass through the epilogue: v = src ? src[rho,n] : 0 over rows (b,t) of a padded
  * (B,Tp,C) geometry.  Used for `zero` main ops (ops.py:62-68), the LSTM input dropout

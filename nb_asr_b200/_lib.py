@@ -26,7 +26,7 @@ class Gemm(C.Structure):
 
 class Wgrad(C.Structure):
     _fields_ = [('dtype', _i32), ('dy', _vp), ('dy_bs', _i64), ('dy_rs', _i64), ('x', _vp), ('x_bs', _i64),
-                ('x_rs', _i64), ('nb', _i32), ('nr', _i32), ('M', _i32), ('N', _i32), ('dw', _vp), ('ldw', _i64)]
+                ('x_rs', _i64), ('nb', _i32), ('nr', _i32), ('M', _i32), ('N', _i32), ('dw', _vp), ('ldw', _i64), ('dbias', _vp)]
 
 
 class GConv(C.Structure):
@@ -41,7 +41,7 @@ _SIGS = {
     'nbasr_pack_gconv_dgrad': [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp],
     'nbasr_pack_gconv_mma': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     'nbasr_gconv_mma_pack_elems': [C.c_int, C.c_int, C.c_int],
-    'nbasr_gconv_wgrad': [C.c_int, _vp, _vp] + [C.c_int] * 8 + [_vp, _vp],
+    'nbasr_gconv_wgrad': [C.c_int, _vp, _vp] + [C.c_int] * 8 + [_vp, _vp, _vp],
     'nbasr_eltwise': [C.c_int, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), _vp],
     'nbasr_colsum': [C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
     'nbasr_layernorm_fwd': [C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _vp],

@@ -52,6 +52,14 @@ int nbasr_gemm_wgrad(const nbasr_wgrad* p, void* stream) {
   a.nkb = p->nb; a.nkr = p->nr; a.N = p->N;
   a.o_r0 = 0; a.o_bs = 0; a.o_rs = 1;
   a.epi.out = p->dw; a.epi.out_dtype = NBASR_F32; a.epi.ld_out = p->ldw; a.epi.accumulate = 1;
+  if (p->dbias) {   // column sums of dY over rows (b, r): geometry-free call (pointer pre-offset by the pad rows)
+    const int es = p->dtype == NBASR_BF16 ? 2 : 4;
+    NBASR_REQUIRE(p->dy_rs == p->M, "SIMT bias gradient needs a dense dY row pitch");
+    for (int b = 0; b < p->nb; ++b) {
+      const char* base = reinterpret_cast<const char*>(p->dy) + (int64_t)b * p->dy_bs * es - (int64_t)NBASR_PAD_L * p->M * es;
+      if (nbasr_colsum(p->dtype, base, 1, p->nr, p->nr, p->M, p->dbias, stream)) return 1;
+    }
+  }
   return simt_gemm_launch(a, as_stream(stream));
 }
 

@@ -100,9 +100,10 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
 // bit arrays addressed by BYTE (8 columns per byte; row pitch ld_mask is given in 32-bit words), so
 // any 8-aligned column range can be produced by one thread without touching its neighbours' bits.
 // ---------------------------------------------------------------------------------------------
-template <int NV>
-__device__ __forceinline__ void epilogue_cols(const nbasr_epilogue& e, int64_t rho, int c0, int nvalid, float* v) {
+template <int NV, bool FULL = false>
+__device__ __forceinline__ void epilogue_cols(const nbasr_epilogue& e, int64_t rho, int c0, int nvalid_, float* v) {
   constexpr int NG = NV / 8;
+  const int nvalid = FULL ? NV : nvalid_;   // FULL: every column valid -> all guards fold at compile time
   uint32_t m[NG];
 #pragma unroll
   for (int g = 0; g < NG; ++g) m[g] = 0xffu;
@@ -161,9 +162,14 @@ __device__ __forceinline__ void epilogue_cols(const nbasr_epilogue& e, int64_t r
   }
   if (e.mask_out) {
     uint8_t* mo = reinterpret_cast<uint8_t*>(e.mask_out) + rho * e.ld_mask * 4 + (c0 >> 3);
+    if (FULL && (NG % 2 == 0) && ((c0 >> 3) % 2 == 0)) {   // 2-byte aligned run of bytes -> 16-bit stores
 #pragma unroll
-    for (int g = 0; g < NG; ++g)
-      if (g * 8 < nvalid) mo[g] = static_cast<uint8_t>(m[g]);
+      for (int g = 0; g < NG; g += 2) *reinterpret_cast<uint16_t*>(mo + g) = static_cast<uint16_t>(m[g] | (m[g + 1] << 8));
+    } else {
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+        if (g * 8 < nvalid) mo[g] = static_cast<uint8_t>(m[g]);
+    }
   }
   if (e.out2) {
     const uint8_t* mi = e.mask2 ? reinterpret_cast<const uint8_t*>(e.mask2) + rho * e.ld_mask * 4 + (c0 >> 3) : nullptr;
@@ -182,7 +188,8 @@ __device__ __forceinline__ void epilogue_cols(const nbasr_epilogue& e, int64_t r
 
 // one (row, aligned 32-column chunk); ncol = number of valid columns of the tensor
 __device__ __forceinline__ void epilogue_chunk(const nbasr_epilogue& e, int64_t rho, int c0, int ncol, float* v) {
-  epilogue_cols<32>(e, rho, c0, min(32, ncol - c0), v);
+  if (ncol - c0 >= 32) epilogue_cols<32, true>(e, rho, c0, 32, v);
+  else epilogue_cols<32, false>(e, rho, c0, ncol - c0, v);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

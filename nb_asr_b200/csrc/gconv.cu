@@ -254,12 +254,13 @@ int nbasr_pack_gconv_dgrad(const float* w, float* wt, int C, int cpg, int ktaps,
 }
 
 int nbasr_gconv_wgrad(int dtype, const void* dz, const void* x, int B, int T, int Tp, int C, int cpg, int ktaps,
-                      int off0, int dstep, float* dw, void* stream) {
+                      int off0, int dstep, float* dw, float* dbias, void* stream) {
   NBASR_REQUIRE(cpg == 6 || cpg == 8 || cpg == 10 || cpg == 12, "cpg");
   NBASR_REQUIRE(ktaps <= 7 && (dstep == 1 || dstep == 2), "taps");
   if (B <= 0 || T <= 0) return 0;
   if (dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT"))
-    return sm100_gconv_wgrad(dz, x, B, T, Tp, C, cpg, ktaps, off0, dstep, dw, as_stream(stream));
+    return sm100_gconv_wgrad(dz, x, B, T, Tp, C, cpg, ktaps, off0, dstep, dw, dbias, as_stream(stream));
+  if (dbias && nbasr_colsum(dtype, dz, B, T, Tp, C, dbias, stream)) return 1;
   int CS = slab_channels(cpg);
   dim3 grid((C + CS - 1) / CS, B);
   size_t sm = wgrad_smem(cpg);

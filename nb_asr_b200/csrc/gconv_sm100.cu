@@ -136,6 +136,12 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   } else {
     const int q = warp & 3;
     const int nvalid = min(p.C, c0 + p.OUT) - c0;
+    // the slab is fixed for the CTA's lifetime: keep its bias in registers, hand the epilogue a bias-free copy
+    float bias_r[48];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) bias_r[i] = (p.epi.bias && i < nvalid) ? __ldg(p.epi.bias + c0 + i) : 0.f;
+    nbasr_epilogue epi = p.epi;
+    epi.bias = nullptr;
     int it = 0;
     for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes, ++it) {
       const int as = it % NACC;
@@ -152,7 +158,10 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       mbar_arrive(tempty_bar(as));       // accumulator is in registers: release the TMEM stage early
       if (t < p.T) {
         const int64_t rho = (int64_t)b * p.Tp + NBASR_PAD_L + t;
-        epilogue_cols<48>(p.epi, rho, c0, nvalid, v);
+#pragma unroll
+        for (int i = 0; i < 48; ++i) v[i] += bias_r[i];
+        if (nvalid == 48) epilogue_cols<48, true>(epi, rho, c0, 48, v);
+        else epilogue_cols<48, false>(epi, rho, c0, nvalid, v);
       }
     }
   }
@@ -174,6 +183,7 @@ struct GcWgArgs {
   int B, T, C, cpg, OUT, ktaps, dstep, off0;
   int nslabs, nchunks, nunits, nlanes;
   float* dw;
+  float* dbias;   // optional: db[c] += sum_t dZ[t][c], computed by the tensor core against a column of ones
 };
 
 __global__ void __launch_bounds__(GC_THREADS, 2)
@@ -221,30 +231,44 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    if (has_work) {
       const uint32_t idesc = make_idesc(128, NW, 1, 1);
+      const uint32_t idesc_b = make_idesc(128, 64, 1, 1);   // pair 0 also multiplies the ones column (N = 64)
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
       for (int u = lane_id; u < p.nunits; u += p.nlanes) {
         mbar_wait(full_bar(stage), phase);
-        tcgen05_fence_after();
         const uint32_t sa = base + stage * WG_STAGE;
         const uint32_t sb = sa + DZ_BYTES;
-        for (int pr = 0; pr < npairs; ++pr) {
-          const int j = 2 * pr;     // rows 64..127 -> tap j (dZ shifted by dstep rows), rows 0..63 -> tap j+1
-#pragma unroll
-          for (int k = 0; k < GT / 16; ++k) {
-            uint64_t ad = make_smem_desc(sa + k * 2048, (uint32_t)p.dstep * 128u, 1024);
-            uint64_t bd = make_smem_desc(sb + (j * p.dstep) * 128 + k * 2048, 8192, 1024);
-            umma_bf16(tm + pr * 64, ad, bd, idesc, (!first || k > 0) ? 1u : 0u);
-          }
+        if (p.dbias) {
+          // channel 48 of the X window (unused by the N = 48 MMAs) <- 1.0 for every frame row: element 0 of the
+          // 16-byte chunk 6, at its 128B-swizzled position (chunk ^ (row & 7)).
+          uint8_t* xb = al + stage * WG_STAGE + DZ_BYTES;
+          for (int r = lane; r < AROWS; r += 32)
+            *reinterpret_cast<uint16_t*>(xb + r * 128 + ((6 ^ (r & 7)) << 4)) = 0x3F80;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
         }
+        tcgen05_fence_after();
+        if (lane == 0) {
+          for (int pr = 0; pr < npairs; ++pr) {
+            const int j = 2 * pr;     // rows 64..127 -> tap j (dZ shifted by dstep rows), rows 0..63 -> tap j+1
+            const uint32_t id = (pr == 0 && p.dbias) ? idesc_b : idesc;
+#pragma unroll
+            for (int k = 0; k < GT / 16; ++k) {
+              uint64_t ad = make_smem_desc(sa + k * 2048, (uint32_t)p.dstep * 128u, 1024);
+              uint64_t bd = make_smem_desc(sb + (j * p.dstep) * 128 + k * 2048, 8192, 1024);
+              umma_bf16(tm + pr * 64, ad, bd, id, (!first || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar(stage));
+        }
+        __syncwarp();
         first = false;
-        umma_commit(empty_bar(stage));
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull);
+      if (lane == 0) umma_commit(tfull);
     }
   } else if (has_work) {
     const int q = warp & 3;
@@ -261,6 +285,11 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
       tmem_ld32(ta, v);
       tmem_ld16(ta + 32, v + 32);
       const int tap = half ? 2 * pr : 2 * pr + 1;
+      if (pr == 0 && p.dbias) {      // column 48 of pair 0, rows 64..127 (tap 0, unshifted dZ): sum_t dZ[t][co]
+        float one[16];
+        tmem_ld16(ta + 48, one);
+        if (row_ok && half) atomicAdd(p.dbias + co, one[0]);
+      }
       if (row_ok && tap < p.ktaps) {
         float* dst = p.dw + ((int64_t)co * p.cpg) * p.ktaps + tap;
 #pragma unroll
@@ -335,7 +364,7 @@ int sm100_gconv_fwd(const nbasr_gconv* g, cudaStream_t st) {
 }
 
 int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C, int cpg, int ktaps, int off0, int dstep,
-                      float* dw, cudaStream_t st) {
+                      float* dw, float* dbias, cudaStream_t st) {
   GcWgArgs a{};
   a.B = B; a.T = T; a.C = C; a.cpg = cpg; a.OUT = slab_out(cpg); a.ktaps = ktaps; a.dstep = dstep; a.off0 = off0;
   NBASR_REQUIRE(off0 >= -NBASR_PAD_L && (ktaps - 1) * dstep <= AROWS - GT && dstep <= DZROWS - GT, "tap reach");
@@ -345,6 +374,7 @@ int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C
   int slots = 2 * nbasr_sm_count();
   a.nlanes = std::max(1, std::min(a.nunits, slots / a.nslabs));
   a.dw = dw;
+  a.dbias = dbias;
   CUtensorMap tmDZ, tmX;
   uint64_t dd[3] = {(uint64_t)C, (uint64_t)Tp, (uint64_t)B};
   int64_t sd[3] = {1, C, (int64_t)Tp * C};

@@ -164,18 +164,35 @@ struct WgArgs {
   int m_tiles, n_tiles, chunks_per_utt, total_units, units_per_split;
   float* dw;
   int64_t ldw;
+  float* dbias;   // optional bias gradient: column sums of dY via one extra N=16 MMA against a tile of ones
 };
+
+constexpr int WG_ONES_BYTES = 8192;   // 64 K-rows x 128 B, every element 1.0 (swizzle invariant)
+constexpr int WG_SMEM_BYTES = STAGES * STAGE_BYTES + WG_ONES_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void tmem_ld16_(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t ones_sm = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = ones_sm + WG_ONES_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + STAGES * STAGE_BYTES + WG_ONES_BYTES + 8 * (2 * STAGES + 4));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
@@ -183,6 +200,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   const int u_begin = blockIdx.y * p.units_per_split;
   const int u_end = min(p.total_units, u_begin + p.units_per_split);
   const int nbox_b = (p.BN + 63) / 64;
+  const bool do_bias = p.dbias != nullptr && n0 == 0;
+  if (do_bias) {
+    uint32_t* o = reinterpret_cast<uint32_t*>(smem_al + STAGES * STAGE_BYTES);
+    for (int i = threadIdx.x; i < WG_ONES_BYTES / 4; i += blockDim.x) o[i] = 0x3F803F80u;   // bf16 (1.0, 1.0)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmDY);
@@ -194,14 +217,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), 256);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (u_begin >= u_end) {  // nothing to do for this split (uniform per CTA)
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 256);
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
     return;
   }
 
@@ -238,6 +261,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           uint64_t ad = make_smem_desc(sa + k * 2048, 8192, 1024);
           uint64_t bd = make_smem_desc(sb + k * 2048, 8192, 1024);
           umma_bf16(tmem_base, ad, bd, idesc, (u > u_begin || k > 0) ? 1u : 0u);
+          if (do_bias)
+            umma_bf16(tmem_base + 256, ad, make_smem_desc(ones_sm + k * 2048, 8192, 1024), make_idesc(BM, 16, 1, 1),
+                      (u > u_begin || k > 0) ? 1u : 0u);
         }
         umma_commit(empty_bar(stage));
         if (u == u_end - 1) umma_commit(tfull_bar);
@@ -250,6 +276,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     mbar_wait(tfull_bar, 0);
     tcgen05_fence_after();
     const int ncol = min(p.N, n0 + p.BN);
+    if (do_bias) {
+      float one[16];
+      tmem_ld16_(tmem_base + ((uint32_t)(q * 32) << 16) + 256, one);
+      if (m < p.M) atomicAdd(p.dbias + m, one[0]);
+    }
     for (int c = 0; c < p.BN; c += 32) {
       if (n0 + c >= ncol) break;
       float v[32];
@@ -270,7 +301,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -398,7 +429,7 @@ int sm100_gemm_wgrad(const nbasr_wgrad* g, cudaStream_t st) {
   int splits = std::max(1, std::min(a.total_units, (2 * sms + tiles - 1) / tiles));
   a.units_per_split = (a.total_units + splits - 1) / splits;
   splits = (a.total_units + a.units_per_split - 1) / a.units_per_split;
-  a.dw = g->dw; a.ldw = g->ldw;
+  a.dw = g->dw; a.ldw = g->ldw; a.dbias = g->dbias;
   CUtensorMap tmDY, tmX;
   uint64_t dd[3] = {(uint64_t)g->M, (uint64_t)g->nr, (uint64_t)g->nb};
   int64_t sd[3] = {1, g->dy_rs, g->dy_bs};
@@ -409,11 +440,11 @@ int sm100_gemm_wgrad(const nbasr_wgrad* g, cudaStream_t st) {
   if (sm100_get_map(g->x, 3, dx, sx, bx, &tmX)) return 1;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
     if (e != cudaSuccess) return nbasr_fail("gemm_wgrad smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  gemm_wgrad_kernel<<<dim3(tiles, splits), NUM_THREADS, SMEM_BYTES, st>>>(tmDY, tmX, a);
+  gemm_wgrad_kernel<<<dim3(tiles, splits), NUM_THREADS, WG_SMEM_BYTES, st>>>(tmDY, tmX, a);
   NBASR_CHECK_LAUNCH();
   return 0;
 }

@@ -33,4 +33,4 @@ int sm100_get_map(const void* base, int rank, const uint64_t* dims, const int64_
 // tcgen05 grouped conv (gconv_sm100.cu)
 int sm100_gconv_fwd(const nbasr_gconv* p, cudaStream_t st);
 int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C, int cpg, int ktaps, int off0, int dstep,
-                      float* dw, cudaStream_t st);
+                      float* dw, float* dbias, cudaStream_t st);

@@ -57,43 +57,49 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(int h_dtype, const void* 
   }
 }
 
-// head backward (input + bias gradient): warp per row
-__global__ void __launch_bounds__(256) head_bwd_kernel(int B, int T, int K, int V, const float* __restrict__ w,
+// head backward, fused: dh = dl W, db += sum dl, dW += dl^T h.  One block walks rows; the 8 warps split the
+// classes (dW rows live in shared memory, warp-private -> no atomics) and the hidden range (dh).
+__global__ void __launch_bounds__(256) head_bwd_kernel(int h_dtype, const void* __restrict__ h, int64_t h_bs, int64_t h_rs,
+                                                       int B, int T, int K, int V, const float* __restrict__ w,
                                                        const float* __restrict__ dl, float* __restrict__ dh,
-                                                       int64_t dh_bs, int64_t dh_rs, float* __restrict__ db) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int nk = (K + 31) / 32;
-  float db0 = 0.f, db1 = 0.f;
-  for (int64_t r = warp; r < (int64_t)B * T; r += nwarps) {
+                                                       int64_t dh_bs, int64_t dh_rs, float* __restrict__ dw,
+                                                       float* __restrict__ db) {
+  extern __shared__ float sm[];
+  float* sdw = sm;                 // V x K (only if dw)
+  float* hrow = sm + (dw ? V * K : 0);   // K
+  float* drow = hrow + K;          // V (padded to 64)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (dw) for (int i = tid; i < V * K; i += blockDim.x) sdw[i] = 0.f;
+  float dbacc = 0.f;               // thread v < V accumulates db[v]
+  __syncthreads();
+  for (int64_t r = blockIdx.x; r < (int64_t)B * T; r += gridDim.x) {
     int b = (int)(r / T), t = (int)(r % T);
-    float d0 = lane < V ? dl[r * V + lane] : 0.f;
-    float d1 = lane + 32 < V ? dl[r * V + lane + 32] : 0.f;
-    db0 += d0; db1 += d1;
-    float acc[HEAD_MAXK32];
-#pragma unroll
-    for (int q = 0; q < HEAD_MAXK32; ++q) acc[q] = 0.f;
-    for (int v = 0; v < V; ++v) {
-      float d = __shfl_sync(0xffffffffu, v < 32 ? d0 : d1, v & 31);
-      const float* wr = w + (int64_t)v * K;
-#pragma unroll
-      for (int q = 0; q < HEAD_MAXK32; ++q) {
-        int k = lane + 32 * q;
-        if (q < nk && k < K) acc[q] = fmaf(d, __ldg(wr + k), acc[q]);
+    int64_t base = (int64_t)b * h_bs + (int64_t)t * h_rs;
+    for (int k = tid; k < K; k += blockDim.x) hrow[k] = ld_dt(h, h_dtype, base + k);
+    if (tid < V) {
+      float d = dl[r * V + tid];
+      drow[tid] = d;
+      dbacc += d;
+    }
+    __syncthreads();
+    // dh[k] = sum_v d_v W[v][k]
+    float* o = dh + (int64_t)b * dh_bs + (int64_t)t * dh_rs;
+    for (int k = tid; k < K; k += blockDim.x) {
+      float acc = 0.f;
+      for (int v = 0; v < V; ++v) acc = fmaf(drow[v], __ldg(w + (int64_t)v * K + k), acc);
+      o[k] = acc;
+    }
+    if (dw) {
+      for (int v = warp; v < V; v += 8) {
+        float d = drow[v];
+        float* row = sdw + v * K;
+        for (int k = lane; k < K; k += 32) row[k] = fmaf(d, hrow[k], row[k]);
       }
     }
-    float* o = dh + (int64_t)b * dh_bs + (int64_t)t * dh_rs;
-#pragma unroll
-    for (int q = 0; q < HEAD_MAXK32; ++q) {
-      int k = lane + 32 * q;
-      if (q < nk && k < K) o[k] = acc[q];
-    }
+    __syncthreads();
   }
-  if (db) {
-    if (lane < V) atomicAdd(db + lane, db0);
-    if (lane + 32 < V) atomicAdd(db + lane + 32, db1);
-  }
+  if (db && tid < V) atomicAdd(db + tid, dbacc);
+  if (dw) for (int i = tid; i < V * K; i += blockDim.x) atomicAdd(dw + i, sdw[i]);
 }
 
 // ---------------------------------------------------------------- CTC
@@ -328,10 +334,15 @@ int nbasr_head_bwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B
   NBASR_REQUIRE(V <= 64 && K <= 32 * HEAD_MAXK32, "head shape");
   int64_t rows = (int64_t)B * T;
   if (rows == 0) return 0;
-  int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 4);
-  head_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(B, T, K, V, w, dlogits, dh, dh_bs, dh_rs, db);
+  const bool fuse_dw = dw && (size_t)(V * K + K + 64) * sizeof(float) <= 200 * 1024;
+  size_t sm = sizeof(float) * ((fuse_dw ? (size_t)V * K : 0) + K + 64);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  int blocks = (int)std::min<int64_t>(rows, nbasr_sm_count());
+  head_bwd_kernel<<<blocks, 256, sm, as_stream(stream)>>>(h_dtype, h, h_bs, h_rs, B, T, K, V, w, dlogits, dh, dh_bs, dh_rs,
+                                                          fuse_dw ? dw : nullptr, db);
   NBASR_CHECK_LAUNCH();
-  if (dw) {
+  if (dw && !fuse_dw) {
     // dW[v, k] += sum_{b,t} dl[b,t,v] * h[b,t,k]
     SimtGemmArgs a{};
     a.a = dlogits; a.a_dtype = NBASR_F32; a.a_ib = 0; a.a_ir = 1; a.a_kb = (int64_t)T * V; a.a_kr = V;

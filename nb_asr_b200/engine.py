@@ -288,8 +288,9 @@ class Engine:
             call(lst, lib.nbasr_gemm_tn, C.byref(g))
             pl.keep.append(g)
 
-        def wgrad(lst, dy_ptr, dy_bs, dy_rs, x_ptr, x_bs, x_rs, nb, nr, M, N, dw_ptr, ldw, dtype=None):
+        def wgrad(lst, dy_ptr, dy_bs, dy_rs, x_ptr, x_bs, x_rs, nb, nr, M, N, dw_ptr, ldw, dtype=None, dbias=None):
             w = Wgrad()
+            w.dbias = dbias
             w.dtype = dt if dtype is None else dtype
             w.dy, w.dy_bs, w.dy_rs, w.x, w.x_bs, w.x_rs = dy_ptr, dy_bs, dy_rs, x_ptr, x_bs, x_rs
             w.nb, w.nr, w.M, w.N, w.dw, w.ldw = nb, nr, M, N, dw_ptr, ldw
@@ -529,16 +530,17 @@ class Engine:
                         pl.keep.append(epi)
                     elif op == 'linear':
                         d = dzb[j]
+                        fuse = dt == BF16       # bias gradient rides on the tensor-core wgrad (ones operand)
                         wgrad(bwd, _ptr(d, PAD_L * Cc), Tp * Cc, Cc, _ptr(src, PAD_L * Cc), Tp * Cc, Cc, B, Ti, Cc, Cc,
-                              self.G(pn + '.linear.weight'), Cc)
-                        call(bwd, lib.nbasr_colsum, dt, d.data_ptr(), B, Ti, Tp, Cc, self.G(pn + '.linear.bias'))
+                              self.G(pn + '.linear.weight'), Cc, dbias=self.G(pn + '.linear.bias') if fuse else None)
+                        if not fuse:
+                            call(bwd, lib.nbasr_colsum, dt, d.data_ptr(), B, Ti, Tp, Cc, self.G(pn + '.linear.bias'))
                         gemm(bwd, _ptr(d, PAD_L * Cc), Tp * Cc, Cc, B, Ti, Cc, Cc, self.wt[pn].data_ptr(), Cc, PAD_L, Tp, 1, epi)
                     else:
                         d = dzb[j]
                         k, dd, lp = nrec['k'], nrec['d'], nrec['lp']
                         call(bwd, lib.nbasr_gconv_wgrad, dt, d.data_ptr(), src.data_ptr(), B, Ti, Tp, Cc, Cc // 100, k, -lp, dd,
-                             self.G(pn + '.conv.weight'))
-                        call(bwd, lib.nbasr_colsum, dt, d.data_ptr(), B, Ti, Tp, Cc, self.G(pn + '.conv.bias'))
+                             self.G(pn + '.conv.weight'), self.G(pn + '.conv.bias'))
                         gc = GConv()
                         gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = dt, d.data_ptr(), B, Ti, Tp, Cc, Cc // 100
                         gc.ktaps, gc.off0, gc.dstep, gc.w = k, lp - (k - 1) * dd, dd, self.wt[pn].data_ptr()
@@ -557,9 +559,11 @@ class Engine:
                  1.0, mw, self.G(lname + '.weight'), self.G(lname + '.bias'))
             pool.append(gout)
             pgeo, s = rec['pg'], rec['s']
+            fuse = dt == BF16
             wgrad(bwd, _ptr(dzc, PAD_L * Cc), Tp * Cc, Cc, rec['a_ptr'], pgeo.Tp * pgeo.C, s * pgeo.C, B, Ti, Cc, rec['K'],
-                  self.G(cname + '.weight'), rec['K'])
-            call(bwd, lib.nbasr_colsum, dt, dzc.data_ptr(), B, Ti, Tp, Cc, self.G(cname + '.bias'))
+                  self.G(cname + '.weight'), rec['K'], dbias=self.G(cname + '.bias') if fuse else None)
+            if not fuse:
+                call(bwd, lib.nbasr_colsum, dt, dzc.data_ptr(), B, Ti, Tp, Cc, self.G(cname + '.bias'))
             if i > 0:
                 gout = pools[i - 1].pop()
                 Cin, Tin = pgeo.C, pgeo.T
@@ -584,7 +588,7 @@ class Engine:
             rc = fn(*args, st)
             if rc != 0:
                 raise _lib.NbasrError(f'{fn.__name__}: {self.lib.nbasr_last_error().decode()}')
-            n += 2 if fn.__name__ == 'nbasr_head_bwd' else 1
+            n += 1
         self.launches += n     # kernels launched (every C-ABI call launches >= 1 kernel of libnbasr)
 
     def forward(self, audio, training=None):

@@ -73,11 +73,12 @@ def run_gemm(dt, a_ptr, a_bs, a_rs, nb, nr, K, N, w, ldw, o_r0, o_bs, o_rs, epi)
     torch.cuda.synchronize()
 
 
-def run_wgrad(dt, dy_ptr, dy_bs, dy_rs, x_ptr, x_bs, x_rs, nb, nr, M, N, dw, ldw):
+def run_wgrad(dt, dy_ptr, dy_bs, dy_rs, x_ptr, x_bs, x_rs, nb, nr, M, N, dw, ldw, dbias=None):
     lib = _lib.load()
     w = Wgrad()
     w.dtype, w.dy, w.dy_bs, w.dy_rs, w.x, w.x_bs, w.x_rs = dt, dy_ptr, dy_bs, dy_rs, x_ptr, x_bs, x_rs
     w.nb, w.nr, w.M, w.N, w.dw, w.ldw = nb, nr, M, N, dw.data_ptr(), ldw
+    w.dbias = dbias.data_ptr() if dbias is not None else None
     _lib.check(lib.nbasr_gemm_wgrad(C.byref(w), stream()), 'gemm_wgrad')
     torch.cuda.synchronize()
 

@@ -130,7 +130,9 @@ def test_gconv_fwd_bwd(dt, op, Cc):
     gx, gw = torch.autograd.grad(z, (x, w), dz)
     dzb = U.to_padded(dz, dt)
     dw = torch.zeros(Cc, cpg, k, device=U.DEV)
-    _lib.check(lib.nbasr_gconv_wgrad(dt, dzb.data_ptr(), xb.data_ptr(), B, T, U.geo(T), Cc, cpg, k, -lp, d, dw.data_ptr(), U.stream()))
+    dbf = torch.zeros(Cc, device=U.DEV)
+    _lib.check(lib.nbasr_gconv_wgrad(dt, dzb.data_ptr(), xb.data_ptr(), B, T, U.geo(T), Cc, cpg, k, -lp, d, dw.data_ptr(),
+                                     dbf.data_ptr(), U.stream()))
     wt = torch.empty_like(wg)
     _lib.check(lib.nbasr_pack_gconv_dgrad(wg.data_ptr(), wt.data_ptr(), Cc, cpg, k, U.stream()))
     dx = U.empty_padded(B, T, Cc, dt)
@@ -149,6 +151,7 @@ def test_gconv_fwd_bwd(dt, op, Cc):
     db = torch.zeros(Cc, device=U.DEV)
     _lib.check(lib.nbasr_colsum(dt, dzb.data_ptr(), B, T, U.geo(T), Cc, db.data_ptr(), U.stream()))
     assert U.relerr(db.cpu(), dz.sum((0, 1))) < 1e-4
+    assert U.relerr(dbf.cpu(), dz.sum((0, 1))) < 1e-4       # bias gradient fused into the weight-gradient kernel
 
 
 @pytest.mark.parametrize('dt', [F32, BF16])

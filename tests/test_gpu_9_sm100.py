@@ -69,9 +69,11 @@ def test_gemm_wgrad(nb, nr, M_, N, ldx):
     ref = torch.einsum('brm,brn->mn', dy, x[:, :, :N])
     dyb, xb = U.to_padded(dy, BF16), U.to_padded(x, BF16)
     dw = torch.zeros(M_, N, device=U.DEV)
+    db = torch.zeros(M_, device=U.DEV)
     args = (BF16, U.ptr(dyb, PAD_L * M_), U.geo(nr) * M_, M_, U.ptr(xb, PAD_L * ldx), U.geo(nr) * ldx, ldx, nb, nr, M_, N, dw, N)
-    U.run_wgrad(*args)
+    U.run_wgrad(*args, dbias=db)
     assert U.relerr(dw.cpu(), ref) < 1e-5, U.relerr(dw.cpu(), ref)
+    assert U.relerr(db.cpu(), dy.sum((0, 1))) < 1e-5       # fused bias gradient (ones operand)
     U.run_wgrad(*args)                                      # accumulates (+=)
     assert U.relerr(dw.cpu(), 2 * ref) < 1e-5
 

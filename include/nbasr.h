@@ -42,8 +42,11 @@ extern "C" {
  *   v += add[0][rho,n] + add[1][rho,n] + ...       (model.py:16-22 skip-connection sum)
  *   out[rho,n] = v ; mask_out bit(rho,n) = m
  *   out2[rho,n] = bit(mask2,rho,n) ? v*scale2 : 0  (backward: gradient through ReLU20/Dropout)
- * All row-indexed tensors share the row mapping of the call; ld_* are row pitches in elements
- * (mask pitches in 32-bit words).  Columns are processed in aligned chunks of 32; N % 8 == 0. */
+ * All row-indexed tensors share the row mapping of the call; ld_out is the row pitch in elements.
+ * Gate-bit masks are PLANE-major bit arrays: columns are cut into planes of `w` columns (w = 32 -> 4-byte
+ * entries, w = 40/48 -> 8-byte entries; the producer kernel's natural slab width), plane p holds one entry per
+ * row: byte address of (row, col) = ((col / w) * mask_rows + row) * entry_bytes + (col % w) / 8, bit col % 8.
+ * Consecutive rows are contiguous, so every producer/consumer reads and writes masks coalesced. */
 typedef struct nbasr_epilogue {
   const float* bias;
   int32_t relu20;
@@ -61,7 +64,9 @@ typedef struct nbasr_epilogue {
   int32_t out2_dtype;
   const uint32_t* mask2;
   float scale2;
-  int64_t ld_mask;
+  int64_t mask_rows;    /* rows per mask plane (same for mask_out and mask2) */
+  int32_t mask_w;       /* plane width of mask_out: 32, 40 or 48 */
+  int32_t mask2_w;      /* plane width of mask2 */
   int32_t accumulate;   /* out += v instead of out = v (fp32 out only, SIMT path) */
 } nbasr_epilogue;
 
@@ -146,7 +151,7 @@ int nbasr_layernorm_fwd(int dtype, const void* x, void* y, int B, int T, int Tp,
 /* dx (+ optional dx2 = dx * bit(mask2) * scale2), dgamma += , dbeta += */
 int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* mean, const float* rstd,
                         const float* gamma, int B, int T, int Tp, int C, void* dx, void* dx2,
-                        const uint32_t* mask2, float scale2, int64_t ld_mask, float* dgamma,
+                        const uint32_t* mask2, float scale2, int64_t mask_rows, int mask2_w, float* dgamma,
                         float* dbeta, void* stream);
 
 /* (B, F, T) fp32 channel-first input (trainer.py:210) -> padded channels-last (B, Tp, F). */

@@ -15,7 +15,7 @@ class Epilogue(C.Structure):
     _fields_ = [('bias', _vp), ('relu20', _i32), ('drop_p', _f32), ('drop_seed', _u64), ('drop_step', _vp),
                 ('n_add', _i32), ('add', _vp * MAX_ADD), ('add_dtype', _i32), ('out', _vp), ('out_dtype', _i32),
                 ('ld_out', _i64), ('mask_out', _vp), ('out2', _vp), ('out2_dtype', _i32), ('mask2', _vp),
-                ('scale2', _f32), ('ld_mask', _i64), ('accumulate', _i32)]
+                ('scale2', _f32), ('mask_rows', _i64), ('mask_w', _i32), ('mask2_w', _i32), ('accumulate', _i32)]
 
 
 class Gemm(C.Structure):
@@ -46,7 +46,7 @@ _SIGS = {
     'nbasr_colsum': [C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
     'nbasr_layernorm_fwd': [C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _vp],
     'nbasr_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
-                            _f32, _i64, _vp, _vp, _vp],
+                            _f32, _i64, C.c_int, _vp, _vp, _vp],
     'nbasr_transpose_in': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     'nbasr_pack_weight': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64, _i64, _i64, _vp],
     'nbasr_convert': [_vp, _vp, C.c_int, _i64, _vp],

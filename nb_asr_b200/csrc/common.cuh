@@ -85,6 +85,13 @@ __device__ __forceinline__ float ld_dt(const void* base, int dtype, int64_t idx)
                              : reinterpret_cast<const float*>(base)[idx];
 }
 
+// plane-major gate-bit masks (see nbasr.h): byte address of (row, column group starting at col, col % 8 == 0)
+__device__ __forceinline__ int64_t mask_byte_addr(int64_t rho, int col, int w, int64_t rows) {
+  const int plane = col / w;
+  const int eb = (w == 32) ? 4 : 8;
+  return ((int64_t)plane * rows + rho) * eb + ((col - plane * w) >> 3);
+}
+
 // Counter-based RNG for dropout: one 32-bit hash per element (seed, element index).
 __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
   uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
@@ -96,15 +103,14 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
 
 // ---------------------------------------------------------------------------------------------
 // Fused output stage on one row and NV (multiple of 8) consecutive columns starting at c0 (multiple
-// of 8).  v[NV] holds the accumulator values; nvalid = number of valid columns (<= NV).  Masks are
-// bit arrays addressed by BYTE (8 columns per byte; row pitch ld_mask is given in 32-bit words), so
-// any 8-aligned column range can be produced by one thread without touching its neighbours' bits.
+// of 8).  v[NV] holds the accumulator values; nvalid = number of valid columns (<= NV).  Gate-bit masks
+// are plane-major bit arrays (mask_byte_addr): any 8-aligned column range is whole bytes of one entry.
 // ---------------------------------------------------------------------------------------------
+// compute half: bias, ReLU20 (+ gate bits), dropout, skip-sum.  m[g] = gate bits of column group g.
 template <int NV, bool FULL = false>
-__device__ __forceinline__ void epilogue_cols(const nbasr_epilogue& e, int64_t rho, int c0, int nvalid_, float* v) {
+__device__ __forceinline__ void epilogue_compute(const nbasr_epilogue& e, int64_t rho, int c0, int nvalid_, float* v, uint32_t* m) {
   constexpr int NG = NV / 8;
   const int nvalid = FULL ? NV : nvalid_;   // FULL: every column valid -> all guards fold at compile time
-  uint32_t m[NG];
 #pragma unroll
   for (int g = 0; g < NG; ++g) m[g] = 0xffu;
   if (e.bias) {
@@ -148,6 +154,13 @@ __device__ __forceinline__ void epilogue_cols(const nbasr_epilogue& e, int64_t r
       }
     }
   }
+}
+
+// store half: out, gate-bit bytes, out2 = v * bit(mask2) * scale2 (per-thread global accesses)
+template <int NV, bool FULL = false>
+__device__ __forceinline__ void epilogue_store(const nbasr_epilogue& e, int64_t rho, int c0, int nvalid_, float* v, const uint32_t* m) {
+  constexpr int NG = NV / 8;
+  const int nvalid = FULL ? NV : nvalid_;
   if (e.out) {
     if (e.accumulate) {
       float* o = reinterpret_cast<float*>(e.out) + rho * e.ld_out + c0;
@@ -161,22 +174,24 @@ __device__ __forceinline__ void epilogue_cols(const nbasr_epilogue& e, int64_t r
     }
   }
   if (e.mask_out) {
-    uint8_t* mo = reinterpret_cast<uint8_t*>(e.mask_out) + rho * e.ld_mask * 4 + (c0 >> 3);
-    if (FULL && (NG % 2 == 0) && ((c0 >> 3) % 2 == 0)) {   // 2-byte aligned run of bytes -> 16-bit stores
+    uint8_t* mo = reinterpret_cast<uint8_t*>(e.mask_out);
+    if (NV == 32 && e.mask_w == 32 && (c0 & 31) == 0) {   // one aligned 32-bit entry per (row, plane): coalesced across rows
+      uint32_t word = 0;
 #pragma unroll
-      for (int g = 0; g < NG; g += 2) *reinterpret_cast<uint16_t*>(mo + g) = static_cast<uint16_t>(m[g] | (m[g + 1] << 8));
+      for (int g = 0; g < NG; ++g) word |= (g * 8 < nvalid ? m[g] : 0u) << (8 * g);
+      *reinterpret_cast<uint32_t*>(mo + mask_byte_addr(rho, c0, 32, e.mask_rows)) = word;
     } else {
 #pragma unroll
       for (int g = 0; g < NG; ++g)
-        if (g * 8 < nvalid) mo[g] = static_cast<uint8_t>(m[g]);
+        if (g * 8 < nvalid) mo[mask_byte_addr(rho, c0 + g * 8, e.mask_w, e.mask_rows)] = static_cast<uint8_t>(m[g]);
     }
   }
   if (e.out2) {
-    const uint8_t* mi = e.mask2 ? reinterpret_cast<const uint8_t*>(e.mask2) + rho * e.ld_mask * 4 + (c0 >> 3) : nullptr;
+    const uint8_t* mi = reinterpret_cast<const uint8_t*>(e.mask2);
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       if (g * 8 < nvalid) {
-        uint32_t w = mi ? mi[g] : 0xffu;
+        uint32_t w = mi ? mi[mask_byte_addr(rho, c0 + g * 8, e.mask2_w, e.mask_rows)] : 0xffu;
         float t[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) t[i] = ((w >> i) & 1u) ? v[g * 8 + i] * e.scale2 : 0.f;
@@ -184,6 +199,13 @@ __device__ __forceinline__ void epilogue_cols(const nbasr_epilogue& e, int64_t r
       }
     }
   }
+}
+
+template <int NV, bool FULL = false>
+__device__ __forceinline__ void epilogue_cols(const nbasr_epilogue& e, int64_t rho, int c0, int nvalid, float* v) {
+  uint32_t m[NV / 8];
+  epilogue_compute<NV, FULL>(e, rho, c0, nvalid, v, m);
+  epilogue_store<NV, FULL>(e, rho, c0, nvalid, v, m);
 }
 
 // one (row, aligned 32-column chunk); ncol = number of valid columns of the tensor

@@ -73,7 +73,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
     const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean_i,
     const float* __restrict__ rstd_i, const float* __restrict__ gamma, int B, int Tt, int Tp, int C,
-    T* __restrict__ dx, T* __restrict__ dx2, const uint32_t* __restrict__ mask2, float scale2, int64_t ld_mask,
+    T* __restrict__ dx, T* __restrict__ dx2, const uint32_t* __restrict__ mask2, float scale2, int64_t mask_rows, int mask2_w,
     float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float red[];  // 8 warps x 2 x (8 x GP) floats, GP = padded group count
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -122,10 +122,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
         for (int i = 0; i < 8; ++i) o[i] = rstd * (gy[q][i] - s1 - xh[q][i] * s2);
         if (dx) store8(dx + rho * C + g * 8, o);
         if (dx2) {
-          uint32_t w = mask2 ? mask2[rho * ld_mask + (g >> 2)] : 0xffffffffu;
+          uint32_t w = mask2 ? reinterpret_cast<const uint8_t*>(mask2)[mask_byte_addr(rho, g * 8, mask2_w, mask_rows)] : 0xffu;
           float o2[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o2[i] = ((w >> ((g & 3) * 8 + i)) & 1u) ? o[i] * scale2 : 0.f;
+          for (int i = 0; i < 8; ++i) o2[i] = ((w >> i) & 1u) ? o[i] * scale2 : 0.f;
           store8(dx2 + rho * C + g * 8, o2);
         }
       }
@@ -273,7 +273,7 @@ int nbasr_layernorm_fwd(int dtype, const void* x, void* y, int B, int T, int Tp,
 
 int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* mean, const float* rstd,
                         const float* gamma, int B, int T, int Tp, int C, void* dx, void* dx2, const uint32_t* mask2,
-                        float scale2, int64_t ld_mask, float* dgamma, float* dbeta, void* stream) {
+                        float scale2, int64_t mask_rows, int mask2_w, float* dgamma, float* dbeta, void* stream) {
   NBASR_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_MAXG, "C");
   int64_t rows = (int64_t)B * T;
   int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 2);
@@ -286,9 +286,9 @@ int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* m
     attr = true;
   }
   if (dtype == NBASR_BF16)
-    layernorm_bwd_kernel<bf16><<<blocks, 256, sm, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, B, T, Tp, C, (bf16*)dx, (bf16*)dx2, mask2, scale2, ld_mask, dgamma, dbeta);
+    layernorm_bwd_kernel<bf16><<<blocks, 256, sm, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, B, T, Tp, C, (bf16*)dx, (bf16*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta);
   else
-    layernorm_bwd_kernel<float><<<blocks, 256, sm, as_stream(stream)>>>((const float*)dy, (const float*)x, mean, rstd, gamma, B, T, Tp, C, (float*)dx, (float*)dx2, mask2, scale2, ld_mask, dgamma, dbeta);
+    layernorm_bwd_kernel<float><<<blocks, 256, sm, as_stream(stream)>>>((const float*)dy, (const float*)x, mean, rstd, gamma, B, T, Tp, C, (float*)dx, (float*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta);
   NBASR_CHECK_LAUNCH();
   return 0;
 }

@@ -34,46 +34,66 @@ constexpr int A_BYTES = AROWS * 128;       // 18432
 constexpr int NW = 48;                     // MMA N (and K window) of a slab
 constexpr int WTAP_BYTES = NW * 128;       // 6144
 constexpr int MAXTAPS = 7;
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 3;                  // (weight-gradient kernel)
 constexpr int NACC = 4;
-constexpr int GC_THREADS = 192;
-constexpr int FWD_SMEM = MAXTAPS * WTAP_BYTES + NSTAGE * A_BYTES + 1024 + 256;
+constexpr int GC_THREADS = 192;            // weight-gradient kernel: producer, MMA, 4 epilogue warps
+constexpr int FWD_THREADS = 320;           // forward kernel: producer, MMA, 8 epilogue warps
+constexpr int NEPI = 256;
+constexpr int OSTAGE_BYTES = GT * NW * 2;  // 12288: bf16 output tile staged for the TMA store
+constexpr int FWD_SMEM_BUDGET = 112 * 1024;
 
 __host__ __device__ inline int slab_out(int cpg) { return cpg == 10 ? 40 : 48; }
+__host__ __device__ inline int fwd_nstage(int ktaps) {
+  int n = (FWD_SMEM_BUDGET - 3072 - ktaps * WTAP_BYTES - 2 * OSTAGE_BYTES) / A_BYTES;
+  return n > 4 ? 4 : n;
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld16_nowait(taddr, v);
+  tmem_ld_wait();
 }
 
 struct GcFwdArgs {
   int B, T, C, OUT, ktaps, dstep, off0;
-  int nslabs, ntiles, tiles_per_utt, nlanes;
+  int nslabs, ntiles, tiles_per_utt, nlanes, nstage;
   nbasr_epilogue epi;
   int64_t Tp;
+  unsigned long long* dbg;   // optional timeline dump (tools/trace_gconv.py): [cta][tile][8] globaltimer ns
 };
 
-__global__ void __launch_bounds__(GC_THREADS, 2)
-gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const GcFwdArgs p) {
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define GC_STAMP(slot)                                                                         \
+  do {                                                                                         \
+    if (p.dbg && blockIdx.x < 8 && it < 64) p.dbg[((size_t)blockIdx.x * 64 + it) * 8 + (slot)] = gtime(); \
+  } while (0)
+
+// Epilogue of the forward / input-gradient kernel.  8 warps: warp pair (w, w+4) shares a TMEM lane quadrant and
+// splits the 48 accumulator columns in two halves of 24.  Results are staged in shared memory as a dense
+// [128][OUT] bf16 tile and written with ONE TMA store per output tensor (coalesced, asynchronous); only the
+// gate-bit bytes and optional skip-sum reads stay per-thread accesses.
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GcFwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  const int NS = p.nstage;
   const uint32_t wsm = base;
-  const uint32_t asm0 = base + MAXTAPS * WTAP_BYTES;
-  const uint32_t bar0 = asm0 + NSTAGE * A_BYTES;
+  const uint32_t asm0 = base + p.ktaps * WTAP_BYTES;
+  const uint32_t osm = asm0 + NS * A_BYTES;          // out staging, then out2 staging
+  const uint32_t bar0 = osm + 2 * OSTAGE_BYTES;
+  uint8_t* ost = al + p.ktaps * WTAP_BYTES + NS * A_BYTES;
+  uint8_t* mst = ost + 2 * OSTAGE_BYTES + 256;    // 128 x 8-byte gate-bit entries
   const uint32_t wbar = bar0;
   auto full_bar = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (1 + NSTAGE + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (1 + 2 * NSTAGE + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (1 + 2 * NSTAGE + NACC + s); };
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(al + MAXTAPS * WTAP_BYTES + NSTAGE * A_BYTES + 8 * (1 + 2 * NSTAGE + 2 * NACC));
+  auto empty_bar = [&](int s) { return bar0 + 8u * (1 + 4 + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (1 + 8 + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (1 + 8 + NACC + s); };
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(ost + 2 * OSTAGE_BYTES + 8 * (1 + 8 + 2 * NACC));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab = blockIdx.x % p.nslabs;
   const int lane_id = blockIdx.x / p.nslabs;
@@ -83,8 +103,8 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmW);
     mbar_init(wbar, 1);
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < NACC; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    for (int s = 0; s < NS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NEPI); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tptr), 256);
@@ -97,14 +117,16 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (lane == 0) {
       mbar_expect_tx(wbar, p.ktaps * WTAP_BYTES);
       for (int j = 0; j < p.ktaps; ++j) tma_load_2d(wsm + j * WTAP_BYTES, &tmW, wbar, 0, (slab * p.ktaps + j) * NW);
-      int stage = 0;
+      int stage = 0, it = 0;
       uint32_t phase = 0;
-      for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes) {
+      for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes, ++it) {
         const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * GT;
+        GC_STAMP(0);
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_expect_tx(full_bar(stage), A_BYTES);
         tma_load_3d(asm0 + stage * A_BYTES, &tmX, full_bar(stage), c0, NBASR_PAD_L + t0 + p.off0, b);
-        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        GC_STAMP(1);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -117,7 +139,9 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int as = it % NACC;
         const uint32_t aphase = (it / NACC) & 1;
         mbar_wait(tempty_bar(as), aphase ^ 1);
+        GC_STAMP(2);
         mbar_wait(full_bar(stage), phase);
+        GC_STAMP(3);
         tcgen05_fence_after();
         const uint32_t sa = asm0 + stage * A_BYTES;
         for (int j = 0; j < p.ktaps; ++j) {
@@ -130,16 +154,21 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(as));
-        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        if (++stage == NS) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    const int q = warp & 3;
-    const int nvalid = min(p.C, c0 + p.OUT) - c0;
-    // the slab is fixed for the CTA's lifetime: keep its bias in registers, hand the epilogue a bias-free copy
-    float bias_r[48];
+    const int ew = warp - 2;                 // 0..7
+    const int q = warp & 3;                  // TMEM lane quadrant of this warp
+    const int hh = ew >> 2;                  // column half: cols [24*hh, 24*hh + 24)
+    const int etid = threadIdx.x - 64;
+    const int row = q * 32 + lane;
+    const int cbeg = c0 + 24 * hh;
+    const int nvalid = max(0, min(24, min(p.C, c0 + p.OUT) - cbeg));     // multiple of 8
+    const int OUTB = p.OUT * 2;              // staged row pitch in bytes
+    float bias_r[24];
 #pragma unroll
-    for (int i = 0; i < 48; ++i) bias_r[i] = (p.epi.bias && i < nvalid) ? __ldg(p.epi.bias + c0 + i) : 0.f;
+    for (int i = 0; i < 24; ++i) bias_r[i] = (p.epi.bias && i < nvalid) ? __ldg(p.epi.bias + cbeg + i) : 0.f;
     nbasr_epilogue epi = p.epi;
     epi.bias = nullptr;
     int it = 0;
@@ -147,23 +176,63 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const int as = it % NACC;
       const uint32_t aphase = (it / NACC) & 1;
       const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * GT;
-      const int t = t0 + q * 32 + lane;
+      const int t = t0 + row;
       mbar_wait(tfull_bar(as), aphase);
+      if (etid == 0) GC_STAMP(4);
       tcgen05_fence_after();
-      float v[48];
-      const uint32_t ta = tm + ((uint32_t)(q * 32) << 16) + as * 64;
-      tmem_ld32(ta, v);
-      tmem_ld16(ta + 32, v + 32);
+      float v[24];
+      const uint32_t ta = tm + ((uint32_t)(q * 32) << 16) + as * 64 + 24 * hh;
+      tmem_ld16_nowait(ta, v);
+      tmem_ld8_nowait(ta + 16, v + 16);
+      tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar(as));       // accumulator is in registers: release the TMEM stage early
-      if (t < p.T) {
-        const int64_t rho = (int64_t)b * p.Tp + NBASR_PAD_L + t;
+      mbar_arrive(tempty_bar(as));           // accumulator is in registers: release the TMEM stage early
+      const bool rowok = t < p.T;
+      const int64_t rho = (int64_t)b * p.Tp + NBASR_PAD_L + t;
+      uint32_t m[3] = {0, 0, 0};
+      if (rowok) {
 #pragma unroll
-        for (int i = 0; i < 48; ++i) v[i] += bias_r[i];
-        if (nvalid == 48) epilogue_cols<48, true>(epi, rho, c0, 48, v);
-        else epilogue_cols<48, false>(epi, rho, c0, nvalid, v);
+        for (int i = 0; i < 24; ++i) v[i] += bias_r[i];
+        if (nvalid == 24) epilogue_compute<24, true>(epi, rho, cbeg, 24, v, m);
+        else epilogue_compute<24, false>(epi, rho, cbeg, nvalid, v, m);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) v[i] = 0.f;      // rows past the utterance land on zero pad rows / are clipped
+      }
+      // staging buffers are free once the previous tile's TMA stores have finished READING shared memory
+      if (etid == 0) bulk_wait_read0();
+      named_bar_sync(1, NEPI);
+      uint8_t* orow = ost + row * OUTB + 48 * hh;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        if (g * 8 < nvalid) {
+          if (epi.out) store8(reinterpret_cast<bf16*>(orow + g * 16), v + g * 8);
+          if (epi.out2) {
+            uint32_t w = 0xffu;
+            if (epi.mask2 && rowok) w = reinterpret_cast<const uint8_t*>(epi.mask2)[mask_byte_addr(rho, cbeg + g * 8, epi.mask2_w, epi.mask_rows)];
+            float t2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t2[i] = ((w >> i) & 1u) ? v[g * 8 + i] * epi.scale2 : 0.f;
+            store8(reinterpret_cast<bf16*>(orow + OSTAGE_BYTES + g * 16), t2);
+          }
+        }
+        if (epi.mask_out) mst[row * 8 + 3 * hh + g] = (g * 8 < nvalid) ? (uint8_t)m[g] : (uint8_t)0;   // 8-byte entry per row
+      }
+      fence_async_smem();
+      named_bar_sync(1, NEPI);
+      if (epi.mask_out && etid < GT && t0 + etid < p.T) {
+        // 128 consecutive 8-byte entries of this slab's mask plane: one fully coalesced store per warp
+        const int64_t r2 = (int64_t)b * p.Tp + NBASR_PAD_L + t0 + etid;
+        reinterpret_cast<uint64_t*>(epi.mask_out)[(int64_t)slab * epi.mask_rows + r2] = reinterpret_cast<const uint64_t*>(mst)[etid];
+      }
+      if (etid == 0) {
+        if (epi.out) tma_store_3d(&tmO, osm, c0, NBASR_PAD_L + t0, b);
+        if (epi.out2) tma_store_3d(&tmO2, osm + OSTAGE_BYTES, c0, NBASR_PAD_L + t0, b);
+        bulk_commit();
+        GC_STAMP(5);
       }
     }
+    if (etid == 0) bulk_wait0();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -332,18 +401,26 @@ __global__ void pack_gconv_mma_kernel(const float* __restrict__ w, bf16* __restr
 
 }  // namespace
 
+static unsigned long long* g_gconv_dbg = nullptr;
+extern "C" void nbasr_dbg_gconv_trace(unsigned long long* buf) { g_gconv_dbg = buf; }
+
 int sm100_gconv_fwd(const nbasr_gconv* g, cudaStream_t st) {
   GcFwdArgs a{};
   a.B = g->B; a.T = g->T; a.Tp = g->Tp; a.C = g->C; a.OUT = slab_out(g->cpg);
   a.ktaps = g->ktaps; a.dstep = g->dstep; a.off0 = g->off0;
   NBASR_REQUIRE(a.off0 >= -NBASR_PAD_L && (a.ktaps - 1) * a.dstep <= AROWS - GT, "tap reach");
+  NBASR_REQUIRE(g->epi.ld_out == g->C, "grouped conv writes dense (B,Tp,C) tensors");
+  NBASR_REQUIRE((!g->epi.out || g->epi.out_dtype == NBASR_BF16) && (!g->epi.out2 || g->epi.out2_dtype == NBASR_BF16) &&
+                    !g->epi.accumulate, "tcgen05 grouped conv stores bf16");
   a.nslabs = (g->C + a.OUT - 1) / a.OUT;
   a.tiles_per_utt = (g->T + GT - 1) / GT;
   a.ntiles = a.tiles_per_utt * g->B;
+  a.nstage = fwd_nstage(a.ktaps);
   int slots = 2 * nbasr_sm_count();
   a.nlanes = std::max(1, std::min(a.ntiles, slots / a.nslabs));
   a.epi = g->epi;
-  CUtensorMap tmX, tmW;
+  a.dbg = g_gconv_dbg;
+  CUtensorMap tmX, tmW, tmO, tmO2;
   uint64_t dx[3] = {(uint64_t)g->C, (uint64_t)g->Tp, (uint64_t)g->B};
   int64_t sx[3] = {1, g->C, (int64_t)g->Tp * g->C};
   uint32_t bx[3] = {64, AROWS, 1};
@@ -352,13 +429,20 @@ int sm100_gconv_fwd(const nbasr_gconv* g, cudaStream_t st) {
   int64_t sw[2] = {1, 64};
   uint32_t bw[2] = {64, NW};
   if (sm100_get_map(g->w, 2, dw, sw, bw, &tmW)) return 1;
+  uint32_t bo[3] = {(uint32_t)a.OUT, GT, 1};
+  const void* o1 = g->epi.out ? g->epi.out : g->x;       // unused maps still need a valid descriptor
+  const void* o2 = g->epi.out2 ? g->epi.out2 : g->x;
+  if (sm100_get_map(o1, 3, dx, sx, bo, &tmO, 0)) return 1;
+  if (sm100_get_map(o2, 3, dx, sx, bo, &tmO2, 0)) return 1;
+  NBASR_REQUIRE(!g->epi.mask_out || g->epi.mask_w == a.OUT, "grouped-conv mask planes are slab wide");
+  size_t smem = (size_t)a.ktaps * WTAP_BYTES + (size_t)a.nstage * A_BYTES + 2 * OSTAGE_BYTES + 1024 + 256 + 1024;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gconv_mma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gconv_mma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BUDGET);
     if (e != cudaSuccess) return nbasr_fail("gconv_mma_fwd smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  gconv_mma_fwd_kernel<<<a.nslabs * a.nlanes, GC_THREADS, FWD_SMEM, st>>>(tmX, tmW, a);
+  gconv_mma_fwd_kernel<<<a.nslabs * a.nlanes, FWD_THREADS, smem, st>>>(tmX, tmW, tmO, tmO2, a);
   NBASR_CHECK_LAUNCH();
   return 0;
 }

@@ -28,7 +28,7 @@ int sm100_gemm_wgrad(const nbasr_wgrad* p, cudaStream_t st);
 // cached bf16 TMA descriptor (rank 2/3, 128B swizzle); strides in elements for dims 1..rank-1
 struct CUtensorMap_st;
 int sm100_get_map(const void* base, int rank, const uint64_t* dims, const int64_t* strides_el, const uint32_t* box,
-                  CUtensorMap_st* out);
+                  CUtensorMap_st* out, int swizzle128 = 1);
 
 // tcgen05 grouped conv (gconv_sm100.cu)
 int sm100_gconv_fwd(const nbasr_gconv* p, cudaStream_t st);

@@ -44,6 +44,15 @@ class _Plan:
     pass
 
 
+class _Mask:
+    """Plane-major gate-bit mask of a (rows, C) tensor: planes of w columns, one 4/8-byte entry per row and plane."""
+
+    def __init__(self, rows, C, w, dev):
+        self.w = w
+        eb = 4 if w == 32 else 8
+        self.t = torch.zeros(((C + w - 1) // w) * rows * eb, dtype=torch.uint8, device=dev)
+
+
 class Engine:
     def __init__(self, model, precision='bf16'):
         assert precision in ('bf16', 'fp32')
@@ -225,8 +234,9 @@ class Engine:
         self._pack_version = v
 
     # ------------------------------------------------------------------ plan construction
-    def _epi(self, ld, bias=0, relu=0, drop_p=0.0, salt=0, adds=(), out=0, out_dtype=None, mask_out=0, out2=0,
-             mask2=0, scale2=1.0, ld_mask=0, accumulate=0):
+    def _epi(self, ld, bias=0, relu=0, drop_p=0.0, salt=0, adds=(), out=0, out_dtype=None, mask_out=None, out2=0,
+             mask2=None, scale2=1.0, mask_rows=0, accumulate=0):
+        """mask_out / mask2 are _Mask objects (tensor + plane width) or None."""
         e = Epilogue()
         e.bias = bias or None
         e.relu20 = relu
@@ -240,12 +250,14 @@ class Engine:
         e.out = out or None
         e.out_dtype = self.dt if out_dtype is None else out_dtype
         e.ld_out = ld
-        e.mask_out = mask_out or None
+        e.mask_out = mask_out.t.data_ptr() if mask_out is not None else None
+        e.mask_w = mask_out.w if mask_out is not None else 32
         e.out2 = out2 or None
         e.out2_dtype = self.dt
-        e.mask2 = mask2 or None
+        e.mask2 = mask2.t.data_ptr() if mask2 is not None else None
+        e.mask2_w = mask2.w if mask2 is not None else 32
         e.scale2 = scale2
-        e.ld_mask = ld_mask
+        e.mask_rows = mask_rows
         e.accumulate = accumulate
         return e
 
@@ -320,10 +332,11 @@ class Engine:
             lpad, _ = pad_rule(8, 1, s)
             K = 8 * pg.C
             z = zbuf(geo.rows, Cc)
-            zmask = zbuf(geo.rows, mw, torch.int32)
+            zmask = _Mask(geo.rows, Cc, 32, dev)
+            pl.keep.append(zmask)
             wf_ptr = self.wf[cname].data_ptr() if self.wf[cname] is not None else self.P(cname + '.weight')
             a_ptr = _ptr(prev, (PAD_L - lpad) * pg.C)
-            epi = self._epi(Cc, bias=self.P(cname + '.bias'), relu=1, out=z.data_ptr(), mask_out=zmask.data_ptr(), ld_mask=mw)
+            epi = self._epi(Cc, bias=self.P(cname + '.bias'), relu=1, out=z.data_ptr(), mask_out=zmask, mask_rows=geo.rows)
             gemm(fwd, a_ptr, pg.Tp * pg.C, s * pg.C, B, Ti, K, Cc, wf_ptr, K, PAD_L, Tp, 1, epi)
             y = zbuf(geo.rows, Cc)
             mean0 = zbuf(geo.rows, 1, torch.float32)
@@ -350,12 +363,15 @@ class Engine:
                         call(fwd, lib.nbasr_eltwise, dt, None, Cc, B, Ti, Tp, Cc, C.byref(epi))
                         pl.keep.append(epi)
                     else:
-                        mask = zbuf(geo.rows, mw, torch.int32)
+                        # plane width = the producing kernel's slab: 32 (GEMM / SIMT) or 48/40 (tcgen05 grouped conv)
+                        mwid = (40 if Cc // 100 == 10 else 48) if (op in CONV_EDGES and dt == BF16) else 32
+                        mask = _Mask(geo.rows, Cc, mwid, dev)
+                        pl.keep.append(mask)
                         nrec['mask'] = mask
                         sl = next_salt()
                         if op == 'linear':
                             epi = self._epi(Cc, bias=self.P(pn + '.linear.bias'), relu=1, drop_p=drop_p, salt=sl, adds=adds,
-                                            out=o.data_ptr(), mask_out=mask.data_ptr(), ld_mask=mw)
+                                            out=o.data_ptr(), mask_out=mask, mask_rows=geo.rows)
                             w_ptr = self.wf[pn].data_ptr() if self.wf[pn] is not None else self.P(pn + '.linear.weight')
                             gemm(fwd, _ptr(src, PAD_L * Cc), Tp * Cc, Cc, B, Ti, Cc, Cc, w_ptr, Cc, PAD_L, Tp, 1, epi)
                         else:
@@ -369,7 +385,7 @@ class Engine:
                             else:
                                 gc.w, gc.w_packed = self.P(pn + '.conv.weight'), 0
                             gc.epi = self._epi(Cc, bias=self.P(pn + '.conv.bias'), relu=1, drop_p=drop_p, salt=sl, adds=adds,
-                                               out=o.data_ptr(), mask_out=mask.data_ptr(), ld_mask=mw)
+                                               out=o.data_ptr(), mask_out=mask, mask_rows=geo.rows)
                             call(fwd, lib.nbasr_gconv_fwd, C.byref(gc))
                             pl.keep.append(gc)
                             nrec.update(k=k, d=d, lp=lp)
@@ -405,8 +421,9 @@ class Engine:
             ln = self.lstm_name
             if drop_p > 0:
                 lin = zbuf(geo3.rows, C3)
-                dmask = zbuf(geo3.rows, geo3.mw, torch.int32)
-                epi = self._epi(C3, drop_p=drop_p, salt=next_salt(), out=lin.data_ptr(), mask_out=dmask.data_ptr(), ld_mask=geo3.mw)
+                dmask = _Mask(geo3.rows, C3, 32, dev)
+                pl.keep.append(dmask)
+                epi = self._epi(C3, drop_p=drop_p, salt=next_salt(), out=lin.data_ptr(), mask_out=dmask, mask_rows=geo3.rows)
                 call(fwd, lib.nbasr_eltwise, dt, prev.data_ptr(), C3, B, Tq, Tp3, C3, C.byref(epi))
                 pl.keep.append(epi)
             else:
@@ -467,7 +484,7 @@ class Engine:
                   HIDDEN, self.G(ln + '.weight_hh_l0'), HIDDEN)
             # dX = dgx W_ih  (through the input dropout mask if any)
             if head['dmask'] is not None:
-                epi = self._epi(C3, out2=gout.data_ptr(), mask2=head['dmask'].data_ptr(), scale2=dscale, ld_mask=geo3.mw)
+                epi = self._epi(C3, out2=gout.data_ptr(), mask2=head['dmask'], scale2=dscale, mask_rows=geo3.rows)
             else:
                 epi = self._epi(C3, out=gout.data_ptr())
             gemm(bwd, dgx_a.data_ptr(), Tq * H4, H4, B, Tq, H4, C3, self.wt[ln].data_ptr(), H4, PAD_L, Tp3, 1, epi)
@@ -501,7 +518,8 @@ class Engine:
                     call(bwd, lib.nbasr_layernorm_bwd, dt, gout.data_ptr(), outs[nn_].data_ptr(), crec['mean'].data_ptr(),
                          crec['rstd'].data_ptr(), self.P(crec['name'] + '.norm_layer.weight'), B, Ti, Tp, Cc,
                          g[nn_].data_ptr(), dz_t.data_ptr() if dz_t is not None else None,
-                         last['mask'].data_ptr() if dz_t is not None else None, dscale, mw,
+                         last['mask'].t.data_ptr() if dz_t is not None else None, dscale, geo.rows,
+                         last['mask'].w if dz_t is not None else 32,
                          self.G(crec['name'] + '.norm_layer.weight'), self.G(crec['name'] + '.norm_layer.bias'))
                     pool.append(gout)
                 else:
@@ -509,7 +527,7 @@ class Engine:
                     if last['op'] != 'zero':
                         dz_t = dz[(nn_ - 1) & 1]
                         dzb[nn_ - 1] = dz_t
-                        epi = self._epi(Cc, out2=dz_t.data_ptr(), mask2=last['mask'].data_ptr(), scale2=dscale, ld_mask=mw)
+                        epi = self._epi(Cc, out2=dz_t.data_ptr(), mask2=last['mask'], scale2=dscale, mask_rows=geo.rows)
                         call(bwd, lib.nbasr_eltwise, dt, gout.data_ptr(), Cc, B, Ti, Tp, Cc, C.byref(epi))
                         pl.keep.append(epi)
                 for j in range(nn_ - 1, -1, -1):
@@ -520,11 +538,11 @@ class Engine:
                     adds = [g[k + 1].data_ptr() for k in range(j, nn_) if nodes[k]['branches'][j]]
                     g[j] = pool.pop()
                     # the epilogue that produces g[j] also emits dZ_{j-1} = g[j] * mask_{j-1}
-                    o2, m2 = 0, 0
+                    o2, m2 = 0, None
                     if j >= 1 and nodes[j - 1]['op'] != 'zero':
                         dzb[j - 1] = dz[(j - 1) & 1]
-                        o2, m2 = dzb[j - 1].data_ptr(), nodes[j - 1]['mask'].data_ptr()
-                    epi = self._epi(Cc, adds=adds, out=g[j].data_ptr(), out2=o2, mask2=m2, scale2=dscale, ld_mask=mw)
+                        o2, m2 = dzb[j - 1].data_ptr(), nodes[j - 1]['mask']
+                    epi = self._epi(Cc, adds=adds, out=g[j].data_ptr(), out2=o2, mask2=m2, scale2=dscale, mask_rows=geo.rows)
                     if op == 'zero':
                         call(bwd, lib.nbasr_eltwise, dt, None, Cc, B, Ti, Tp, Cc, C.byref(epi))
                         pl.keep.append(epi)
@@ -555,8 +573,8 @@ class Engine:
             dzc = dz[0]
             lname, cname = self.block_ln[i], self.block_conv[i]
             call(bwd, lib.nbasr_layernorm_bwd, dt, gout.data_ptr(), rec['z'].data_ptr(), rec['mean'].data_ptr(),
-                 rec['rstd'].data_ptr(), self.P(lname + '.weight'), B, Ti, Tp, Cc, None, dzc.data_ptr(), rec['zmask'].data_ptr(),
-                 1.0, mw, self.G(lname + '.weight'), self.G(lname + '.bias'))
+                 rec['rstd'].data_ptr(), self.P(lname + '.weight'), B, Ti, Tp, Cc, None, dzc.data_ptr(), rec['zmask'].t.data_ptr(),
+                 1.0, geo.rows, 32, self.G(lname + '.weight'), self.G(lname + '.bias'))
             pool.append(gout)
             pgeo, s = rec['pg'], rec['s']
             fuse = dt == BF16

@@ -44,8 +44,14 @@ def ptr(t, off=0):
     return t.data_ptr() + off * t.element_size()
 
 
+def new_mask(rows, Cc, w=32):
+    """plane-major gate-bit mask buffer (see include/nbasr.h): (planes, rows, entry bytes) uint8"""
+    eb = 4 if w == 32 else 8
+    return torch.zeros((Cc + w - 1) // w, rows, eb, dtype=torch.uint8, device=DEV)
+
+
 def epilogue(dt, ld, bias=None, relu=0, drop_p=0.0, salt=0, adds=(), out=None, out_dtype=None, mask_out=None, out2=None,
-             mask2=None, scale2=1.0, ld_mask=0, accumulate=0):
+             mask2=None, scale2=1.0, mask_w=32, mask2_w=32, accumulate=0):
     e = Epilogue()
     e.bias = bias.data_ptr() if bias is not None else None
     e.relu20, e.drop_p, e.drop_seed, e.drop_step = relu, drop_p, salt, None
@@ -60,7 +66,10 @@ def epilogue(dt, ld, bias=None, relu=0, drop_p=0.0, salt=0, adds=(), out=None, o
     e.out2 = out2.data_ptr() if out2 is not None else None
     e.out2_dtype = dt
     e.mask2 = mask2.data_ptr() if mask2 is not None else None
-    e.scale2, e.ld_mask, e.accumulate = scale2, ld_mask, accumulate
+    e.scale2, e.accumulate = scale2, accumulate
+    e.mask_w, e.mask2_w = mask_w, mask2_w
+    m_any = mask_out if mask_out is not None else mask2
+    e.mask_rows = m_any.shape[1] if m_any is not None else 0
     return e
 
 
@@ -88,10 +97,11 @@ def relerr(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-300))
 
 
-def unpack_mask(mask, B, T, Cc):
-    """(rows, mw) int32 bit mask -> bool (B,T,C)."""
+def unpack_mask(mask, B, T, Cc, w=32):
+    """(planes, rows, eb) uint8 plane-major bit mask -> bool (B,T,C)."""
     Tp = geo(T)
-    mw = mask.shape[1]
-    m = mask[:B * Tp].view(B, Tp, mw)[:, PAD_L:PAD_L + T].to(torch.int64) & 0xffffffff
-    bits = ((m.unsqueeze(-1) >> torch.arange(32, device=m.device)) & 1).bool()
-    return bits.reshape(B, T, mw * 32)[:, :, :Cc]
+    planes, rows, eb = mask.shape
+    m = mask[:, :B * Tp].view(planes, B, Tp, eb)[:, :, PAD_L:PAD_L + T]          # (planes, B, T, eb)
+    bits = ((m.unsqueeze(-1).to(torch.int32) >> torch.arange(8, device=m.device, dtype=torch.int32)) & 1).bool()
+    bits = bits.reshape(planes, B, T, eb * 8)[..., :w]                              # (planes, B, T, w)
+    return bits.permute(1, 2, 0, 3).reshape(B, T, planes * w)[:, :, :Cc]

@@ -33,7 +33,7 @@ def test_struct_layouts_match_c(tmp_path):
 #include "nbasr.h"
 int main(void) {
   printf("%zu %zu %zu %zu ", sizeof(nbasr_epilogue), sizeof(nbasr_gemm), sizeof(nbasr_wgrad), sizeof(nbasr_gconv));
-  printf("%zu %zu %zu %zu %zu\\n", offsetof(nbasr_epilogue, out), offsetof(nbasr_epilogue, ld_mask),
+  printf("%zu %zu %zu %zu %zu\\n", offsetof(nbasr_epilogue, out), offsetof(nbasr_epilogue, mask_rows),
          offsetof(nbasr_gemm, epi), offsetof(nbasr_gconv, epi), offsetof(nbasr_wgrad, dw));
   return 0;
 }''')
@@ -41,7 +41,7 @@ int main(void) {
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(prog), '-o', str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     E, G, W, GC = _lib.Epilogue, _lib.Gemm, _lib.Wgrad, _lib.GConv
-    exp = [ctypes.sizeof(E), ctypes.sizeof(G), ctypes.sizeof(W), ctypes.sizeof(GC), E.out.offset, E.ld_mask.offset,
+    exp = [ctypes.sizeof(E), ctypes.sizeof(G), ctypes.sizeof(W), ctypes.sizeof(GC), E.out.offset, E.mask_rows.offset,
            G.epi.offset, GC.epi.offset, W.dw.offset]
     assert got == exp
 

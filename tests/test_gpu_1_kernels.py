@@ -36,9 +36,9 @@ def test_simt_dense_conv_as_gemm(stride):
     wp = w.permute(0, 2, 1).contiguous().view(Cout, 8 * Cin).to(U.DEV)       # (Cout, k, Cin)
     out = U.empty_padded(B, To, Cout, F32)
     sk = U.to_padded(skip, F32)
-    mask = torch.zeros(out.shape[0], (Cout + 31) // 32, dtype=torch.int32, device=U.DEV)
+    mask = U.new_mask(out.shape[0], Cout)
     lpad, _ = pad_rule(8, 1, stride)
-    epi = U.epilogue(F32, Cout, bias=bias.to(U.DEV), relu=1, adds=[sk], out=out, mask_out=mask, ld_mask=mask.shape[1])
+    epi = U.epilogue(F32, Cout, bias=bias.to(U.DEV), relu=1, adds=[sk], out=out, mask_out=mask)
     U.run_gemm(F32, U.ptr(xb, (PAD_L - lpad) * Cin), U.geo(T) * Cin, stride * Cin, B, To, 8 * Cin, Cout, wp, 8 * Cin,
                PAD_L, U.geo(To), 1, epi)
     got = U.from_padded(out, B, To).cpu()
@@ -105,8 +105,8 @@ def test_gconv_fwd_bwd(dt, op, Cc):
     lib = _lib.load()
     xb, sk = U.to_padded(x.detach(), dt), U.to_padded(skip, dt)
     out = U.empty_padded(B, T, Cc, dt)
-    mw = (Cc + 31) // 32
-    mask = torch.zeros(out.shape[0], mw, dtype=torch.int32, device=U.DEV)
+    mwid = (40 if cpg == 10 else 48) if mma else 32        # mask plane width = the producing kernel's slab
+    mask = U.new_mask(out.shape[0], Cc, mwid)
     wg, bg = w.detach().to(U.DEV), bias.to(U.DEV)
     gc = GConv()
     gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg, gc.ktaps, gc.off0, gc.dstep = dt, xb.data_ptr(), B, T, U.geo(T), Cc, cpg, k, -lp, d
@@ -118,13 +118,15 @@ def test_gconv_fwd_bwd(dt, op, Cc):
         _lib.check(lib.nbasr_pack_gconv_mma(wg.data_ptr(), wpk.data_ptr(), Cc, cpg, k, 0, U.stream()))
         _lib.check(lib.nbasr_pack_gconv_mma(wg.data_ptr(), wpk_t.data_ptr(), Cc, cpg, k, 1, U.stream()))
         gc.w, gc.w_packed = wpk.data_ptr(), 1
-    gc.epi = U.epilogue(dt, Cc, bias=bg, relu=1, adds=[sk], out=out, mask_out=mask, ld_mask=mw)
+    gc.epi = U.epilogue(dt, Cc, bias=bg, relu=1, adds=[sk], out=out, mask_out=mask, mask_w=mwid)
     _lib.check(lib.nbasr_gconv_fwd(C.byref(gc), U.stream()), 'gconv')
     torch.cuda.synchronize()
     tol = 1e-5 if dt == F32 else 6e-3
     assert U.relerr(U.from_padded(out, B, T).cpu(), ref) < tol
     if dt == F32:
         assert torch.equal(U.unpack_mask(mask, B, T, Cc).cpu(), (z > 0) & (z <= 20))
+    if mma:
+        assert (U.unpack_mask(mask, B, T, Cc, mwid).cpu() != ((z > 0) & (z <= 20))).float().mean() < 1e-3
     # backward: dz given
     dz = rnd(torch.randn(B, T, Cc))
     gx, gw = torch.autograd.grad(z, (x, w), dz)
@@ -178,7 +180,7 @@ def test_layernorm_fwd_bwd(dt, Cc):
     dyb, dxb = U.to_padded(dy, dt), U.empty_padded(B, T, Cc, dt)
     dg, db = torch.zeros(Cc, device=U.DEV), torch.zeros(Cc, device=U.DEV)
     _lib.check(lib.nbasr_layernorm_bwd(dt, dyb.data_ptr(), xb.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gd.data_ptr(), B, T,
-                                       U.geo(T), Cc, dxb.data_ptr(), None, None, 1.0, 0, dg.data_ptr(), db.data_ptr(), U.stream()))
+                                       U.geo(T), Cc, dxb.data_ptr(), None, None, 1.0, 0, 32, dg.data_ptr(), db.data_ptr(), U.stream()))
     torch.cuda.synchronize()
     assert U.relerr(U.from_padded(dxb, B, T).cpu(), gx) < (1e-4 if dt == F32 else 8e-3)
     assert U.relerr(dg.cpu(), gg) < 1e-4 and U.relerr(db.cpu(), gb) < 1e-4
@@ -378,9 +380,8 @@ def test_dropout_statistics_and_mask_consistency():
     lib = _lib.load()
     src = U.to_padded(torch.ones(B, T, Cc), F32)
     out = U.empty_padded(B, T, Cc, F32)
-    mw = (Cc + 31) // 32
-    mask = torch.zeros(out.shape[0], mw, dtype=torch.int32, device=U.DEV)
-    epi = U.epilogue(F32, Cc, drop_p=p, salt=1234, out=out, mask_out=mask, ld_mask=mw)
+    mask = U.new_mask(out.shape[0], Cc)
+    epi = U.epilogue(F32, Cc, drop_p=p, salt=1234, out=out, mask_out=mask)
     _lib.check(lib.nbasr_eltwise(F32, src.data_ptr(), Cc, B, T, U.geo(T), Cc, C.byref(epi), U.stream()))
     torch.cuda.synchronize()
     o = U.from_padded(out, B, T)

@@ -46,10 +46,9 @@ def test_gemm_tn_conv_epilogue(stride):
     wp = w.permute(0, 2, 1).contiguous().view(Cout, 8 * Cin).bfloat16().to(U.DEV)
     out = U.empty_padded(B, To, Cout, BF16)
     sk = U.to_padded(skip, BF16)
-    mw = (Cout + 31) // 32
-    mask = torch.zeros(out.shape[0], mw, dtype=torch.int32, device=U.DEV)
+    mask = U.new_mask(out.shape[0], Cout)
     lpad, _ = pad_rule(8, 1, stride)
-    epi = U.epilogue(BF16, Cout, bias=bias.to(U.DEV), relu=1, adds=[sk], out=out, mask_out=mask, ld_mask=mw)
+    epi = U.epilogue(BF16, Cout, bias=bias.to(U.DEV), relu=1, adds=[sk], out=out, mask_out=mask)
     U.run_gemm(BF16, U.ptr(xb, (PAD_L - lpad) * Cin), U.geo(T) * Cin, stride * Cin, B, To, 8 * Cin, Cout, wp, 8 * Cin, PAD_L,
                U.geo(To), 1, epi)
     got = U.from_padded(out, B, To).cpu()

@@ -57,47 +57,82 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(int h_dtype, const void* 
   }
 }
 
-// head backward, fused: dh = dl W, db += sum dl, dW += dl^T h.  One block walks rows; the 8 warps split the
-// classes (dW rows live in shared memory, warp-private -> no atomics) and the hidden range (dh).
+// head backward, fused: dh = dl W, db += sum dl, dW += dl^T h.  W and the block's dW partial live in shared
+// memory; a block walks its rows 4 at a time (each W element read from smem feeds 4 FMAs); the 8 warps split the
+// classes for dW (warp-private rows -> no atomics) and the hidden range for dh.
+constexpr int HB_R = 4;
+
 __global__ void __launch_bounds__(256) head_bwd_kernel(int h_dtype, const void* __restrict__ h, int64_t h_bs, int64_t h_rs,
                                                        int B, int T, int K, int V, const float* __restrict__ w,
                                                        const float* __restrict__ dl, float* __restrict__ dh,
                                                        int64_t dh_bs, int64_t dh_rs, float* __restrict__ dw,
                                                        float* __restrict__ db) {
   extern __shared__ float sm[];
-  float* sdw = sm;                 // V x K (only if dw)
-  float* hrow = sm + (dw ? V * K : 0);   // K
-  float* drow = hrow + K;          // V (padded to 64)
+  float* ws = sm;                           // V x K
+  float* sdw = ws + V * K;                  // V x K (only if dw)
+  float* hrow = sdw + (dw ? V * K : 0);     // HB_R x K
+  float* drow = hrow + HB_R * K;            // HB_R x 64
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (dw) for (int i = tid; i < V * K; i += blockDim.x) sdw[i] = 0.f;
-  float dbacc = 0.f;               // thread v < V accumulates db[v]
-  __syncthreads();
-  for (int64_t r = blockIdx.x; r < (int64_t)B * T; r += gridDim.x) {
-    int b = (int)(r / T), t = (int)(r % T);
-    int64_t base = (int64_t)b * h_bs + (int64_t)t * h_rs;
-    for (int k = tid; k < K; k += blockDim.x) hrow[k] = ld_dt(h, h_dtype, base + k);
-    if (tid < V) {
-      float d = dl[r * V + tid];
+  for (int i = tid; i < V * K; i += blockDim.x) {
+    ws[i] = w[i];
+    if (dw) sdw[i] = 0.f;
+  }
+  float dbacc = 0.f;                        // thread v < V accumulates db[v]
+  const int64_t nrows = (int64_t)B * T;
+  const int64_t ngroups = (nrows + HB_R - 1) / HB_R;
+  for (int64_t gidx = blockIdx.x; gidx < ngroups; gidx += gridDim.x) {
+    __syncthreads();
+    const int64_t r0 = gidx * HB_R;
+    for (int i = tid; i < HB_R * K; i += blockDim.x) {
+      int rr = i / K, k = i - rr * K;
+      int64_t r = r0 + rr;
+      float v = 0.f;
+      if (r < nrows) v = ld_dt(h, h_dtype, (r / T) * h_bs + (r % T) * h_rs + k);
+      hrow[i] = v;
+    }
+    if (tid < HB_R * 64) {
+      int rr = tid >> 6, v = tid & 63;
+      int64_t r = r0 + rr;
+      float d = (v < V && r < nrows) ? dl[r * V + v] : 0.f;
       drow[tid] = d;
-      dbacc += d;
     }
     __syncthreads();
-    // dh[k] = sum_v d_v W[v][k]
-    float* o = dh + (int64_t)b * dh_bs + (int64_t)t * dh_rs;
+    if (tid < V) {
+#pragma unroll
+      for (int rr = 0; rr < HB_R; ++rr) dbacc += drow[rr * 64 + tid];
+    }
+    // dh[r][k] = sum_v d[r][v] W[v][k]
     for (int k = tid; k < K; k += blockDim.x) {
-      float acc = 0.f;
-      for (int v = 0; v < V; ++v) acc = fmaf(drow[v], __ldg(w + (int64_t)v * K + k), acc);
-      o[k] = acc;
+      float acc[HB_R];
+#pragma unroll
+      for (int rr = 0; rr < HB_R; ++rr) acc[rr] = 0.f;
+      for (int v = 0; v < V; ++v) {
+        float wv = ws[v * K + k];
+#pragma unroll
+        for (int rr = 0; rr < HB_R; ++rr) acc[rr] = fmaf(drow[rr * 64 + v], wv, acc[rr]);
+      }
+#pragma unroll
+      for (int rr = 0; rr < HB_R; ++rr) {
+        int64_t r = r0 + rr;
+        if (r < nrows) dh[(r / T) * dh_bs + (r % T) * dh_rs + k] = acc[rr];
+      }
     }
     if (dw) {
       for (int v = warp; v < V; v += 8) {
-        float d = drow[v];
+        float d[HB_R];
+#pragma unroll
+        for (int rr = 0; rr < HB_R; ++rr) d[rr] = drow[rr * 64 + v];
         float* row = sdw + v * K;
-        for (int k = lane; k < K; k += 32) row[k] = fmaf(d, hrow[k], row[k]);
+        for (int k = lane; k < K; k += 32) {
+          float a = row[k];
+#pragma unroll
+          for (int rr = 0; rr < HB_R; ++rr) a = fmaf(d[rr], hrow[rr * K + k], a);
+          row[k] = a;
+        }
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
   if (db && tid < V) atomicAdd(db + tid, dbacc);
   if (dw) for (int i = tid; i < V * K; i += blockDim.x) atomicAdd(dw + i, sdw[i]);
 }
@@ -334,11 +369,12 @@ int nbasr_head_bwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B
   NBASR_REQUIRE(V <= 64 && K <= 32 * HEAD_MAXK32, "head shape");
   int64_t rows = (int64_t)B * T;
   if (rows == 0) return 0;
-  const bool fuse_dw = dw && (size_t)(V * K + K + 64) * sizeof(float) <= 200 * 1024;
-  size_t sm = sizeof(float) * ((fuse_dw ? (size_t)V * K : 0) + K + 64);
+  const bool fuse_dw = dw && (size_t)(2 * V * K + HB_R * K + HB_R * 64) * sizeof(float) <= 220 * 1024;
+  size_t sm = sizeof(float) * ((size_t)V * K + (fuse_dw ? (size_t)V * K : 0) + HB_R * K + HB_R * 64);
+  NBASR_REQUIRE(sm <= 220 * 1024, "head too wide for the fused backward kernel");
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  int blocks = (int)std::min<int64_t>(rows, nbasr_sm_count());
+  if (!attr) { cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+  int blocks = (int)std::min<int64_t>((rows + HB_R - 1) / HB_R, nbasr_sm_count());
   head_bwd_kernel<<<blocks, 256, sm, as_stream(stream)>>>(h_dtype, h, h_bs, h_rs, B, T, K, V, w, dlogits, dh, dh_bs, dh_rs,
                                                           fuse_dw ? dw : nullptr, db);
   NBASR_CHECK_LAUNCH();

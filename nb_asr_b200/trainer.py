@@ -343,10 +343,8 @@ class Trainer:
         return ws.loss[0].clone(), pl.logp.clone(), audio_len // 4
 
     def _allreduce_grads(self, eng):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(eng.flat_g, op=dist.ReduceOp.SUM)
-            eng.flat_g.mul_(1.0 / dist.get_world_size())
+        from .distributed import allreduce_mean_
+        allreduce_mean_(eng.flat_g)
 
     def decode(self, output, output_len, val_inputs):
         """Greedy CTC decode + 48->39 fold + PER (batch mean of edit_distance / ref_len)."""

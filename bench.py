@@ -147,6 +147,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = os.environ.get('NBASR_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     B, T = args.batch, args.frames
     nb.set_seed(1235)

@@ -198,3 +198,46 @@ def test_dropout_training_runs_and_differs():
     a, b, _ = tr.step(batch, training=False)
     c, d, _ = tr.step(batch, training=False)
     assert torch.equal(b, d)                                   # eval is deterministic (no dropout)
+
+
+def test_train_loop_checkpoints_and_resume(tmp_path):
+    """Trainer.train (trainer.py:80-206): warm-up epochs, validation with greedy PER, best/latest checkpoints, resume."""
+    loaders = nb.get_dataloaders(batch_size=4, frames=96, n_train=2, n_val=1, n_test=1)
+    nb.set_seed(1235)
+    model = nb.get_model([[0, 1], [1, 1, 0], [5, 0, 1, 1]], use_rnn=True, dropout_rate=0.1, gpu=0)
+    tr = nb.get_trainer(loaders, nb.get_loss(), gpus=[0], save_dir=tmp_path, verbose=False)
+    val_scores, test_loss, test_per = tr.train(model, epochs=1, lr=1e-4, model_name='m')
+    assert len(val_scores) == 1 and np.isfinite(test_loss) and np.isfinite(test_per)
+    assert (tmp_path / 'm' / 'latest.ckpt').exists() and (tmp_path / 'm' / 'best.ckpt').exists()
+    st = torch.load(tmp_path / 'm' / 'latest.ckpt', map_location='cpu')
+    assert set(st) == {'model', 'optim'} and len(st['optim']['state']) == len(list(model.parameters()))
+    # resume: a fresh model picks the checkpoint up (trainer.py:110-120)
+    nb.set_seed(7)
+    model2 = nb.get_model([[0, 1], [1, 1, 0], [5, 0, 1, 1]], use_rnn=True, dropout_rate=0.1, gpu=0)
+    tr2 = nb.get_trainer(loaders, nb.get_loss(), gpus=[0], save_dir=tmp_path, verbose=False)
+    tr2.train(model2, epochs=0, lr=1e-4, model_name='m')
+    for k, v in model2.state_dict().items():
+        assert torch.equal(v.cpu(), st['model'][k]), k
+
+
+def test_long_mixed_length_utterances_fp32():
+    """cfg 5 shape class: long utterances, mixed lengths, one infeasible alignment (zero_infinity), odd frame counts."""
+    arch = [[3, 1], [0, 0, 1], [2, 1, 0, 0]]
+    B, T = 3, 1203
+    (audio, alen), (tg, tl) = nb.data.make_batch(B, T, seed=3, min_len=300, tgt_lo=40, tgt_hi=90)
+    alen[1] = 301                                   # 75 output frames for >= 40 labels: may be infeasible with repeats
+    tl[2] = min(int(tl[2]), tg.shape[1])
+    alen[2] = 4 * 20                                # 20 frames < target length -> infeasible -> zero loss / zero grad
+    model = build(arch, 'fp32').train()
+    tr = trainer(model)
+    tr.optimizer = nb.trainer.FusedAdam(model, lr=1e-4)
+    sd0 = M.build_state_dict(arch, seed=1235)
+    loss_ref, _, raw, total, _, _, logits_ref = M.train_step(sd0, arch, audio, alen, tg, tl, None)
+    with torch.no_grad():
+        model.eval()
+        assert rel64(model(audio.to(DEV)), logits_ref) < 1e-4
+        assert model(audio.to(DEV)).shape == (B, 301, 49)        # 1203 -> 602 -> 301
+        model.train()
+    loss, logp, out_len = tr.step(((audio, alen), (tg, tl)), training=True)
+    assert abs(loss.item() - loss_ref.item()) < 1e-4 * abs(loss_ref.item())
+    check_grads(model, raw, total)

@@ -207,11 +207,26 @@ int nbasr_greedy_per(const float* logp, int B, int T, int V, const int64_t* audi
 /* Optimiser tail of Trainer.step (trainer.py:221-225): regulariser 0.01*sum_i ||W_i||_F over the
  * PadConvRelu weights (segments), clip_grad_norm_(5), Adam(eps=1e-7).  Flat fp32 buffers of n
  * elements.  seg_off/seg_len (nseg, int64, device) delimit the regularised tensors.
+ * seg_chunks = sum_s ceil(seg_len[s]/16384) (grid size of the per-segment kernels).
  * state: [0]=step count (as float), [1]=lr, [2]=sum of squares scratch, [3]=clip coef,
  *        [4..4+nseg) per-segment sum of squares.  All on device, so the step is graph-replayable. */
 int nbasr_optim_step(float* param, float* grad, float* m, float* v, int64_t n, const int64_t* seg_off,
-                     const int64_t* seg_len, int nseg, float reg_coef, float max_norm, float beta1,
-                     float beta2, float eps, float* state, void* stream);
+                     const int64_t* seg_len, int nseg, int64_t seg_chunks, float reg_coef, float max_norm,
+                     float beta1, float beta2, float eps, float* state, void* stream);
+
+/* Batched operand refresh: ONE launch executes a device-resident table of pack jobs (what
+ * nbasr_convert / nbasr_pack_weight / nbasr_pack_gconv_mma / nbasr_pack_gconv_dgrad do one at a time).
+ * jobs: device array of n nbasr_pack_job; blocks: total 4096-element chunks = sum_j ceil(n_out_j / 4096). */
+typedef struct nbasr_pack_job {
+  int32_t kind;          /* 0 convert, 1 pack_weight, 2 pack_gconv_mma, 3 pack_gconv_dgrad */
+  int32_t out_dtype;
+  const float* src;
+  void* dst;
+  int64_t n_out;         /* output elements */
+  int32_t a[8];          /* kind 1: M,N,nq,t0,tstep ; kind 2: C,cpg,ktaps,transposed ; kind 3: C,cpg,ktaps */
+  int64_t s[3];          /* kind 1: ws_m, ws_n, ws_t */
+} nbasr_pack_job;
+int nbasr_pack_batch(const nbasr_pack_job* jobs, int n, int64_t blocks, void* stream);
 
 /* misc */
 int nbasr_fill_u32(uint32_t* p, uint32_t val, int64_t n, void* stream);

@@ -29,6 +29,10 @@ class Wgrad(C.Structure):
                 ('x_rs', _i64), ('nb', _i32), ('nr', _i32), ('M', _i32), ('N', _i32), ('dw', _vp), ('ldw', _i64), ('dbias', _vp)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [('kind', _i32), ('out_dtype', _i32), ('src', _vp), ('dst', _vp), ('n_out', _i64), ('a', _i32 * 8), ('s', _i64 * 3)]
+
+
 class GConv(C.Structure):
     _fields_ = [('dtype', _i32), ('x', _vp), ('B', _i32), ('T', _i32), ('Tp', _i32), ('C', _i32), ('cpg', _i32),
                 ('ktaps', _i32), ('off0', _i32), ('dstep', _i32), ('w', _vp), ('w_packed', _i32), ('epi', Epilogue)]
@@ -58,7 +62,8 @@ _SIGS = {
     'nbasr_ctc': [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp],
     'nbasr_greedy_per': [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp, _vp],
-    'nbasr_optim_step': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, C.c_int, _f32, _f32, _f32, _f32, _f32, _vp, _vp],
+    'nbasr_optim_step': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, C.c_int, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp],
+    'nbasr_pack_batch': [_vp, C.c_int, _i64, _vp],
     'nbasr_fill_u32': [_vp, C.c_uint32, _i64, _vp],
     'nbasr_version': [],
     'nbasr_sm_count': [],

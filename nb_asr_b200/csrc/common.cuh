@@ -107,13 +107,13 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
 // are plane-major bit arrays (mask_byte_addr): any 8-aligned column range is whole bytes of one entry.
 // ---------------------------------------------------------------------------------------------
 // compute half: bias, ReLU20 (+ gate bits), dropout, skip-sum.  m[g] = gate bits of column group g.
-template <int NV, bool FULL = false>
+template <int NV, bool FULL = false, bool NOBIAS = false>
 __device__ __forceinline__ void epilogue_compute(const nbasr_epilogue& e, int64_t rho, int c0, int nvalid_, float* v, uint32_t* m) {
   constexpr int NG = NV / 8;
   const int nvalid = FULL ? NV : nvalid_;   // FULL: every column valid -> all guards fold at compile time
 #pragma unroll
   for (int g = 0; g < NG; ++g) m[g] = 0xffu;
-  if (e.bias) {
+  if (!NOBIAS && e.bias) {
 #pragma unroll
     for (int i = 0; i < NV; ++i)
       if (i < nvalid) v[i] += __ldg(e.bias + c0 + i);

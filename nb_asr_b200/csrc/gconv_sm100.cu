@@ -121,11 +121,9 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       uint32_t phase = 0;
       for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes, ++it) {
         const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * GT;
-        GC_STAMP(0);
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_expect_tx(full_bar(stage), A_BYTES);
         tma_load_3d(asm0 + stage * A_BYTES, &tmX, full_bar(stage), c0, NBASR_PAD_L + t0 + p.off0, b);
-        GC_STAMP(1);
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
     }
@@ -169,8 +167,7 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     float bias_r[24];
 #pragma unroll
     for (int i = 0; i < 24; ++i) bias_r[i] = (p.epi.bias && i < nvalid) ? __ldg(p.epi.bias + cbeg + i) : 0.f;
-    nbasr_epilogue epi = p.epi;
-    epi.bias = nullptr;
+    const nbasr_epilogue& epi = p.epi;       // stays in the kernel-parameter bank (a local copy would live on the stack)
     int it = 0;
     for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes, ++it) {
       const int as = it % NACC;
@@ -187,21 +184,46 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));           // accumulator is in registers: release the TMEM stage early
+      if (etid == 0) GC_STAMP(6);
       const bool rowok = t < p.T;
       const int64_t rho = (int64_t)b * p.Tp + NBASR_PAD_L + t;
       uint32_t m[3] = {0, 0, 0};
       if (rowok) {
+        if (nvalid == 24 && epi.drop_p == 0.f && epi.n_add == 0) {
+          // lean path (every forward of a skip-free node, most input-gradients): ~6 instructions / element
 #pragma unroll
-        for (int i = 0; i < 24; ++i) v[i] += bias_r[i];
-        if (nvalid == 24) epilogue_compute<24, true>(epi, rho, cbeg, 24, v, m);
-        else epilogue_compute<24, false>(epi, rho, cbeg, nvalid, v, m);
+          for (int g = 0; g < 3; ++g) {
+            uint32_t mm = 0xffu;
+            if (epi.relu20) {
+              mm = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float z = v[g * 8 + i] + bias_r[g * 8 + i];
+                // 0 < z <= 20  <=>  bits(z) - 1 < bits(20.0f) as unsigned (negative z and +0 wrap to huge values)
+                mm |= ((__float_as_uint(z) - 1u) < 0x41A00000u) ? (1u << i) : 0u;
+                v[g * 8 + i] = fminf(fmaxf(z, 0.f), 20.f);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[g * 8 + i] += bias_r[g * 8 + i];
+            }
+            m[g] = mm;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 24; ++i) v[i] += bias_r[i];
+          if (nvalid == 24) epilogue_compute<24, true, true>(epi, rho, cbeg, 24, v, m);
+          else epilogue_compute<24, false, true>(epi, rho, cbeg, nvalid, v, m);
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 24; ++i) v[i] = 0.f;      // rows past the utterance land on zero pad rows / are clipped
       }
       // staging buffers are free once the previous tile's TMA stores have finished READING shared memory
+      if (etid == 0) GC_STAMP(0);
       if (etid == 0) bulk_wait_read0();
       named_bar_sync(1, NEPI);
+      if (etid == 0) GC_STAMP(7);
       uint8_t* orow = ost + row * OUTB + 48 * hh;
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
@@ -219,6 +241,7 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (epi.mask_out) mst[row * 8 + 3 * hh + g] = (g * 8 < nvalid) ? (uint8_t)m[g] : (uint8_t)0;   // 8-byte entry per row
       }
       fence_async_smem();
+      if (etid == 0) GC_STAMP(1);
       named_bar_sync(1, NEPI);
       if (epi.mask_out && etid < GT && t0 + etid < p.T) {
         // 128 consecutive 8-byte entries of this slab's mask plane: one fully coalesced store per warp

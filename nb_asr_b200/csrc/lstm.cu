@@ -73,15 +73,22 @@ __global__ void __launch_bounds__(L_NT, 1) lstm_fwd_kernel(LstmFwdArgs p) {
   const bool pair_ok = (pbl < BG) && (u0 + pul < H) && (b0 + pbl < p.B);
   float c_reg = 0.f;
   unsigned int* cnt = p.cnt + blockIdx.y;
+  // input projection of the NEXT step is fetched before the barrier wait (it does not depend on h)
+  float gx_next[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pair_ok && p.T > 0) {
+    const float* gxr = p.gx + ((int64_t)(b0 + pbl) * p.T) * H4;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) gx_next[g] = __ldg(gxr + g * H + u0 + pul);
+  }
 
   for (int t = 0; t < p.T; ++t) {
     // stage h_{t-1} of this batch group (zero for t = 0 and for the K padding)
     const float* hprev = p.hbuf + (int64_t)((t + 1) & 1) * p.B * H;
-    for (int idx = tid; idx < BG * L_KP; idx += L_NT) {
-      int bl = idx / L_KP, k = idx % L_KP;
-      float v = 0.f;
-      if (t > 0 && k < H && b0 + bl < p.B) v = __ldcg(hprev + (int64_t)(b0 + bl) * H + k);
-      h_s[idx] = v;
+    for (int idx = tid; idx < BG * (L_KP / 4); idx += L_NT) {
+      int bl = idx / (L_KP / 4), k = (idx % (L_KP / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t > 0 && k < H && b0 + bl < p.B) v = __ldcg(reinterpret_cast<const float4*>(hprev + (int64_t)(b0 + bl) * H + k));   // H % 4 == 0
+      *reinterpret_cast<float4*>(h_s + bl * L_KP + k) = v;
     }
     __syncthreads();
     for (int bl = 0; bl < BG; bl += 4) {
@@ -104,11 +111,10 @@ __global__ void __launch_bounds__(L_NT, 1) lstm_fwd_kernel(LstmFwdArgs p) {
     __syncthreads();
     if (pair_ok) {
       const int b = b0 + pbl, u = u0 + pul;
-      const float* gxr = p.gx + ((int64_t)b * p.T + t) * H4;
       float pre[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float s = gxr[g * H + u];
+        float s = gx_next[g];
 #pragma unroll
         for (int q = 0; q < L_KS; ++q) s += part[(q * L_ROWS + g * L_U + pul) * BGP + pbl];
         pre[g] = s;
@@ -124,6 +130,11 @@ __global__ void __launch_bounds__(L_NT, 1) lstm_fwd_kernel(LstmFwdArgs p) {
         float* gr = p.gates + ((int64_t)b * p.T + t) * H4;
         gr[u] = ig; gr[H + u] = fg; gr[2 * H + u] = gg; gr[3 * H + u] = og;
         p.cstate[((int64_t)b * p.T + t) * H + u] = c_reg;
+      }
+      if (t + 1 < p.T) {
+        const float* gxr = p.gx + ((int64_t)b * p.T + t + 1) * H4;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) gx_next[g] = __ldg(gxr + g * H + u);
       }
     }
     if (t + 1 < p.T) group_barrier(cnt, (unsigned)(t + 1) * nslices);
@@ -167,15 +178,26 @@ __global__ void __launch_bounds__(L_NT, 1) lstm_bwd_kernel(LstmBwdArgs p) {
   float dc_next = 0.f, dh_rec = 0.f;
   unsigned int* cnt = p.cnt + blockIdx.y;
 
+  // saved activations of the step are fetched one step ahead (they do not depend on the recurrence)
+  float nx[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dh_seq, i, f, g, o, c, c_prev
+  auto prefetch = [&](int t) {
+    const int b = b0 + pbl, u = u0 + pul;
+    nx[0] = __ldg(p.dh_seq + (int64_t)b * p.dh_bs + (int64_t)t * p.dh_rs + u);
+    const float* gr = p.gates + ((int64_t)b * p.T + t) * H4;
+    nx[1] = __ldg(gr + u); nx[2] = __ldg(gr + H + u); nx[3] = __ldg(gr + 2 * H + u); nx[4] = __ldg(gr + 3 * H + u);
+    nx[5] = __ldg(p.cstate + ((int64_t)b * p.T + t) * H + u);
+    nx[6] = t > 0 ? __ldg(p.cstate + ((int64_t)b * p.T + t - 1) * H + u) : 0.f;
+  };
+  if (pair_ok && p.T > 0) prefetch(p.T - 1);
+
   for (int step = 0; step < p.T; ++step) {
     const int t = p.T - 1 - step;
     if (pair_ok) {
       const int b = b0 + pbl, u = u0 + pul;
-      float dh = p.dh_seq[(int64_t)b * p.dh_bs + (int64_t)t * p.dh_rs + u] + dh_rec;
-      const float* gr = p.gates + ((int64_t)b * p.T + t) * H4;
-      float ig = gr[u], fg = gr[H + u], gg = gr[2 * H + u], og = gr[3 * H + u];
-      float c = p.cstate[((int64_t)b * p.T + t) * H + u];
-      float cprev = t > 0 ? p.cstate[((int64_t)b * p.T + t - 1) * H + u] : 0.f;
+      float dh = nx[0] + dh_rec;
+      float ig = nx[1], fg = nx[2], gg = nx[3], og = nx[4];
+      float c = nx[5];
+      float cprev = nx[6];
       float tc = tanhf(c);
       float dov = dh * tc;
       float dc = dc_next + dh * og * (1.f - tc * tc);
@@ -186,15 +208,16 @@ __global__ void __launch_bounds__(L_NT, 1) lstm_bwd_kernel(LstmBwdArgs p) {
       __stcg(dr + H + u, df * fg * (1.f - fg));
       __stcg(dr + 2 * H + u, dgv * (1.f - gg * gg));
       __stcg(dr + 3 * H + u, dov * og * (1.f - og));
+      if (t > 0) prefetch(t - 1);
     }
     if (t == 0) break;
     group_barrier(cnt, (unsigned)(step + 1) * nslices);
     // stage dgates_t of the batch group, then dh_rec[b][k] = sum_row dg[b][row] * W_hh[row][k]
-    for (int idx = tid; idx < BG * LB_RP; idx += L_NT) {
-      int bl = idx / LB_RP, row = idx % LB_RP;
-      float v = 0.f;
-      if (row < H4 && b0 + bl < p.B) v = __ldcg(p.dgx + ((int64_t)(b0 + bl) * p.T + t) * H4 + row);
-      dg_s[idx] = v;
+    for (int idx = tid; idx < BG * (LB_RP / 4); idx += L_NT) {
+      int bl = idx / (LB_RP / 4), row = (idx % (LB_RP / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < H4 && b0 + bl < p.B) v = __ldcg(reinterpret_cast<const float4*>(p.dgx + ((int64_t)(b0 + bl) * p.T + t) * H4 + row));
+      *reinterpret_cast<float4*>(dg_s + bl * LB_RP + row) = v;
     }
     __syncthreads();
     for (int bl = 0; bl < BG; bl += 4) {
@@ -238,7 +261,7 @@ extern "C" {
 int nbasr_lstm_fwd(const float* gx, const float* w_hh, int T, int B, int H, void* h_seq, int h_dtype, int64_t h_bs,
                    int64_t h_rs, int64_t ld_h, float* gates, float* cstate, float* hstate, float* work, void* stream) {
   (void)ld_h; (void)hstate;
-  NBASR_REQUIRE(H <= L_KP, "hidden size");
+  NBASR_REQUIRE(H <= L_KP && H % 4 == 0, "hidden size");
   int sms = nbasr_sm_count();
   int nslices = (H + L_U - 1) / L_U;
   int bg = pick_bg(B, sms, nslices, 32);
@@ -261,7 +284,7 @@ int nbasr_lstm_fwd(const float* gx, const float* w_hh, int T, int B, int H, void
 int nbasr_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, int64_t ld_dh, const float* w_hh,
                    const float* gates, const float* cstate, int T, int B, int H, float* dgx, float* work, void* stream) {
   (void)ld_dh;
-  NBASR_REQUIRE(4 * H <= LB_RP && H <= L_KP, "hidden size");
+  NBASR_REQUIRE(4 * H <= LB_RP && H <= L_KP && H % 4 == 0, "hidden size");
   int sms = nbasr_sm_count();
   int nslices = (H + L_U - 1) / L_U;
   int bg = pick_bg(B, sms, nslices, 16);

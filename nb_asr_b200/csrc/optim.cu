@@ -21,26 +21,41 @@ __device__ __forceinline__ float block_sum(float v) {
   return v;
 }
 
+// Regularised segments are cut into chunks of SEG_CHUNK elements; block b finds its (segment, chunk) by walking
+// the (<= 64) segment lengths -- big tensors get proportionally many blocks.
+constexpr int SEG_CHUNK = 16384;
+
+__device__ __forceinline__ bool seg_locate(const int64_t* __restrict__ len, int nseg, int64_t blk, int& s, int64_t& start) {
+  for (s = 0; s < nseg; ++s) {
+    int64_t nch = (len[s] + SEG_CHUNK - 1) / SEG_CHUNK;
+    if (blk < nch) { start = blk * SEG_CHUNK; return true; }
+    blk -= nch;
+  }
+  return false;
+}
+
 __global__ void seg_sumsq_kernel(const float* __restrict__ p, const int64_t* __restrict__ off, const int64_t* __restrict__ len,
-                                 float* __restrict__ state) {
-  int s = blockIdx.y;
+                                 int nseg, float* __restrict__ state) {
+  int s; int64_t start;
+  if (!seg_locate(len, nseg, blockIdx.x, s, start)) return;
   const float* x = p + off[s];
-  int64_t n = len[s];
+  int64_t end = min(len[s], start + SEG_CHUNK);
   float acc = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += x[i] * x[i];
+  for (int64_t i = start + threadIdx.x; i < end; i += blockDim.x) acc += x[i] * x[i];
   acc = block_sum(acc);
   if (threadIdx.x == 0 && acc != 0.f) atomicAdd(state + 4 + s, acc);
 }
 
 __global__ void reg_grad_kernel(const float* __restrict__ p, float* __restrict__ g, const int64_t* __restrict__ off,
-                                const int64_t* __restrict__ len, const float* __restrict__ state, float reg_coef) {
-  int s = blockIdx.y;
+                                const int64_t* __restrict__ len, int nseg, const float* __restrict__ state, float reg_coef) {
+  int s; int64_t start;
+  if (!seg_locate(len, nseg, blockIdx.x, s, start)) return;
   float nrm = sqrtf(state[4 + s]);
   float k = nrm > 0.f ? reg_coef / nrm : 0.f;
   const float* x = p + off[s];
   float* gg = g + off[s];
-  int64_t n = len[s];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) gg[i] += k * x[i];
+  int64_t end = min(len[s], start + SEG_CHUNK);
+  for (int64_t i = start + threadIdx.x; i < end; i += blockDim.x) gg[i] += k * x[i];
 }
 
 __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
@@ -59,7 +74,23 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   const float bc1 = 1.f - powf(b1, step);
   const float bc2s = sqrtf(1.f - powf(b2, step));
   const float step_size = lr / bc1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t n4 = n >> 2;   // flat buffers are padded to multiples of 64 elements
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+    float* gp = &g4.x; float* mp = &m4.x; float* vp = &v4.x; float* pp = &p4.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gi = gp[j] * coef;
+      mp[j] = b1 * mp[j] + (1.f - b1) * gi;
+      vp[j] = b2 * vp[j] + (1.f - b2) * gi * gi;
+      pp[j] -= step_size * mp[j] / (sqrtf(vp[j]) / bc2s + eps);
+    }
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i] * coef;
     float mi = b1 * m[i] + (1.f - b1) * gi;
     float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -79,14 +110,15 @@ __global__ void optim_finish_kernel(float* state, int nseg, float max_norm) {
 }  // namespace
 
 extern "C" int nbasr_optim_step(float* param, float* grad, float* m, float* v, int64_t n, const int64_t* seg_off,
-                                const int64_t* seg_len, int nseg, float reg_coef, float max_norm, float beta1, float beta2,
-                                float eps, float* state, void* stream) {
+                                const int64_t* seg_len, int nseg, int64_t seg_chunks, float reg_coef, float max_norm, float beta1,
+                                float beta2, float eps, float* state, void* stream) {
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(state + 2, 0, sizeof(float) * (2 + nseg), st);
   if (nseg > 0 && reg_coef != 0.f) {
-    seg_sumsq_kernel<<<dim3(32, nseg), 256, 0, st>>>(param, seg_off, seg_len, state);
+    // seg_chunks = sum_s ceil(seg_len[s] / 16384), computed once by the host that owns the segment table
+    seg_sumsq_kernel<<<(unsigned)seg_chunks, 256, 0, st>>>(param, seg_off, seg_len, nseg, state);
     NBASR_CHECK_LAUNCH();
-    reg_grad_kernel<<<dim3(32, nseg), 256, 0, st>>>(param, grad, seg_off, seg_len, state, reg_coef);
+    reg_grad_kernel<<<(unsigned)seg_chunks, 256, 0, st>>>(param, grad, seg_off, seg_len, nseg, state, reg_coef);
     NBASR_CHECK_LAUNCH();
   }
   sumsq_kernel<<<592, 256, 0, st>>>(grad, n, state + 2);

@@ -113,7 +113,9 @@ class Engine:
         self.opt_state = torch.zeros(8 + len(reg), dtype=torch.float32, device=dev)
         self.drop_step = torch.zeros(1, dtype=torch.int64, device=dev)
         self._bound_ptr = (self.params[0].data_ptr(), dev)
+        self.seg_chunks = int(sum((l + 16383) // 16384 for _, l in reg))
         self._build_packs()
+        self._compile_pack_jobs()
         self.plans = {}
         self._pack_version = None
 
@@ -216,6 +218,37 @@ class Engine:
             idx += 1
         self.head_name = f'model.{idx}'
 
+    def _compile_pack_jobs(self):
+        """Translate the per-buffer pack calls into one device-resident job table (single launch per refresh)."""
+        import ctypes as C_
+        lib = self.lib
+        kinds = {lib.nbasr_convert: 0, lib.nbasr_pack_weight: 1, lib.nbasr_pack_gconv_mma: 2, lib.nbasr_pack_gconv_dgrad: 3}
+        jobs = (_lib.PackJob * len(self.pack_ops))()
+        blocks = 0
+        for j, (fn, a) in zip(jobs, self.pack_ops):
+            j.kind = [k for f, k in kinds.items() if f is fn][0]
+            if j.kind == 0:
+                src, dst, odt, n = a
+                j.src, j.dst, j.out_dtype, j.n_out = src, dst, odt, n
+            elif j.kind == 1:
+                src, dst, odt, M, N, nq, t0, ts, wm, wn, wt = a
+                j.src, j.dst, j.out_dtype, j.n_out = src, dst, odt, N * nq * M
+                j.a[0], j.a[1], j.a[2], j.a[3], j.a[4] = M, N, nq, t0, ts
+                j.s[0], j.s[1], j.s[2] = wm, wn, wt
+            elif j.kind == 2:
+                src, dst, Cc, cpg, k, tr_ = a
+                j.src, j.dst, j.out_dtype = src, dst, BF16
+                j.n_out = int(lib.nbasr_gconv_mma_pack_elems(Cc, cpg, k))
+                j.a[0], j.a[1], j.a[2], j.a[3] = Cc, cpg, k, tr_
+            else:
+                src, dst, Cc, cpg, k = a
+                j.src, j.dst, j.out_dtype, j.n_out = src, dst, F32, Cc * cpg * k
+                j.a[0], j.a[1], j.a[2] = Cc, cpg, k
+            blocks += (j.n_out + 4095) // 4096
+        raw = bytes(jobs)
+        self.pack_jobs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        self.pack_njobs, self.pack_blocks = len(self.pack_ops), blocks
+
     def _param_version(self):
         return sum(p._version for p in self.params)
 
@@ -224,9 +257,9 @@ class Engine:
         if not force and v == self._pack_version:
             return
         st = torch.cuda.current_stream().cuda_stream
-        for fn, args in self.pack_ops:
-            _lib.check(fn(*args, st), 'pack')
-        self.launches += len(self.pack_ops)
+        if self.pack_njobs:
+            _lib.check(self.lib.nbasr_pack_batch(self.pack_jobs.data_ptr(), self.pack_njobs, self.pack_blocks, st), 'pack_batch')
+            self.launches += 1
         if self.model.use_rnn:
             off_i, n = self.slices[self.lstm_name + '.bias_ih_l0']
             off_h, _ = self.slices[self.lstm_name + '.bias_hh_l0']
@@ -663,7 +696,7 @@ class Engine:
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.nbasr_optim_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.adam_m.data_ptr(),
                                              self.adam_v.data_ptr(), self.n_flat, self.seg_off.data_ptr(),
-                                             self.seg_len.data_ptr(), int(self.seg_off.numel()), reg_coef, max_norm,
+                                             self.seg_len.data_ptr(), int(self.seg_off.numel()), self.seg_chunks, reg_coef, max_norm,
                                              betas[0], betas[1], eps, self.opt_state.data_ptr(), st), 'optim')
         self.launches += 5 if self.seg_off.numel() else 3
         self.refresh_packs(force=True)

@@ -368,7 +368,8 @@ def test_optim_step_matches_reference_formulas():
         vr = 0.999 * vr + 0.001 * gr * gr
         pr = pr - (1e-3 / (1 - 0.9 ** step)) * mr / (vr.sqrt() / math.sqrt(1 - 0.999 ** step) + 1e-7)
         _lib.check(lib.nbasr_optim_step(pd.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, so.data_ptr(), sl.data_ptr(), 2,
-                                        0.01, 5.0, 0.9, 0.999, 1e-7, state.data_ptr(), U.stream()))
+                                        sum((l + 16383) // 16384 for _, l in segs), 0.01, 5.0, 0.9, 0.999, 1e-7, state.data_ptr(),
+                                        U.stream()))
         torch.cuda.synchronize()
         assert U.relerr(pd.cpu(), pr) < 1e-6
         assert abs(state[3].item() - coef) < 1e-5 * coef

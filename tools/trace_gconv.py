@@ -41,9 +41,9 @@ for name, kw in (('full', dict(bias=bias, relu=1, out=out, mask_out=mask, mask_w
     t0 = int(t[t > 0].min())
     print('=== variant', name)
     for cta in (0, 1):
-        print(f'CTA {cta}: tile | prod_wait_start prod_issued | mma_tempty_ok mma_full_ok | epi_start epi_end   (us since first stamp)')
-        for it in range(26):
+        print(f'CTA {cta}: tile | compute_done fence_done | mma_tempty_ok mma_full_ok | epi_start epi_end | tmem_ld_done bar1_done  (us since first stamp)')
+        for it in range(10, 16):
             r = t[cta, it]
             if r[1] == 0:
                 break
-            print(f'  {it:3d} | ' + ' '.join(f'{(int(v) - t0) / 1e3:8.2f}' if v > 0 else '     -  ' for v in r[:6]))
+            print(f'  {it:3d} | ' + ' '.join(f'{(int(v) - t0) / 1e3:8.2f}' if v > 0 else '     -  ' for v in r[:8]))

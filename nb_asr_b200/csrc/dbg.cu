@@ -3,6 +3,8 @@
 // mode 0: K-major A tile of (128+pad) rows x 64 bf16; D[m][n] = sum_k A[m+shift][k] * B[n][k]
 // mode 1: MN-major: D[m][n] = sum_{k<64} Y[k][m] * X[k+shift][n]   (Y: 64 x 128, X: (64+pad) x 64)
 // bo_mode 0: base_offset field = 0; 1: base_offset = (start_addr >> 7) & 7.
+// mode 2: B operand in the NO-SWIZZLE K-major canonical layout [k-chunk of 8][row group][8 rows][8 elems], N = 16,
+//         K = 64, filled by plain st.shared (the LSTM kernel's h operand): D[m][n] = sum_k A[m][k] * B[n][k]
 #include "common.cuh"
 #include "kernels.h"
 #include "sm100_ptx.cuh"
@@ -35,8 +37,22 @@ dbg_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tm = *tptr;
+  if (mode == 2) {
+    // B (16 x 64 bf16, row-major in global, passed via D's neighbour pointer trick: tmB unused) -> canonical layout
+    const bf16* Bg = reinterpret_cast<const bf16*>(D + 128 * 64);
+    bf16* bs = reinterpret_cast<bf16*>(al + 32768);
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+      int n = i / 64, k = i % 64;
+      bs[((k >> 3) * 2 + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7)] = Bg[i];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
-    if (mode == 0) {
+    if (mode == 2) {
+      mbar_expect_tx(bar, 128 * 128);
+      tma_load_2d(sa, &tmA, bar, 0, 0);
+    } else if (mode == 0) {
       mbar_expect_tx(bar, (128 + PADROWS) * 128 + 64 * 128);
       tma_load_2d(sa, &tmA, bar, 0, 0);
       tma_load_2d(sb, &tmB, bar, 0, 0);
@@ -50,6 +66,13 @@ dbg_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tcgen05_fence_after();
     for (int k = 0; k < 4; ++k) {
       uint64_t ad, bd;
+      if (mode == 2) {
+        ad = make_smem_desc(sa + k * 32, 16, 1024);
+        // no swizzle: layout type 0; LBO = distance between K-adjacent 8x16B core matrices, SBO = between row groups
+        bd = make_smem_desc(sb + k * 512, shift ? 128 : 256, shift ? 256 : 128) & ~((uint64_t)7 << 61);
+        umma_bf16(tm, ad, bd, make_idesc(128, 16, 0, 0), k != 0);
+        continue;
+      }
       if (mode == 0) {
         uint32_t a0 = sa + shift * 128 + k * 32;
         ad = make_smem_desc(a0, 16, 1024, bo_mode ? (a0 >> 7) & 7 : 0);
@@ -79,7 +102,13 @@ dbg_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 extern "C" int nbasr_dbg_shift(const void* A, const void* B, float* D, int mode, int shift, int bo_mode, void* stream) {
   CUtensorMap tmA, tmB;
-  if (mode == 0) {
+  if (mode == 2) {
+    uint64_t da[2] = {64, 128};
+    int64_t sa[2] = {1, 64};
+    uint32_t ba[2] = {64, 128};
+    if (sm100_get_map(A, 2, da, sa, ba, &tmA)) return 1;
+    tmB = tmA;
+  } else if (mode == 0) {
     uint64_t da[2] = {64, 128 + PADROWS};
     int64_t sa[2] = {1, 64};
     uint32_t ba[2] = {64, 128 + PADROWS};

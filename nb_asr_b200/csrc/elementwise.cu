@@ -67,97 +67,52 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
   }
 }
 
-// Backward.  Each warp owns a private multi-stage ring in shared memory that 1-D bulk copies (TMA,
-// cp.async.bulk + mbarrier) fill with whole (x, dy) rows several rows ahead: memory-level parallelism comes
-// from the copy engine instead of from warp count, rows are read from smem twice (statistics, then output)
-// and the registers hold the dgamma / dbeta partials of the lane's channels.
-__device__ __forceinline__ uint32_t ln_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void ln_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void ln_mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LN_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra LN_DONE;\n"
-      "bra LN_WAIT;\n"
-      "LN_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-
-template <typename T, int NST>
-__global__ void __launch_bounds__(256, 1) layernorm_bwd_kernel(
+// Backward: per-warp rows, dgamma/dbeta partials live in warp-private shared memory (layout [i][group] so
+// that the 32 lanes of a warp hit 32 different banks), which keeps registers low enough for 16 warps / SM.
+template <typename T>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
     const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean_i,
     const float* __restrict__ rstd_i, const float* __restrict__ gamma, int B, int Tt, int Tp, int C,
     T* __restrict__ dx, T* __restrict__ dx2, const uint32_t* __restrict__ mask2, float scale2, int64_t mask_rows, int mask2_w,
     float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ __align__(128) uint8_t lnsm[];
+  extern __shared__ float red[];  // 8 warps x 2 x (8 x GP) floats, GP = padded group count
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int ngroups = C >> 3;
+  const int GP = 32 * LN_MAXG;
   const int64_t nrows = (int64_t)B * Tt;
-  const uint32_t row_bytes = (uint32_t)C * sizeof(T);
-  const uint32_t stage_bytes = 2 * row_bytes;                      // x row then dy row
-  uint8_t* ring = lnsm + (size_t)wib * NST * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lnsm + (size_t)8 * NST * stage_bytes) + wib * NST;
-  float* red = reinterpret_cast<float*>(lnsm + (size_t)8 * NST * stage_bytes + 8 * NST * 8);   // 2*C floats, block reduction
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
-  if (lane == 0) {
-    for (int s = 0; s < NST; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ln_smem_u32(bars + s)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  auto row_of = [&](int64_t r) { return (int64_t)(r / Tt) * Tp + NBASR_PAD_L + (r % Tt); };
-  auto issue = [&](int64_t r, int s) {          // lane 0 only
-    const uint32_t bar = ln_smem_u32(bars + s);
-    const int64_t rho = row_of(r);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes) : "memory");
-    ln_bulk_load(ln_smem_u32(ring + (size_t)s * stage_bytes), x + rho * C, row_bytes, bar);
-    ln_bulk_load(ln_smem_u32(ring + (size_t)s * stage_bytes + row_bytes), dy + rho * C, row_bytes, bar);
-  };
-  float dg[LN_MAXG][8], db[LN_MAXG][8], ga[LN_MAXG][8];
+  float* my_dg = red + (size_t)wib * 2 * 8 * GP;
+  float* my_db = my_dg + 8 * GP;
+  for (int i = lane; i < 2 * 8 * GP; i += 32) my_dg[i] = 0.f;
+  __syncwarp();
+  // plane-major gate-bit mask: per-lane byte offsets are row independent up to "+ rho * entry_bytes"
+  int64_t moff[LN_MAXG];
+  const int meb = (mask2_w == 32) ? 4 : 8;
 #pragma unroll
-  for (int q = 0; q < LN_MAXG; ++q) {
-    int g = lane + 32 * q;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dg[q][i] = db[q][i] = ga[q][i] = 0.f;
-    if (g < ngroups) load8(gamma + g * 8, ga[q]);
-  }
-  if (lane == 0)
-    for (int s = 0; s < NST; ++s) {
-      int64_t r = warp + (int64_t)s * nwarps;
-      if (r < nrows) issue(r, s);
-    }
-  int st = 0;
-  uint32_t ph = 0;
+  for (int q = 0; q < LN_MAXG; ++q) moff[q] = mask_byte_addr(0, (lane + 32 * q) * 8, mask2_w, mask_rows);
   for (int64_t r = warp; r < nrows; r += nwarps) {
-    const int64_t rho = row_of(r);
-    const float mean = mean_i[rho], rstd = rstd_i[rho];
-    ln_mbar_wait(ln_smem_u32(bars + st), ph);
-    const T* xs = reinterpret_cast<const T*>(ring + (size_t)st * stage_bytes);
-    const T* ds = reinterpret_cast<const T*>(ring + (size_t)st * stage_bytes + row_bytes);
+    int b = (int)(r / Tt), t = (int)(r % Tt);
+    int64_t rho = (int64_t)b * Tp + NBASR_PAD_L + t;
+    float mean = mean_i[rho], rstd = rstd_i[rho];
+    float xh[LN_MAXG][8], gy[LN_MAXG][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int q = 0; q < LN_MAXG; ++q) {
       int g = lane + 32 * q;
       if (g < ngroups) {
-        float xv[8], dv[8];
-        load8(xs + g * 8, xv);
-        load8(ds + g * 8, dv);
+        float xv[8], dv[8], ga[8];
+        load8(x + rho * C + g * 8, xv);
+        load8(dy + rho * C + g * 8, dv);
+        load8(gamma + g * 8, ga);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float xh = (xv[i] - mean) * rstd;
-          dg[q][i] += dv[i] * xh;
-          db[q][i] += dv[i];
-          float gy = dv[i] * ga[q][i];
-          s1 += gy;
-          s2 += gy * xh;
+          xh[q][i] = (xv[i] - mean) * rstd;
+          my_dg[i * GP + g] += dv[i] * xh[q][i];
+          my_db[i * GP + g] += dv[i];
+          gy[q][i] = dv[i] * ga[i];
+          s1 += gy[q][i];
+          s2 += gy[q][i] * xh[q][i];
         }
       }
     }
@@ -167,17 +122,12 @@ __global__ void __launch_bounds__(256, 1) layernorm_bwd_kernel(
     for (int q = 0; q < LN_MAXG; ++q) {
       int g = lane + 32 * q;
       if (g < ngroups) {
-        float xv[8], dv[8], o[8];
-        load8(xs + g * 8, xv);
-        load8(ds + g * 8, dv);
+        float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float xh = (xv[i] - mean) * rstd;
-          o[i] = rstd * (dv[i] * ga[q][i] - s1 - xh * s2);
-        }
+        for (int i = 0; i < 8; ++i) o[i] = rstd * (gy[q][i] - s1 - xh[q][i] * s2);
         if (dx) store8(dx + rho * C + g * 8, o);
         if (dx2) {
-          uint32_t w = mask2 ? reinterpret_cast<const uint8_t*>(mask2)[mask_byte_addr(rho, g * 8, mask2_w, mask_rows)] : 0xffu;
+          uint32_t w = mask2 ? reinterpret_cast<const uint8_t*>(mask2)[moff[q] + rho * meb] : 0xffu;
           float o2[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) o2[i] = ((w >> i) & 1u) ? o[i] * scale2 : 0.f;
@@ -185,30 +135,19 @@ __global__ void __launch_bounds__(256, 1) layernorm_bwd_kernel(
         }
       }
     }
-    // the stage is consumed: refill it with the row NST iterations ahead (generic reads -> async write)
-    __syncwarp();
-    const int64_t rn = r + (int64_t)NST * nwarps;
-    if (lane == 0 && rn < nrows) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(rn, st);
-    }
-    if (++st == NST) { st = 0; ph ^= 1; }
-  }
-#pragma unroll
-  for (int q = 0; q < LN_MAXG; ++q) {
-    int g = lane + 32 * q;
-    if (g < ngroups) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(&red[g * 8 + i], dg[q][i]);
-        atomicAdd(&red[C + g * 8 + i], db[q][i]);
-      }
-    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(dgamma + i, red[i]);
-    atomicAdd(dbeta + i, red[C + i]);
+  // block reduction over the 8 warps, then one atomic per channel per block
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c >> 3, i = c & 7;
+    float a = 0.f, bsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += red[(size_t)w * 2 * 8 * GP + i * GP + g];
+      bsum += red[(size_t)w * 2 * 8 * GP + 8 * GP + i * GP + g];
+    }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, bsum);
   }
 }
 
@@ -342,22 +281,19 @@ int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* m
                         float scale2, int64_t mask_rows, int mask2_w, float* dgamma, float* dbeta, void* stream) {
   NBASR_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_MAXG, "C");
   int64_t rows = (int64_t)B * T;
-  int blocks = (int)std::min<int64_t>((rows + 7) / 8, nbasr_sm_count());
+  int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 2);
   if (blocks < 1) return 0;
-  const int nst_bf16 = 3, nst_f32 = 2;
+  size_t sm = (size_t)8 * 2 * 8 * 32 * LN_MAXG * sizeof(float);   // 80 KB
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, nst_bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(layernorm_bwd_kernel<float, nst_f32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(layernorm_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr = true;
   }
-  if (dtype == NBASR_BF16) {
-    size_t sm = (size_t)8 * nst_bf16 * 2 * C * 2 + 8 * nst_bf16 * 8 + (size_t)2 * C * 4;
-    layernorm_bwd_kernel<bf16, nst_bf16><<<blocks, 256, sm, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, B, T, Tp, C, (bf16*)dx, (bf16*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta);
-  } else {
-    size_t sm = (size_t)8 * nst_f32 * 2 * C * 4 + 8 * nst_f32 * 8 + (size_t)2 * C * 4;
-    layernorm_bwd_kernel<float, nst_f32><<<blocks, 256, sm, as_stream(stream)>>>((const float*)dy, (const float*)x, mean, rstd, gamma, B, T, Tp, C, (float*)dx, (float*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta);
-  }
+  if (dtype == NBASR_BF16)
+    layernorm_bwd_kernel<bf16><<<blocks, 256, sm, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, B, T, Tp, C, (bf16*)dx, (bf16*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta);
+  else
+    layernorm_bwd_kernel<float><<<blocks, 256, sm, as_stream(stream)>>>((const float*)dy, (const float*)x, mean, rstd, gamma, B, T, Tp, C, (float*)dx, (float*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta);
   NBASR_CHECK_LAUNCH();
   return 0;
 }

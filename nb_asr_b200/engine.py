@@ -222,11 +222,11 @@ class Engine:
         """Translate the per-buffer pack calls into one device-resident job table (single launch per refresh)."""
         import ctypes as C_
         lib = self.lib
-        kinds = {lib.nbasr_convert: 0, lib.nbasr_pack_weight: 1, lib.nbasr_pack_gconv_mma: 2, lib.nbasr_pack_gconv_dgrad: 3}
+        kinds = {'nbasr_convert': 0, 'nbasr_pack_weight': 1, 'nbasr_pack_gconv_mma': 2, 'nbasr_pack_gconv_dgrad': 3}
         jobs = (_lib.PackJob * len(self.pack_ops))()
         blocks = 0
         for j, (fn, a) in zip(jobs, self.pack_ops):
-            j.kind = [k for f, k in kinds.items() if f is fn][0]
+            j.kind = kinds[fn.__name__]
             if j.kind == 0:
                 src, dst, odt, n = a
                 j.src, j.dst, j.out_dtype, j.n_out = src, dst, odt, n

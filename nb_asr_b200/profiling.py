@@ -25,7 +25,8 @@ def op_work(fn_name, args, es):
         rows = g.nb * g.nr
         flops = 2.0 * rows * g.K * g.N
         a_cols = min(g.K, g.a_rs) if g.a_rs > 0 else g.K      # overlapping rows are read once
-        byts = rows * a_cols * es + g.N * g.K * es + rows * g.N * es * (1 + g.epi.n_add)
+        n_o = g.epi.n_add + (1 if g.epi.out else 0) + (1 if g.epi.out2 else 0)
+        byts = rows * a_cols * es + g.N * g.K * es + rows * g.N * es * n_o
         return f'gemm_tn K={g.K} N={g.N}', flops, byts
     if fn_name == 'nbasr_gemm_wgrad':
         w = _struct_of(args[0], Wgrad)
@@ -37,7 +38,9 @@ def op_work(fn_name, args, es):
     if fn_name == 'nbasr_gconv_fwd':
         g = _struct_of(args[0], GConv)
         el = g.B * g.T * g.C
-        return f'gconv C={g.C} k={g.ktaps} d={g.dstep}', 2.0 * el * g.cpg * g.ktaps, el * es * (2 + g.epi.n_add)
+        n_t = 1 + g.epi.n_add + (1 if g.epi.out else 0) + (1 if g.epi.out2 else 0)     # tensors read/written once
+        n_m = (1 if g.epi.mask_out else 0) + (1 if g.epi.mask2 else 0)                 # 1 bit / element each
+        return f'gconv C={g.C} k={g.ktaps} d={g.dstep}', 2.0 * el * g.cpg * g.ktaps, el * es * n_t + el * n_m / 8.0
     if fn_name == 'nbasr_gconv_wgrad':
         dt, dz, x, B, T, Tp, Cc, cpg, k = args[:9]
         el = B * T * Cc

@@ -30,3 +30,15 @@ for mode in (0, 1):
             err = float((D - ref).norm() / ref.norm())
             res.append(f'{shift}:{err:.1e}')
         print(f'mode {mode} base_offset_mode {bo}:', ' '.join(res), flush=True)
+
+# mode 2: no-swizzle K-major B operand (N=16, K=64); "shift" selects the LBO/SBO assignment under test
+A = torch.randn(128, 64, device=dev).bfloat16()
+Bm = torch.randn(16, 64, device=dev).bfloat16()
+for variant in (0, 1):
+    buf = torch.zeros(128 * 64 + 16 * 32, device=dev)          # D followed by the bf16 B matrix
+    buf[128 * 64:].view(torch.bfloat16)[:16 * 64] = Bm.flatten()
+    rc = f(A.data_ptr(), None, buf.data_ptr(), 2, variant, 0, None)
+    torch.cuda.synchronize()
+    D = buf[:128 * 64].view(128, 64)[:, :16]
+    ref = A.float() @ Bm.float().t()
+    print(f'mode 2 (no-swizzle B) variant {variant} [0: LBO=K-stride 256, SBO=row-group 128 | 1: swapped]: err {float((D - ref).norm() / ref.norm()):.2e}', flush=True)

@@ -168,8 +168,11 @@ int nbasr_convert(const float* src, void* dst, int dst_dtype, int64_t n, void* s
  * Outputs: h_seq (B, Tp?, ld_h) act dtype written at row b*h_bs + t*h_rs; saves gates (B,T,4H)
  * post-activation and c (B,T,H) for BPTT.  work: 2*B*H floats (h ping-pong). Cooperative launch. */
 int nbasr_lstm_fwd(const float* gx, const float* w_hh, int T, int B, int H, void* h_seq, int h_dtype,
-                   int64_t h_bs, int64_t h_rs, int64_t ld_h, float* gates, float* cstate, float* hstate,
-                   float* work, void* stream);
+                   int64_t h_bs, int64_t h_rs, int64_t ld_h, float* gates, float* cstate,
+                   const void* w_hh_packed, float* work, void* stream);
+/* w_hh_packed (optional): bf16 [16][gate*32+unit][512] pack of W_hh (nbasr_pack_batch kind 4).  When given and
+ * h_dtype is BF16 the recurrence runs on tcgen05 tensor cores in 16-CTA clusters (bf16 h / W_hh operands, fp32
+ * accumulation, gates and cell state); otherwise the fp32 SIMT kernel is used. */
 /* BPTT: dh_seq (same addressing as h_seq, fp32) -> dgx (B,T,4H) fp32 (gradient of gx).
  * dW_hh / dW_ih / biases then follow from nbasr_gemm_wgrad / nbasr_colsum over dgx. */
 int nbasr_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, int64_t ld_dh, const float* w_hh,
@@ -218,7 +221,7 @@ int nbasr_optim_step(float* param, float* grad, float* m, float* v, int64_t n, c
  * nbasr_convert / nbasr_pack_weight / nbasr_pack_gconv_mma / nbasr_pack_gconv_dgrad do one at a time).
  * jobs: device array of n nbasr_pack_job; blocks: total 4096-element chunks = sum_j ceil(n_out_j / 4096). */
 typedef struct nbasr_pack_job {
-  int32_t kind;          /* 0 convert, 1 pack_weight, 2 pack_gconv_mma, 3 pack_gconv_dgrad */
+  int32_t kind;          /* 0 convert, 1 pack_weight, 2 pack_gconv_mma, 3 pack_gconv_dgrad, 4 LSTM W_hh cluster pack (a[0]=H) */
   int32_t out_dtype;
   const float* src;
   void* dst;

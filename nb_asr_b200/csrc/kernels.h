@@ -34,3 +34,7 @@ int sm100_get_map(const void* base, int rank, const uint64_t* dims, const int64_
 int sm100_gconv_fwd(const nbasr_gconv* p, cudaStream_t st);
 int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C, int cpg, int ktaps, int off0, int dstep,
                       float* dw, float* dbias, cudaStream_t st);
+
+// cluster / tcgen05 LSTM recurrence (lstm_sm100.cu)
+int sm100_lstm_fwd(const float* gx, const void* w_packed, int T, int B, int H, void* h_seq, int h_dtype, int64_t h_bs, int64_t h_rs,
+                   float* gates, float* cstate, cudaStream_t st);

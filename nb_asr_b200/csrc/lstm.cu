@@ -259,8 +259,10 @@ int pick_bg(int B, int sms, int nslices, int max_bg) {
 extern "C" {
 
 int nbasr_lstm_fwd(const float* gx, const float* w_hh, int T, int B, int H, void* h_seq, int h_dtype, int64_t h_bs,
-                   int64_t h_rs, int64_t ld_h, float* gates, float* cstate, float* hstate, float* work, void* stream) {
-  (void)ld_h; (void)hstate;
+                   int64_t h_rs, int64_t ld_h, float* gates, float* cstate, const void* hstate, float* work, void* stream) {
+  (void)ld_h;
+  if (hstate && h_dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT"))   // bf16 mode: tensor-core cluster kernel
+    return sm100_lstm_fwd(gx, hstate, T, B, H, h_seq, h_dtype, h_bs, h_rs, gates, cstate, as_stream(stream));
   NBASR_REQUIRE(H <= L_KP && H % 4 == 0, "hidden size");
   int sms = nbasr_sm_count();
   int nslices = (H + L_U - 1) / L_U;

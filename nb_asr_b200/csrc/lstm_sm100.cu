@@ -1,0 +1,231 @@
+// LSTM recurrence on tcgen05 tensor cores with thread-block clusters (bf16 mode).
+//
+// One cluster of 16 CTAs per group of 16 utterances.  CTA j owns hidden units [32j, 32j+32): its 128 gate
+// rows (i,f,g,o x 32 units) of W_hh stay in shared memory for the whole sequence (128 x 512 bf16 = 128 KB,
+// K-major, 128B swizzle, TMA-loaded once).  Per time step
+//     D[128 gate rows x 16 utterances] = W_slice[128 x 512] * h_{t-1}^T[512 x 16]
+// is 32 tcgen05.mma (M=128, N=16, K=16) into TMEM; 4 epilogue warps read the accumulator, add the input
+// projection, apply the gates (fp32, cell state in registers), and the CTA's new h slice (32 units x 16
+// utterances, bf16) is pushed into the h-operand buffer of ALL 16 CTAs of the cluster with one 1-KB
+// cp.async.bulk (smem -> distributed smem) per destination.  The h operand uses the un-swizzled K-major
+// canonical layout [k-chunk][row group][8 rows][8 elems] in which a CTA's slice is one contiguous KB; each
+// destination's mbarrier counts the 16 KB it expects, so data arrival IS the inter-CTA synchronisation --
+// there is no cluster barrier and no global-memory round trip inside the time loop.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int LC_NCTA = 16;
+constexpr int LC_U = 32;
+constexpr int LC_BG = 16;
+constexpr int LC_KP = 512;
+constexpr int LC_W_BYTES = 128 * LC_KP * 2;      // 131072
+constexpr int LC_H_BYTES = LC_BG * LC_KP * 2;    // 16384
+constexpr int LC_SLICE = LC_U * LC_BG * 2;       // 1024: one CTA's h slice
+constexpr int LC_PRE_LD = 17;
+constexpr int LC_THREADS = 160;                  // warp 0: control (TMA, MMA), warps 1-4: epilogue
+constexpr int LC_SMEM = LC_W_BYTES + 2 * LC_H_BYTES + 2 * LC_SLICE + 128 * LC_PRE_LD * 4 + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+struct LstmCArgs {
+  const float* gx;     // (B, T, 4H)
+  int T, B, H;
+  void* h_seq;
+  int h_dtype;
+  int64_t h_bs, h_rs;
+  float* gates;        // (B, T, 4H)
+  float* cstate;       // (B, T, H)
+};
+
+__global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LstmCArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t wsm = base;
+  const uint32_t hsm = base + LC_W_BYTES;                         // 2 buffers
+  const uint32_t stg = hsm + 2 * LC_H_BYTES;                      // 2 x 1 KB staging of the own slice
+  uint8_t* stg_p = al + LC_W_BYTES + 2 * LC_H_BYTES;
+  float* pre_s = reinterpret_cast<float*>(al + LC_W_BYTES + 2 * LC_H_BYTES + 2 * LC_SLICE);
+  const uint32_t bar0 = stg + 2 * LC_SLICE + 128 * LC_PRE_LD * 4;
+  const uint32_t wbar = bar0, mma_bar = bar0 + 8;
+  auto hfull = [&](int b) { return bar0 + 16 + 8u * b; };
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(al + LC_W_BYTES + 2 * LC_H_BYTES + 2 * LC_SLICE + 128 * LC_PRE_LD * 4 + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t j = cluster_ctarank();
+  const int cluster_id = blockIdx.x / LC_NCTA;
+  const int b0 = cluster_id * LC_BG;
+  const int H = p.H, H4 = 4 * p.H;
+
+  // zero both h operand buffers (h_{-1} = 0; K padding stays 0 because invalid units always send 0)
+  for (int i = threadIdx.x; i < 2 * LC_H_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(al + LC_W_BYTES)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmW);
+    mbar_init(wbar, 1);
+    mbar_init(mma_bar, 1);
+    mbar_init(hfull(0), 1);
+    mbar_init(hfull(1), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tptr), 32);
+  fence_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  cluster_sync_all();                     // every CTA's barriers / buffers are ready before any remote traffic
+  const uint32_t tm = *tptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wbar, LC_W_BYTES);
+      for (int kb = 0; kb < 8; ++kb) tma_load_2d(wsm + kb * 16384, &tmW, wbar, kb * 64, (int)j * 128);
+      const uint32_t idesc = make_idesc(128, LC_BG, 0, 0);
+      mbar_wait(wbar, 0);
+      for (int t = 0; t < p.T; ++t) {
+        const int pb = t & 1;
+        if (t + 1 < p.T) mbar_expect_tx(hfull(pb ^ 1), LC_H_BYTES);        // arm the buffer that receives h_t
+        if (t > 0) mbar_wait(hfull(pb), ((t - 1) >> 1) & 1);                // h_{t-1} from all 16 CTAs has landed
+        tcgen05_fence_after();
+        const uint32_t hb = hsm + pb * LC_H_BYTES;
+#pragma unroll 4
+        for (int k = 0; k < LC_KP / 16; ++k) {
+          uint64_t ad = make_smem_desc(wsm + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          // un-swizzled K-major operand: LBO = stride between K-adjacent core matrices (256 B), SBO = row groups (128 B)
+          uint64_t bd = make_smem_desc(hb + k * 512, 256, 128) & ~((uint64_t)7 << 61);
+          umma_bf16(tm, ad, bd, idesc, k != 0);
+        }
+        umma_commit(mma_bar);
+      }
+    }
+  } else {
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may read = gate index (rows are gate-major)
+    const int etid = threadIdx.x - 32;            // 0..127
+    const int ul = etid & 31, bq = etid >> 5;     // pair role: unit ul, utterances bq*4 .. bq*4+3
+    const int u = (int)j * LC_U + ul;
+    const bool unit_ok = u < H;
+    float c_reg[4] = {0.f, 0.f, 0.f, 0.f};
+    float gxr[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = b0 + bq * 4 + i;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gxr[i][g] = (unit_ok && b < p.B && p.T > 0) ? __ldg(p.gx + ((int64_t)b * p.T) * H4 + g * H + u) : 0.f;
+    }
+    for (int t = 0; t < p.T; ++t) {
+      mbar_wait(mma_bar, t & 1);
+      tcgen05_fence_after();
+      float v[16];
+      tmem_ld16_nowait(tm + ((uint32_t)(q * 32) << 16), v);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+#pragma unroll
+      for (int b = 0; b < 16; ++b) pre_s[(q * 32 + lane) * LC_PRE_LD + b] = v[b];
+      named_bar_sync(1, 128);
+      uint8_t* hs = stg_p + (t & 1) * LC_SLICE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int bl = bq * 4 + i, b = b0 + bl;
+        const bool ok = unit_ok && b < p.B;
+        float pre[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pre[g] = pre_s[(g * 32 + ul) * LC_PRE_LD + bl] + gxr[i][g];
+        const float ig = sigmoid_(pre[0]), fg = sigmoid_(pre[1]), gg = tanhf(pre[2]), og = sigmoid_(pre[3]);
+        c_reg[i] = fg * c_reg[i] + ig * gg;
+        const float h = ok ? og * tanhf(c_reg[i]) : 0.f;
+        // own slice in the destination layout: [chunk = ul/8][row group = bl/8][row = bl%8][elem = ul%8]
+        reinterpret_cast<bf16*>(hs)[(((ul >> 3) * 2 + (bl >> 3)) * 8 + (bl & 7)) * 8 + (ul & 7)] = __float2bfloat16(h);
+        if (ok) {
+          const int64_t ho = (int64_t)b * p.h_bs + (int64_t)t * p.h_rs + u;
+          if (p.h_dtype == NBASR_BF16) reinterpret_cast<bf16*>(p.h_seq)[ho] = __float2bfloat16(h);
+          else reinterpret_cast<float*>(p.h_seq)[ho] = h;
+          if (p.gates) {
+            float* gr = p.gates + ((int64_t)b * p.T + t) * H4;
+            gr[u] = ig; gr[H + u] = fg; gr[2 * H + u] = gg; gr[3 * H + u] = og;
+            p.cstate[((int64_t)b * p.T + t) * H + u] = c_reg[i];
+          }
+          if (t + 1 < p.T) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) gxr[i][g] = __ldg(p.gx + ((int64_t)b * p.T + t + 1) * H4 + g * H + u);
+          }
+        }
+      }
+      fence_async_smem();
+      named_bar_sync(1, 128);
+      if (etid < LC_NCTA && t + 1 < p.T) {
+        // push the 1-KB slice into CTA `etid`'s buffer for step t+1; its mbarrier counts the bytes
+        const uint32_t dst = mapa(hsm + ((t & 1) ^ 1) * LC_H_BYTES + j * LC_SLICE, etid);
+        const uint32_t bar = mapa(hfull((t & 1) ^ 1), etid);
+        dsmem_bulk_copy(dst, stg + (t & 1) * LC_SLICE, LC_SLICE, bar);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                     // nobody leaves while a peer may still write into its shared memory
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tm, 32);
+  }
+}
+
+}  // namespace
+
+// w_packed: [16][128 rows = gate*32 + unit][512] bf16, made by nbasr_pack_batch kind 4
+int sm100_lstm_fwd(const float* gx, const void* w_packed, int T, int B, int H, void* h_seq, int h_dtype, int64_t h_bs, int64_t h_rs,
+                   float* gates, float* cstate, cudaStream_t st) {
+  NBASR_REQUIRE(H <= LC_KP && H <= LC_NCTA * LC_U, "hidden size");
+  LstmCArgs a{gx, T, B, H, h_seq, h_dtype, h_bs, h_rs, gates, cstate};
+  CUtensorMap tmW;
+  uint64_t dw[2] = {LC_KP, (uint64_t)LC_NCTA * 128};
+  int64_t sw[2] = {1, LC_KP};
+  uint32_t bw[2] = {64, 128};
+  if (sm100_get_map(w_packed, 2, dw, sw, bw, &tmW)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_cluster_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return nbasr_fail("lstm_cluster attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  const int nclusters = (B + LC_BG - 1) / LC_BG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nclusters * LC_NCTA);
+  cfg.blockDim = dim3(LC_THREADS);
+  cfg.dynamicSmemBytes = LC_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = LC_NCTA;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_cluster_fwd_kernel, tmW, a);
+  if (e != cudaSuccess) return nbasr_fail("lstm_cluster_fwd launch: %s", cudaGetErrorString(e));
+  return 0;
+}

@@ -42,6 +42,13 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const nbasr_pack_job* _
       int c0 = s * OUT, cn = c0 + nn, ck = c0 + kk;
       if (nn < OUT && cn < Cc && ck < Cc && kk < 48 && (cn / cpg) == (ck / cpg))
         v = tr ? J.src[((int64_t)ck * cpg + (cn % cpg)) * ktaps + (ktaps - 1 - jt)] : J.src[((int64_t)cn * cpg + (ck % cpg)) * ktaps + jt];
+    } else if (J.kind == 4) {           // LSTM W_hh for the cluster kernel: [cta 16][row = gate*32 + unit][k 512] (lstm_sm100.cu)
+      const int H = J.a[0];
+      int k = (int)(idx % 512);
+      int r = (int)((idx / 512) % 128);
+      int cj = (int)(idx / (512 * 128));
+      int g = r >> 5, u = cj * 32 + (r & 31);
+      if (u < H && k < H) v = J.src[((int64_t)g * H + u) * H + k];
     } else {                            // group-transposed, tap-flipped fp32 (SIMT input-gradient operand)
       const int cpg = J.a[1], ktaps = J.a[2];
       int jt = (int)(idx % ktaps), o = (int)((idx / ktaps) % cpg), ci = (int)(idx / (ktaps * cpg));

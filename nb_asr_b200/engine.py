@@ -215,6 +215,11 @@ class Engine:
                                                            FILTERS[-1], 1, 0, 0, FILTERS[-1], 1, 0)))
             self.wt[ln] = bt
             self.lstm_bias = torch.zeros(4 * HIDDEN, dtype=torch.float32, device=dev)
+            self.whh_packed = None
+            if self.dt == BF16:
+                # W_hh operand of the tcgen05 cluster recurrence: [16 CTAs][gate*32 + unit][512] bf16
+                self.whh_packed = torch.zeros(16 * 128 * 512, dtype=tdt, device=dev)
+                self.pack_ops.append(('lstm_whh', (self.P(ln + '.weight_hh_l0'), self.whh_packed.data_ptr(), HIDDEN)))
             idx += 1
         self.head_name = f'model.{idx}'
 
@@ -226,6 +231,11 @@ class Engine:
         jobs = (_lib.PackJob * len(self.pack_ops))()
         blocks = 0
         for j, (fn, a) in zip(jobs, self.pack_ops):
+            if fn == 'lstm_whh':
+                j.kind, j.src, j.dst, j.out_dtype, j.n_out = 4, a[0], a[1], BF16, 16 * 128 * 512
+                j.a[0] = a[2]
+                blocks += (j.n_out + 4095) // 4096
+                continue
             j.kind = kinds[fn.__name__]
             if j.kind == 0:
                 src, dst, odt, n = a
@@ -472,7 +482,8 @@ class Engine:
             cst = zbuf(B * Tq, HIDDEN, torch.float32)
             work = zbuf(1, 2 * B * HIDDEN + 256, torch.float32)
             call(fwd, lib.nbasr_lstm_fwd, gx.data_ptr(), self.P(ln + '.weight_hh_l0'), Tq, B, HIDDEN, _ptr(hseq, PAD_L * HP), dt,
-                 gh.Tp * HP, HP, HP, gates.data_ptr(), cst.data_ptr(), None, work.data_ptr())
+                 gh.Tp * HP, HP, HP, gates.data_ptr(), cst.data_ptr(),
+                 self.whh_packed.data_ptr() if self.whh_packed is not None else None, work.data_ptr())
             call(fwd, lib.nbasr_head_fwd, dt, _ptr(hseq, PAD_L * HP), gh.Tp * HP, HP, B, Tq, HIDDEN, V, self.P(hn + '.weight'),
                  self.P(hn + '.bias'), pl.logits.data_ptr(), pl.logp.data_ptr())
             head.update(lin=lin, dmask=dmask, gx=gx, hseq=hseq, gh=gh, gates=gates, cst=cst, work=work)

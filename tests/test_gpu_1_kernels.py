@@ -390,3 +390,44 @@ def test_dropout_statistics_and_mask_consistency():
     assert abs(keep.float().mean().item() - (1 - p)) < 0.01
     assert torch.allclose(o[keep], torch.full_like(o[keep], 1 / (1 - p)))
     assert torch.equal(U.unpack_mask(mask, B, T, Cc), keep)
+
+
+@pytest.mark.parametrize('B,T', [(16, 7), (20, 12), (64, 5)])
+def test_lstm_cluster_tensor_core_forward(B, T):
+    """bf16 mode: 16-CTA cluster kernel (tcgen05 MMA, distributed-shared-memory h exchange) vs fp32 reference."""
+    import ctypes as C_
+    torch.manual_seed(7)
+    H = 500
+    gx = torch.randn(B, T, 4 * H) * 0.7
+    w_hh = torch.randn(4 * H, H) * 0.08
+    w_bf = w_hh.bfloat16().float()
+    # reference with the same operand rounding (bf16 W_hh, bf16 h fed back), fp32 state
+    h = torch.zeros(B, H)
+    c = torch.zeros(B, H)
+    outs = []
+    for t in range(T):
+        g = gx[:, t] + h.bfloat16().float() @ w_bf.t()
+        i, f, gg, o = g.split(H, 1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        outs.append(h)
+    hs = torch.stack(outs, 1)
+    lib = _lib.load()
+    whh = w_hh.to(U.DEV)
+    wp = torch.zeros(16 * 128 * 512, dtype=torch.bfloat16, device=U.DEV)
+    job = (_lib.PackJob * 1)()
+    job[0].kind, job[0].out_dtype, job[0].src, job[0].dst, job[0].n_out = 4, BF16, whh.data_ptr(), wp.data_ptr(), 16 * 128 * 512
+    job[0].a[0] = H
+    jd = torch.frombuffer(bytearray(bytes(job)), dtype=torch.uint8).to(U.DEV)
+    _lib.check(lib.nbasr_pack_batch(jd.data_ptr(), 1, (16 * 128 * 512 + 4095) // 4096, U.stream()))
+    gxd = gx.contiguous().to(U.DEV)
+    hseq = torch.zeros(B, T, 512, dtype=torch.bfloat16, device=U.DEV)
+    gates = torch.zeros(B * T, 4 * H, device=U.DEV)
+    cst = torch.zeros(B * T, H, device=U.DEV)
+    work = torch.zeros(2 * B * H + 256, device=U.DEV)
+    _lib.check(lib.nbasr_lstm_fwd(gxd.data_ptr(), whh.data_ptr(), T, B, H, hseq.data_ptr(), BF16, T * 512, 512, 512, gates.data_ptr(),
+                                  cst.data_ptr(), wp.data_ptr(), work.data_ptr(), U.stream()), 'lstm_fwd cluster')
+    torch.cuda.synchronize()
+    assert U.relerr(hseq[:, :, :H].float().cpu(), hs) < 6e-3          # bf16 output rounding
+    assert U.relerr(cst.view(B, T, H)[:, -1].cpu(), c) < 2e-3
+    assert float(hseq[:, :, H:].float().abs().sum()) == 0.0

@@ -177,7 +177,8 @@ int nbasr_lstm_fwd(const float* gx, const float* w_hh, int T, int B, int H, void
  * dW_hh / dW_ih / biases then follow from nbasr_gemm_wgrad / nbasr_colsum over dgx. */
 int nbasr_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, int64_t ld_dh, const float* w_hh,
                    const float* gates, const float* cstate, int T, int B, int H, float* dgx, float* work,
-                   void* stream);
+                   const void* w_hh_packed, void* dgx_bf16, void* stream);
+/* w_hh_packed given -> tcgen05 / cluster kernel (bf16 recurrent operands); it can also emit dgx as bf16 (dgx_bf16). */
 
 /* Classifier + log-softmax: logits = h W^T + b (model.py:101 nn.Linear(500,49)),
  * logp = log_softmax(logits) (trainer.py:218). h rows at b*h_bs + t*h_rs, pitch implied by strides. */

@@ -55,7 +55,7 @@ _SIGS = {
     'nbasr_pack_weight': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64, _i64, _i64, _vp],
     'nbasr_convert': [_vp, _vp, C.c_int, _i64, _vp],
     'nbasr_lstm_fwd': [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
-    'nbasr_lstm_bwd': [_vp, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp],
+    'nbasr_lstm_bwd': [_vp, _i64, _i64, _i64, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp],
     'nbasr_head_fwd': [C.c_int, _vp, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp],
     'nbasr_head_bwd': [C.c_int, _vp, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _i64, _i64,
                        _vp, _vp, _vp],

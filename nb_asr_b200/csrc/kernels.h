@@ -38,3 +38,5 @@ int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C
 // cluster / tcgen05 LSTM recurrence (lstm_sm100.cu)
 int sm100_lstm_fwd(const float* gx, const void* w_packed, int T, int B, int H, void* h_seq, int h_dtype, int64_t h_bs, int64_t h_rs,
                    float* gates, float* cstate, cudaStream_t st);
+int sm100_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, const void* w_packed, const float* gates, const float* cstate,
+                   int T, int B, int H, float* dgx, void* dgx_bf16, cudaStream_t st);

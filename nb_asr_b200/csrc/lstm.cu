@@ -284,8 +284,12 @@ int nbasr_lstm_fwd(const float* gx, const float* w_hh, int T, int B, int H, void
 }
 
 int nbasr_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, int64_t ld_dh, const float* w_hh,
-                   const float* gates, const float* cstate, int T, int B, int H, float* dgx, float* work, void* stream) {
+                   const float* gates, const float* cstate, int T, int B, int H, float* dgx, float* work,
+                   const void* w_hh_packed, void* dgx_bf16, void* stream) {
   (void)ld_dh;
+  if (w_hh_packed && !getenv("NBASR_FORCE_SIMT"))
+    return sm100_lstm_bwd(dh_seq, dh_bs, dh_rs, w_hh_packed, gates, cstate, T, B, H, dgx, dgx_bf16, as_stream(stream));
+  if (dgx_bf16) return nbasr_fail("the fp32 SIMT recurrence does not write a bf16 copy");
   NBASR_REQUIRE(4 * H <= LB_RP && H <= L_KP && H % 4 == 0, "hidden size");
   int sms = nbasr_sm_count();
   int nslices = (H + L_U - 1) / L_U;

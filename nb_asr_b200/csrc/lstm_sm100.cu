@@ -193,6 +193,193 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const _
   }
 }
 
+// ---------------------------------------------------------------- backward (BPTT)
+// Same ownership (CTA j: units [32j, 32j+32), its 128 gate rows of W_hh in shared memory).  Per step the CTA turns
+// dh_t of its units into the 128 x 16 gate gradients dg (fp32 to global for the weight-gradient GEMMs, bf16 into the
+// un-swizzled MMA operand buffer) and computes its PARTIAL contribution to dh_{t-1} of ALL 512 units:
+//     partial[k][b] = sum_{own rows r} W_hh[r][k] dg[r][b]   -- 4 M-tiles x 8 tcgen05.mma (M=128 k's, N=16, K=16 rows),
+// reading the SAME shared-memory W slice as an MN-major A operand.  The 32 x 16 block that belongs to CTA i's units is
+// sent to CTA i (reduce-scatter over distributed shared memory, 1 KB bulk copies, bf16 partials); the receiver sums the
+// 16 partials in fp32.  Again the mbarrier byte count is the only inter-CTA synchronisation.
+constexpr int LB_DG_BYTES = 128 * LC_BG * 2;          // 4096: dg operand (N=16 x K=128)
+constexpr int LB_SEND_BYTES = LC_NCTA * LC_SLICE;     // 16384: one 1-KB block per destination
+constexpr int LB_SMEM = LC_W_BYTES + LB_DG_BYTES + 2 * LB_SEND_BYTES + 2 * LB_SEND_BYTES + 1024 + 256;
+
+struct LstmCBwdArgs {
+  const float* dh_seq;
+  int64_t dh_bs, dh_rs;
+  const float* gates;
+  const float* cstate;
+  int T, B, H;
+  float* dgx;          // (B, T, 4H) fp32
+  bf16* dgx_bf16;      // optional bf16 copy for the tensor-core GEMMs that follow
+};
+
+__global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LstmCBwdArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t wsm = base;
+  const uint32_t dsm = base + LC_W_BYTES;                       // dg operand
+  const uint32_t snd = dsm + LB_DG_BYTES;                       // 2 x 16 KB send staging
+  const uint32_t rcv = snd + 2 * LB_SEND_BYTES;                 // 2 x 16 KB receive buffers [src][l][b]
+  uint8_t* dsm_p = al + LC_W_BYTES;
+  uint8_t* snd_p = dsm_p + LB_DG_BYTES;
+  uint8_t* rcv_p = snd_p + 2 * LB_SEND_BYTES;
+  const uint32_t bar0 = rcv + 2 * LB_SEND_BYTES;
+  const uint32_t wbar = bar0, mma_bar = bar0 + 8, dg_bar = bar0 + 16;
+  auto rfull = [&](int b) { return bar0 + 24 + 8u * b; };
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(rcv_p + 2 * LB_SEND_BYTES + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t j = cluster_ctarank();
+  const int b0 = (blockIdx.x / LC_NCTA) * LC_BG;
+  const int H = p.H, H4 = 4 * p.H;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmW);
+    mbar_init(wbar, 1);
+    mbar_init(mma_bar, 1);
+    mbar_init(dg_bar, 128);
+    mbar_init(rfull(0), 1);
+    mbar_init(rfull(1), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tptr), 64);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  cluster_sync_all();
+  const uint32_t tm = *tptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wbar, LC_W_BYTES);
+      for (int kb = 0; kb < 8; ++kb) tma_load_2d(wsm + kb * 16384, &tmW, wbar, kb * 64, (int)j * 128);
+      const uint32_t idesc = make_idesc(128, LC_BG, 1, 0);        // A: MN-major (W slice read "transposed"), B: K-major
+      mbar_wait(wbar, 0);
+      for (int s = 0; s + 1 < p.T; ++s) {                          // step s handles t = T-1-s; the last step needs no matmul
+        mbar_expect_tx(rfull(s & 1), LB_SEND_BYTES);               // arm the buffer that receives this step's partials
+        mbar_wait(dg_bar, s & 1);                                  // dg operand of this step is in shared memory
+        tcgen05_fence_after();
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint64_t ad = make_smem_desc(wsm + (2 * mt) * 16384 + k * 2048, 16384, 1024);
+            uint64_t bd = make_smem_desc(dsm + k * 512, 256, 128) & ~((uint64_t)7 << 61);
+            umma_bf16(tm + mt * 16, ad, bd, idesc, k != 0);
+          }
+        }
+        umma_commit(mma_bar);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int etid = threadIdx.x - 32;
+    const int ul = etid & 31, bq = etid >> 5;
+    const int u = (int)j * LC_U + ul;
+    const bool unit_ok = u < H;
+    float dc_next[4] = {0.f, 0.f, 0.f, 0.f}, dh_rec[4] = {0.f, 0.f, 0.f, 0.f};
+    float nx[4][7];
+    auto prefetch = [&](int t) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int b = b0 + bq * 4 + i;
+        if (unit_ok && b < p.B) {
+          nx[i][0] = __ldg(p.dh_seq + (int64_t)b * p.dh_bs + (int64_t)t * p.dh_rs + u);
+          const float* gr = p.gates + ((int64_t)b * p.T + t) * H4;
+          nx[i][1] = __ldg(gr + u); nx[i][2] = __ldg(gr + H + u); nx[i][3] = __ldg(gr + 2 * H + u); nx[i][4] = __ldg(gr + 3 * H + u);
+          nx[i][5] = __ldg(p.cstate + ((int64_t)b * p.T + t) * H + u);
+          nx[i][6] = t > 0 ? __ldg(p.cstate + ((int64_t)b * p.T + t - 1) * H + u) : 0.f;
+        } else {
+#pragma unroll
+          for (int z = 0; z < 7; ++z) nx[i][z] = 0.f;
+        }
+      }
+    };
+    if (p.T > 0) prefetch(p.T - 1);
+    for (int s = 0; s < p.T; ++s) {
+      const int t = p.T - 1 - s;
+      if (s > 0) {
+        // partial sums of dh_t for the own units from all 16 CTAs (sent during step s-1)
+        mbar_wait(rfull((s - 1) & 1), ((s - 1) >> 1) & 1);
+        const bf16* rb = reinterpret_cast<const bf16*>(rcv_p + ((s - 1) & 1) * LB_SEND_BYTES);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float acc = 0.f;
+#pragma unroll
+          for (int src = 0; src < LC_NCTA; ++src) acc += __bfloat162float(rb[(src * 32 + ul) * LC_BG + bq * 4 + i]);
+          dh_rec[i] = acc;
+        }
+      }
+      bf16* dgo = reinterpret_cast<bf16*>(dsm_p);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int bl = bq * 4 + i, b = b0 + bl;
+        const bool ok = unit_ok && b < p.B;
+        const float dh = nx[i][0] + dh_rec[i];
+        const float ig = nx[i][1], fg = nx[i][2], gg = nx[i][3], og = nx[i][4], c = nx[i][5], cprev = nx[i][6];
+        const float tc = tanhf(c);
+        const float dov = dh * tc;
+        const float dc = dc_next[i] + dh * og * (1.f - tc * tc);
+        dc_next[i] = dc * fg;
+        float d[4];
+        d[0] = dc * gg * ig * (1.f - ig);
+        d[1] = dc * cprev * fg * (1.f - fg);
+        d[2] = dc * ig * (1.f - gg * gg);
+        d[3] = dov * og * (1.f - og);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float v = ok ? d[g] : 0.f;
+          const int r = g * 32 + ul;                         // own gate row = K index of the MMA
+          dgo[(((r >> 3) * 2 + (bl >> 3)) * 8 + (bl & 7)) * 8 + (r & 7)] = __float2bfloat16(v);
+          if (ok) {
+            const int64_t o = ((int64_t)b * p.T + t) * H4 + g * H + u;
+            p.dgx[o] = v;
+            if (p.dgx_bf16) p.dgx_bf16[o] = __float2bfloat16(v);
+          }
+        }
+      }
+      if (t == 0) break;
+      prefetch(t - 1);
+      fence_async_smem();
+      mbar_arrive(dg_bar);                                   // 128 arrivals -> the MMA thread may read the dg operand
+      mbar_wait(mma_bar, s & 1);
+      tcgen05_fence_after();
+      uint8_t* sb = snd_p + (s & 1) * LB_SEND_BYTES;
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        float v[16];
+        tmem_ld16_nowait(tm + ((uint32_t)(q * 32) << 16) + mt * 16, v);
+        tmem_ld_wait();
+        // lane l of quadrant q holds k = mt*128 + q*32 + l -> unit l of CTA (4*mt + q)
+        bf16* dst = reinterpret_cast<bf16*>(sb + (4 * mt + q) * LC_SLICE) + lane * LC_BG;
+        uint4 pk[2];
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) h2[x] = __floats2bfloat162_rn(v[2 * x], v[2 * x + 1]);
+        reinterpret_cast<uint4*>(dst)[0] = pk[0];
+        reinterpret_cast<uint4*>(dst)[1] = pk[1];
+      }
+      tcgen05_fence_before();
+      fence_async_smem();
+      named_bar_sync(1, 128);
+      if (etid < LC_NCTA) {
+        const uint32_t dst = mapa(rcv + (s & 1) * LB_SEND_BYTES + j * LC_SLICE, etid);
+        const uint32_t bar = mapa(rfull(s & 1), etid);
+        dsmem_bulk_copy(dst, snd + (s & 1) * LB_SEND_BYTES + etid * LC_SLICE, LC_SLICE, bar);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tm, 64);
+  }
+}
+
 }  // namespace
 
 // w_packed: [16][128 rows = gate*32 + unit][512] bf16, made by nbasr_pack_batch kind 4
@@ -227,5 +414,39 @@ int sm100_lstm_fwd(const float* gx, const void* w_packed, int T, int B, int H, v
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_cluster_fwd_kernel, tmW, a);
   if (e != cudaSuccess) return nbasr_fail("lstm_cluster_fwd launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int sm100_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, const void* w_packed, const float* gates, const float* cstate,
+                   int T, int B, int H, float* dgx, void* dgx_bf16, cudaStream_t st) {
+  NBASR_REQUIRE(H <= LC_KP && H <= LC_NCTA * LC_U, "hidden size");
+  LstmCBwdArgs a{dh_seq, dh_bs, dh_rs, gates, cstate, T, B, H, dgx, reinterpret_cast<bf16*>(dgx_bf16)};
+  CUtensorMap tmW;
+  uint64_t dw[2] = {LC_KP, (uint64_t)LC_NCTA * 128};
+  int64_t sw[2] = {1, LC_KP};
+  uint32_t bw[2] = {64, 128};
+  if (sm100_get_map(w_packed, 2, dw, sw, bw, &tmW)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_cluster_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return nbasr_fail("lstm_cluster_bwd attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  const int nclusters = (B + LC_BG - 1) / LC_BG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nclusters * LC_NCTA);
+  cfg.blockDim = dim3(LC_THREADS);
+  cfg.dynamicSmemBytes = LB_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = LC_NCTA;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_cluster_bwd_kernel, tmW, a);
+  if (e != cudaSuccess) return nbasr_fail("lstm_cluster_bwd launch: %s", cudaGetErrorString(e));
   return 0;
 }

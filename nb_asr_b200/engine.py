@@ -511,13 +511,11 @@ class Engine:
                  self.P(hn + '.weight'), pl.dlogits.data_ptr(), dh.data_ptr(), Tq * HIDDEN, HIDDEN, self.G(hn + '.weight'),
                  self.G(hn + '.bias'))
             dgx = zbuf(B * Tq, H4, torch.float32)
+            dgx_a = zbuf(B * Tq, H4) if dt == BF16 else dgx     # bf16 copy written by the cluster kernel itself
             call(bwd, lib.nbasr_lstm_bwd, dh.data_ptr(), Tq * HIDDEN, HIDDEN, HIDDEN, self.P(ln + '.weight_hh_l0'),
-                 head['gates'].data_ptr(), head['cst'].data_ptr(), Tq, B, HIDDEN, dgx.data_ptr(), head['work'].data_ptr())
-            if dt == BF16:
-                dgx_a = zbuf(B * Tq, H4)
-                call(bwd, lib.nbasr_convert, dgx.data_ptr(), dgx_a.data_ptr(), BF16, B * Tq * H4)
-            else:
-                dgx_a = dgx
+                 head['gates'].data_ptr(), head['cst'].data_ptr(), Tq, B, HIDDEN, dgx.data_ptr(), head['work'].data_ptr(),
+                 self.whh_packed.data_ptr() if self.whh_packed is not None else None,
+                 dgx_a.data_ptr() if dt == BF16 else None)
             # biases: column sums of dgx (B*Tq rows, unpadded) -> both bias vectors
             for bn in ('.bias_ih_l0', '.bias_hh_l0'):
                 call(bwd, lib.nbasr_colsum, F32, dgx.data_ptr() - PAD_L * H4 * 4, 1, B * Tq, B * Tq, H4, self.G(ln + bn))

@@ -236,7 +236,7 @@ def test_lstm_fwd_bwd(B, T):
     dhd = dh.contiguous().to(U.DEV)
     dgx = torch.zeros(B * T, 4 * H, device=U.DEV)
     _lib.check(lib.nbasr_lstm_bwd(dhd.data_ptr(), T * H, H, H, whh.data_ptr(), gates.data_ptr(), cst.data_ptr(), T, B, H, dgx.data_ptr(),
-                                  work.data_ptr(), U.stream()), 'lstm_bwd')
+                                  work.data_ptr(), None, None, U.stream()), 'lstm_bwd')
     torch.cuda.synchronize()
     assert U.relerr(dgx.view(B, T, 4 * H).cpu(), ggx) < 5e-5
     # dW_hh = dgx^T h_{t-1} via the SIMT wgrad over a row-shifted view of h_seq
@@ -431,3 +431,15 @@ def test_lstm_cluster_tensor_core_forward(B, T):
     assert U.relerr(hseq[:, :, :H].float().cpu(), hs) < 6e-3          # bf16 output rounding
     assert U.relerr(cst.view(B, T, H)[:, -1].cpu(), c) < 2e-3
     assert float(hseq[:, :, H:].float().abs().sum()) == 0.0
+    # backward through the cluster kernel vs the fp32 SIMT kernel on the SAME saved gates / cell states
+    dh = torch.randn(B, T, H, device=U.DEV)
+    dgx_ref = torch.zeros(B * T, 4 * H, device=U.DEV)
+    _lib.check(lib.nbasr_lstm_bwd(dh.data_ptr(), T * H, H, H, whh.data_ptr(), gates.data_ptr(), cst.data_ptr(), T, B, H,
+                                  dgx_ref.data_ptr(), work.data_ptr(), None, None, U.stream()), 'lstm_bwd simt')
+    dgx = torch.zeros(B * T, 4 * H, device=U.DEV)
+    dgx16 = torch.zeros(B * T, 4 * H, dtype=torch.bfloat16, device=U.DEV)
+    _lib.check(lib.nbasr_lstm_bwd(dh.data_ptr(), T * H, H, H, whh.data_ptr(), gates.data_ptr(), cst.data_ptr(), T, B, H,
+                                  dgx.data_ptr(), work.data_ptr(), wp.data_ptr(), dgx16.data_ptr(), U.stream()), 'lstm_bwd cluster')
+    torch.cuda.synchronize()
+    assert U.relerr(dgx.cpu(), dgx_ref.cpu()) < 1.5e-2, U.relerr(dgx.cpu(), dgx_ref.cpu())     # bf16 W_hh / dg / partial sums
+    assert U.relerr(dgx16.float().cpu(), dgx.cpu()) < 4e-3

@@ -241,8 +241,15 @@ def main():
     else:
         achieved = dom['bytes'] / dom['ms'] / 1e6
         peak, unit = pk['hbm'], 'GB/s'
+    traffic, traffic_note = None, None
+    ncu_path = os.path.join(ROOT, 'profiles', 'r1_ncu_gconv_fwd_v5.json')
+    if dom_name == 'gconv' and os.path.exists(ncu_path):
+        nc = json.load(open(ncu_path))
+        traffic = nc['avg_dram_bytes_per_launch']
+        traffic_note = f"dram read+write per launch, ncu --set full over {nc['launches']} launches of {nc['kernel']} (profiles/r1_ncu_gconv_fwd_v5.json)"
     roofline = {'kernel': dom_name, 'bound': 'tensor' if tensor_bound else 'hbm', 'achieved': achieved, 'peak': peak, 'unit': unit,
-                'frac': achieved / peak, 'traffic': None, 'peak_source': pk['src'] + (' sustained' if tensor_bound else ''),
+                'frac': achieved / peak, 'traffic': traffic, 'traffic_note': traffic_note,
+                'algorithmic_bytes_per_launch': dom['bytes'] / max(dom['n'], 1), 'algorithmic_flops_per_launch': dom['flops'] / max(dom['n'], 1), 'peak_source': pk['src'] + (' sustained' if tensor_bound else ''),
                 'launches_per_step': dom['n'], 'avg_launch_ms': dom['ms'] / max(dom['n'], 1),
                 'share_of_step_kernel_time': dom['ms'] / tot_ms,
                 'families': {k: {'ms': round(v['ms'], 4), 'n': v['n'],

@@ -220,7 +220,8 @@ int nbasr_optim_step(float* param, float* grad, float* m, float* v, int64_t n, c
 
 /* Batched operand refresh: ONE launch executes a device-resident table of pack jobs (what
  * nbasr_convert / nbasr_pack_weight / nbasr_pack_gconv_mma / nbasr_pack_gconv_dgrad do one at a time).
- * jobs: device array of n nbasr_pack_job; blocks: total 4096-element chunks = sum_j ceil(n_out_j / 4096). */
+ * jobs: device array of n nbasr_pack_job; blockmap: device int32 pairs (job, chunk) for each of the `blocks`
+ * 4096-element chunks (blocks = sum_j ceil(n_out_j / 4096)). */
 typedef struct nbasr_pack_job {
   int32_t kind;          /* 0 convert, 1 pack_weight, 2 pack_gconv_mma, 3 pack_gconv_dgrad, 4 LSTM W_hh cluster pack (a[0]=H) */
   int32_t out_dtype;
@@ -230,7 +231,7 @@ typedef struct nbasr_pack_job {
   int32_t a[8];          /* kind 1: M,N,nq,t0,tstep ; kind 2: C,cpg,ktaps,transposed ; kind 3: C,cpg,ktaps */
   int64_t s[3];          /* kind 1: ws_m, ws_n, ws_t */
 } nbasr_pack_job;
-int nbasr_pack_batch(const nbasr_pack_job* jobs, int n, int64_t blocks, void* stream);
+int nbasr_pack_batch(const nbasr_pack_job* jobs, int n, const int32_t* blockmap, int64_t blocks, void* stream);
 
 /* misc */
 int nbasr_fill_u32(uint32_t* p, uint32_t val, int64_t n, void* stream);

@@ -63,7 +63,7 @@ _SIGS = {
     'nbasr_greedy_per': [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp, _vp],
     'nbasr_optim_step': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, C.c_int, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp],
-    'nbasr_pack_batch': [_vp, C.c_int, _i64, _vp],
+    'nbasr_pack_batch': [_vp, C.c_int, _vp, _i64, _vp],
     'nbasr_fill_u32': [_vp, C.c_uint32, _i64, _vp],
     'nbasr_version': [],
     'nbasr_sm_count': [],

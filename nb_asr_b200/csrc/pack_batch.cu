@@ -10,14 +10,12 @@ constexpr int PB_CHUNK = 4096;
 template <typename T>
 __device__ __forceinline__ void put(void* dst, int64_t i, float v) { reinterpret_cast<T*>(dst)[i] = static_cast<T>(v); }
 
-__global__ void __launch_bounds__(256) pack_batch_kernel(const nbasr_pack_job* __restrict__ jobs, int n) {
-  int64_t blk = blockIdx.x;
-  int j = 0;
-  for (; j < n; ++j) {
-    int64_t nch = (jobs[j].n_out + PB_CHUNK - 1) / PB_CHUNK;
-    if (blk < nch) break;
-    blk -= nch;
-  }
+__global__ void __launch_bounds__(256) pack_batch_kernel(const nbasr_pack_job* __restrict__ jobs, int n,
+                                                         const int2* __restrict__ blockmap) {
+  // blockmap[b] = (job, chunk) -- precomputed by the host that built the table (no per-block search)
+  const int2 bm = blockmap[blockIdx.x];
+  const int j = bm.x;
+  const int64_t blk = bm.y;
   if (j >= n) return;
   const nbasr_pack_job J = jobs[j];
   const int64_t start = blk * PB_CHUNK;
@@ -62,9 +60,9 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const nbasr_pack_job* _
 
 }  // namespace
 
-extern "C" int nbasr_pack_batch(const nbasr_pack_job* jobs, int n, int64_t blocks, void* stream) {
+extern "C" int nbasr_pack_batch(const nbasr_pack_job* jobs, int n, const int32_t* blockmap, int64_t blocks, void* stream) {
   if (n <= 0 || blocks <= 0) return 0;
-  pack_batch_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(jobs, n);
+  pack_batch_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(jobs, n, reinterpret_cast<const int2*>(blockmap));
   NBASR_CHECK_LAUNCH();
   return 0;
 }

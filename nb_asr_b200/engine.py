@@ -257,6 +257,11 @@ class Engine:
             blocks += (j.n_out + 4095) // 4096
         raw = bytes(jobs)
         self.pack_jobs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        bmap = []
+        for ji, j in enumerate(jobs):
+            nch = (j.n_out + 4095) // 4096
+            bmap.append(torch.stack([torch.full((nch,), ji, dtype=torch.int32), torch.arange(nch, dtype=torch.int32)], 1))
+        self.pack_blockmap = torch.cat(bmap).contiguous().to(self.device)
         self.pack_njobs, self.pack_blocks = len(self.pack_ops), blocks
 
     def _param_version(self):
@@ -268,7 +273,7 @@ class Engine:
             return
         st = torch.cuda.current_stream().cuda_stream
         if self.pack_njobs:
-            _lib.check(self.lib.nbasr_pack_batch(self.pack_jobs.data_ptr(), self.pack_njobs, self.pack_blocks, st), 'pack_batch')
+            _lib.check(self.lib.nbasr_pack_batch(self.pack_jobs.data_ptr(), self.pack_njobs, self.pack_blockmap.data_ptr(), self.pack_blocks, st), 'pack_batch')
             self.launches += 1
         if self.model.use_rnn:
             off_i, n = self.slices[self.lstm_name + '.bias_ih_l0']

@@ -419,7 +419,9 @@ def test_lstm_cluster_tensor_core_forward(B, T):
     job[0].kind, job[0].out_dtype, job[0].src, job[0].dst, job[0].n_out = 4, BF16, whh.data_ptr(), wp.data_ptr(), 16 * 128 * 512
     job[0].a[0] = H
     jd = torch.frombuffer(bytearray(bytes(job)), dtype=torch.uint8).to(U.DEV)
-    _lib.check(lib.nbasr_pack_batch(jd.data_ptr(), 1, (16 * 128 * 512 + 4095) // 4096, U.stream()))
+    nblk = (16 * 128 * 512 + 4095) // 4096
+    bmap = torch.stack([torch.zeros(nblk, dtype=torch.int32), torch.arange(nblk, dtype=torch.int32)], 1).contiguous().to(U.DEV)
+    _lib.check(lib.nbasr_pack_batch(jd.data_ptr(), 1, bmap.data_ptr(), nblk, U.stream()))
     gxd = gx.contiguous().to(U.DEV)
     hseq = torch.zeros(B, T, 512, dtype=torch.bfloat16, device=U.DEV)
     gates = torch.zeros(B * T, 4 * H, device=U.DEV)

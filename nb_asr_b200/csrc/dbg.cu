@@ -16,8 +16,11 @@ namespace {
 constexpr int PADROWS = 16;
 
 __global__ void __launch_bounds__(128, 1)
-dbg_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* D, int mode, int shift,
+dbg_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* D, int mode_in, int shift,
                  int bo_mode) {
+  // modes 3/4/5: mode-0 layout with operand formats (A,B) = (f16,bf16) / (bf16,f16) / (f16,f16) in the instruction descriptor
+  const int mode = mode_in >= 3 ? 0 : mode_in;
+  const uint32_t fmt_clear = (mode_in == 3 || mode_in == 5 ? (7u << 7) : 0u) | (mode_in == 4 || mode_in == 5 ? (7u << 10) : 0u);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
@@ -82,7 +85,7 @@ dbg_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ad = make_smem_desc(sa + k * 2048, 8192, 1024);
         bd = make_smem_desc(b0, 8192, 1024, bo_mode ? (b0 >> 7) & 7 : 0);
       }
-      umma_bf16(tm, ad, bd, make_idesc(128, 64, mode, mode), k != 0);
+      umma_bf16(tm, ad, bd, make_idesc(128, 64, mode, mode) & ~fmt_clear, k != 0);
     }
     umma_commit(tbar);
   }
@@ -108,7 +111,7 @@ extern "C" int nbasr_dbg_shift(const void* A, const void* B, float* D, int mode,
     uint32_t ba[2] = {64, 128};
     if (sm100_get_map(A, 2, da, sa, ba, &tmA)) return 1;
     tmB = tmA;
-  } else if (mode == 0) {
+  } else if (mode == 0 || mode >= 3) {
     uint64_t da[2] = {64, 128 + PADROWS};
     int64_t sa[2] = {1, 64};
     uint32_t ba[2] = {64, 128 + PADROWS};
@@ -128,6 +131,99 @@ extern "C" int nbasr_dbg_shift(const void* A, const void* B, float* D, int mode,
   }
   cudaFuncSetAttribute(dbg_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024);
   dbg_shift_kernel<<<1, 128, 70 * 1024, as_stream(stream)>>>(tmA, tmB, D, mode, shift, bo_mode);
+  NBASR_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Micro-benchmarks (test-only): what=0: back-to-back tcgen05.mma 128 x N x 16 (SS, bf16) issue+execute cycles;
+// what=1: tcgen05.ld 32x32b.x32 throughput over `nw` warps; what=2: warp-shuffle throughput over `nw` warps.
+// out[cta] = elapsed clock64 cycles for `iters` operations (per warp for what=1/2).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(512, 1)
+dbg_bench_kernel(unsigned long long* out, int what, int N, int iters, int variant) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sa = base;                 // 160 rows x 128 B
+  const uint32_t sb = base + 24576;         // 256 rows x 128 B
+  const uint32_t bar = base + 24576 + 32768;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(al + 24576 + 32768 + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (24576 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(al)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tptr), 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tm = *tptr;
+  if (what == 0) {
+    if (threadIdx.x == 0) {
+      const uint32_t idesc = make_idesc(128, N, 0, 0);
+      long long t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        // variant bit0: alternate accumulators; bit1: walk taps (row shift) and k-chunks like the grouped-conv kernel
+        const int j = (variant & 2) ? (i / 3) % 5 : 0, k = (variant & 2) ? i % 3 : 0;
+        uint64_t ad = make_smem_desc(sa + j * 128 + k * 32, 16, 1024);
+        uint64_t bd = make_smem_desc(sb + k * 32, 16, 1024);
+        umma_bf16(tm + ((variant & 1) ? (i & 1) * 256 : 0), ad, bd, idesc, i != 0);
+      }
+      long long t1 = clock64();
+      umma_commit(bar);
+      mbar_wait(bar, 0);
+      long long t2 = clock64();
+      out[blockIdx.x * 2] = t2 - t0;
+      out[blockIdx.x * 2 + 1] = t1 - t0;
+    }
+  } else if (what == 1) {
+    if (warp < N) {   // N = number of warps taking part
+      float acc = 0.f;
+      long long t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        float v[32];
+        tmem_ld32(tm + ((uint32_t)((warp & 3) * 32) << 16) + ((i * 32) & 255) + (warp >> 2) * 256 % 512, v);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc += v[q];
+      }
+      long long t1 = clock64();
+      if (lane == 0) out[blockIdx.x * 16 + warp] = t1 - t0;
+      if (acc == 123.456f) out[0] = 0;
+    }
+  } else {
+    if (warp < N) {
+      float v[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] = lane * 0.5f + q;
+      long long t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] += __shfl_down_sync(0xffffffffu, v[q], 1);
+      }
+      long long t1 = clock64();
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) acc += v[q];
+      if (lane == 0) out[blockIdx.x * 16 + warp] = t1 - t0;
+      if (acc == 123.456f) out[0] = 0;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tm, 512);
+  }
+}
+}  // namespace
+
+extern "C" int nbasr_dbg_bench(unsigned long long* out, int what, int N, int iters, int variant, int ctas, void* stream) {
+  cudaFuncSetAttribute(dbg_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  dbg_bench_kernel<<<ctas, 512, 60 * 1024, as_stream(stream)>>>(out, what, N, iters, variant);
   NBASR_CHECK_LAUNCH();
   return 0;
 }

@@ -42,3 +42,13 @@ for variant in (0, 1):
     D = buf[:128 * 64].view(128, 64)[:, :16]
     ref = A.float() @ Bm.float().t()
     print(f'mode 2 (no-swizzle B) variant {variant} [0: LBO=K-stride 256, SBO=row-group 128 | 1: swapped]: err {float((D - ref).norm() / ref.norm()):.2e}', flush=True)
+
+# modes 3/4/5: mixed operand formats inside kind::f16 (A,B) = (f16,bf16) / (bf16,f16) / (f16,f16)
+for mode, (ta, tb) in ((3, (torch.float16, torch.bfloat16)), (4, (torch.bfloat16, torch.float16)), (5, (torch.float16, torch.float16))):
+    A = torch.randn(144, 64, device=dev).to(ta)
+    B = torch.randn(64, 64, device=dev).to(tb)
+    D = torch.zeros(128, 64, device=dev)
+    rc = f(A.data_ptr(), B.data_ptr(), D.data_ptr(), mode, 0, 0, None)
+    torch.cuda.synchronize()
+    ref = A[:128].float() @ B.float().t()
+    print(f'mode {mode} A={ta} B={tb}: err {float((D - ref).norm() / ref.norm()):.2e}', flush=True)

@@ -424,10 +424,10 @@ __global__ void pack_gconv_mma_kernel(const float* __restrict__ w, bf16* __restr
 
 }  // namespace
 
-static unsigned long long* g_gconv_dbg = nullptr;
+unsigned long long* g_gconv_dbg = nullptr;
 extern "C" void nbasr_dbg_gconv_trace(unsigned long long* buf) { g_gconv_dbg = buf; }
 
-int sm100_gconv_fwd(const nbasr_gconv* g, cudaStream_t st) {
+int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st) {
   GcFwdArgs a{};
   a.B = g->B; a.T = g->T; a.Tp = g->Tp; a.C = g->C; a.OUT = slab_out(g->cpg);
   a.ktaps = g->ktaps; a.dstep = g->dstep; a.off0 = g->off0;

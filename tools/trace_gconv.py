@@ -41,7 +41,7 @@ for name, kw in (('full', dict(bias=bias, relu=1, out=out, mask_out=mask, mask_w
     t0 = int(t[t > 0].min())
     print('=== variant', name)
     for cta in (0, 1):
-        print(f'CTA {cta}: tile | compute_done fence_done | mma_tempty_ok mma_full_ok | epi_start epi_end | tmem_ld_done bar1_done  (us since first stamp)')
+        print(f'CTA {cta}: item | bar2_done mma_full_ok mma_issued | epi_tfull tmem_released bar1_done staged store_issued  (us since first stamp; v1 kernel: see gconv_sm100.cu)')
         for it in range(10, 16):
             r = t[cta, it]
             if r[1] == 0:

@@ -15,9 +15,11 @@
 //    epilogue (bias, ReLU20, dropout, skip-sum, gradient mask) works on 8-column groups because slab
 //    boundaries are only 8-aligned.
 //  * Weight gradient: dW_j[co][ci] = sum_t dZ[t][co] X[t+off_j][ci], both operands MN-major (frames
-//    are the reduction index).  Two taps share one M=128 MMA: the A descriptor's "leading byte offset"
-//    makes rows 64..127 the same dZ tile shifted by `dstep` frames, so rows 0-63 give tap j+1 and rows
-//    64-127 tap j.  Diagonal blocks are extracted from TMEM and atomically added to the fp32 gradient.
+//    are the reduction index).  ALL taps share one M=128 x N=64*ceil(k/2) MMA per 16-frame K step: the A
+//    descriptor's "leading byte offset" makes rows 64..127 the same dZ tile shifted by `dstep` frames, the
+//    B descriptor's makes N atom i the same X tile shifted by 2 i dstep frames, so (atom i, rows 64-127)
+//    gives tap 2i and (atom i, rows 0-63) tap 2i+1.  Diagonal blocks are extracted from TMEM and atomically
+//    added to the fp32 gradient.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -43,6 +45,11 @@ constexpr int OSTAGE_BYTES = GT * NW * 2;  // 12288: bf16 output tile staged for
 constexpr int FWD_SMEM_BUDGET = 112 * 1024;
 
 __host__ __device__ inline int slab_out(int cpg) { return cpg == 10 ? 40 : 48; }
+// weight-gradient slabs: as many whole groups as fit in 56 channels: 54 / 56 / 50 / 48 for cpg 6 / 8 / 10 / 12 -> fewer,
+// fuller 128-byte loads.  TMA boxes must start on a 16-byte (8-channel) boundary, so the box starts at c0 & ~7 and the
+// slab sits at offset c0 & 7 inside the 64-channel window; channel 63 of the window is never part of a slab and carries
+// the ones column of the fused bias gradient.
+__host__ __device__ inline int wg_slab_out(int cpg) { return (56 / cpg) * cpg; }
 __host__ __device__ inline int fwd_nstage(int ktaps) {
   int n = (FWD_SMEM_BUDGET - 3072 - ktaps * WTAP_BYTES - 2 * OSTAGE_BYTES) / A_BYTES;
   return n > 4 ? 4 : n;
@@ -292,6 +299,7 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
   const int slab = blockIdx.x % p.nslabs;
   const int lane_id = blockIdx.x / p.nslabs;
   const int c0 = slab * p.OUT;
+  const int cbox = c0 & ~7, coff = c0 - cbox;       // TMA box start (16-byte aligned) and slab offset inside the window
   const int npairs = (p.ktaps + 1) / 2;
 
   if (warp == 0 && lane == 0) {
@@ -317,15 +325,18 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_expect_tx(full_bar(stage), DZ_BYTES + A_BYTES);
         const uint32_t sa = base + stage * WG_STAGE;
-        tma_load_3d(sa, &tmDZ, full_bar(stage), c0, NBASR_PAD_L + t0 - p.dstep, b);
-        tma_load_3d(sa + DZ_BYTES, &tmX, full_bar(stage), c0, NBASR_PAD_L + t0 + p.off0, b);
+        tma_load_3d(sa, &tmDZ, full_bar(stage), cbox, NBASR_PAD_L + t0 - p.dstep, b);
+        tma_load_3d(sa + DZ_BYTES, &tmX, full_bar(stage), cbox, NBASR_PAD_L + t0 + p.off0, b);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (has_work) {
-      const uint32_t idesc = make_idesc(128, NW, 1, 1);
-      const uint32_t idesc_b = make_idesc(128, 64, 1, 1);   // pair 0 also multiplies the ones column (N = 64)
+      // ONE MMA per 16-frame K step covers every tap: the B descriptor's leading-byte offset (2 dstep rows) makes the
+      // N atoms 0..npairs-1 the same X tile shifted by 0, 2, 4, .. taps, the A descriptor's (dstep rows) makes rows
+      // 64..127 / 0..63 the dZ tile unshifted / shifted by one tap: atom i, rows 64..127 -> tap 2i, rows 0..63 -> tap 2i+1.
+      // (A tcgen05.mma costs ~88 cycles of issue whatever N <= 176 is, 96 at N = 192, 128 at N = 256: tools/dbg_bench.py.)
+      const uint32_t idesc = make_idesc(128, 64 * npairs, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
@@ -334,25 +345,21 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
         const uint32_t sa = base + stage * WG_STAGE;
         const uint32_t sb = sa + DZ_BYTES;
         if (p.dbias) {
-          // channel 48 of the X window (unused by the N = 48 MMAs) <- 1.0 for every frame row: element 0 of the
-          // 16-byte chunk 6, at its 128B-swizzled position (chunk ^ (row & 7)).
+          // channel 63 of the X window (never part of a slab) <- 1.0 for every frame row: element 7 of the
+          // 16-byte chunk 7, at its 128B-swizzled position (chunk ^ (row & 7)).
           uint8_t* xb = al + stage * WG_STAGE + DZ_BYTES;
           for (int r = lane; r < AROWS; r += 32)
-            *reinterpret_cast<uint16_t*>(xb + r * 128 + ((6 ^ (r & 7)) << 4)) = 0x3F80;
+            *reinterpret_cast<uint16_t*>(xb + r * 128 + ((7 ^ (r & 7)) << 4) + 14) = 0x3F80;
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
         }
         tcgen05_fence_after();
         if (lane == 0) {
-          for (int pr = 0; pr < npairs; ++pr) {
-            const int j = 2 * pr;     // rows 64..127 -> tap j (dZ shifted by dstep rows), rows 0..63 -> tap j+1
-            const uint32_t id = (pr == 0 && p.dbias) ? idesc_b : idesc;
 #pragma unroll
-            for (int k = 0; k < GT / 16; ++k) {
-              uint64_t ad = make_smem_desc(sa + k * 2048, (uint32_t)p.dstep * 128u, 1024);
-              uint64_t bd = make_smem_desc(sb + (j * p.dstep) * 128 + k * 2048, 8192, 1024);
-              umma_bf16(tm + pr * 64, ad, bd, id, (!first || k > 0) ? 1u : 0u);
-            }
+          for (int k = 0; k < GT / 16; ++k) {
+            uint64_t ad = make_smem_desc(sa + k * 2048, (uint32_t)p.dstep * 128u, 1024);
+            uint64_t bd = make_smem_desc(sb + k * 2048, 2u * (uint32_t)p.dstep * 128u, 1024);
+            umma_bf16(tm, ad, bd, idesc, (!first || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
         }
@@ -366,27 +373,24 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int half = m >> 6, co_l = m & 63;
-    const int co = c0 + co_l;
-    const bool row_ok = co_l < p.OUT && co < p.C;
-    const int g_l = co_l / p.cpg;
+    const int co = cbox + co_l;
+    const bool row_ok = co_l >= coff && co_l < coff + p.OUT && co < p.C;
+    const int g_l = (co_l - coff) / p.cpg;
     mbar_wait(tfull, 0);
     tcgen05_fence_after();
     for (int pr = 0; pr < npairs; ++pr) {
-      float v[48];
+      float v[64];
       const uint32_t ta = tm + ((uint32_t)(q * 32) << 16) + pr * 64;
       tmem_ld32(ta, v);
-      tmem_ld16(ta + 32, v + 32);
+      tmem_ld32(ta + 32, v + 32);
       const int tap = half ? 2 * pr : 2 * pr + 1;
-      if (pr == 0 && p.dbias) {      // column 48 of pair 0, rows 64..127 (tap 0, unshifted dZ): sum_t dZ[t][co]
-        float one[16];
-        tmem_ld16(ta + 48, one);
-        if (row_ok && half) atomicAdd(p.dbias + co, one[0]);
-      }
+      // column 63 of atom 0, rows 64..127 (tap 0, unshifted dZ) = sum_t dZ[t][co]
+      if (pr == 0 && p.dbias && row_ok && half) atomicAdd(p.dbias + co, v[63]);
       if (row_ok && tap < p.ktaps) {
         float* dst = p.dw + ((int64_t)co * p.cpg) * p.ktaps + tap;
 #pragma unroll
-        for (int i = 0; i < 48; ++i) {
-          const int il = i - g_l * p.cpg;
+        for (int i = 0; i < 64; ++i) {
+          const int il = i - coff - g_l * p.cpg;
           if (il >= 0 && il < p.cpg) atomicAdd(dst + il * p.ktaps, v[i]);
         }
       }
@@ -473,7 +477,7 @@ int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st) {
 int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C, int cpg, int ktaps, int off0, int dstep,
                       float* dw, float* dbias, cudaStream_t st) {
   GcWgArgs a{};
-  a.B = B; a.T = T; a.C = C; a.cpg = cpg; a.OUT = slab_out(cpg); a.ktaps = ktaps; a.dstep = dstep; a.off0 = off0;
+  a.B = B; a.T = T; a.C = C; a.cpg = cpg; a.OUT = wg_slab_out(cpg); a.ktaps = ktaps; a.dstep = dstep; a.off0 = off0;
   NBASR_REQUIRE(off0 >= -NBASR_PAD_L && (ktaps - 1) * dstep <= AROWS - GT && dstep <= DZROWS - GT, "tap reach");
   a.nslabs = (C + a.OUT - 1) / a.OUT;
   a.nchunks = (T + dstep + GT - 1) / GT;

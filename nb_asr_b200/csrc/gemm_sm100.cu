@@ -14,6 +14,8 @@
 //              64-frame chunk) units, fp32 red.global.add epilogue.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -32,7 +34,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
 constexpr int B_STAGE_BYTES = BN_MAX * BK * 2;    // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;        // weight-gradient kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int TN_THREADS = 320;         // gemm_tn: TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
 
 using namespace sm100;
 
@@ -43,7 +46,7 @@ struct TnArgs {
   nbasr_epilogue epi;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -69,7 +72,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), 256);
     }
     fence_barrier_init();
   }
@@ -128,6 +131,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int hh = (warp - 2) >> 2;   // the two warps of a quadrant take alternate 32-column chunks
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -140,7 +144,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(as), aphase);
       tcgen05_fence_after();
       const int64_t rho = p.o_r0 + (int64_t)b * p.o_bs + (int64_t)r * p.o_rs;
-      for (int c = 0; c < p.BN; c += 32) {
+      for (int c = 32 * hh; c < p.BN; c += 64) {
         if (n0 + c >= ncol) break;   // warp-uniform
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN_MAX + c, v);
@@ -372,13 +376,18 @@ int sm100_get_map(const void* base, int rank, const uint64_t* dims, const int64_
 
 namespace {
 
-int pick_bn(int N) {
-  // multiple of 32, <= 256, minimising padded columns then tile count
+// Tile width: minimise  waves x cycles-per-K-block.  A K block (64) costs max(MMA issue, operand ingest): four MMAs of
+// max(88, BN/2) cycles (tools/dbg_bench.py) against (16 KB of A + 128 BN bytes of B) at ~64 B/clk/SM from L2 (measured:
+// the 128 x 256 tile runs ~750 cycles per K block, not 512).  Narrow tiles (the old "least padding" rule picked BN = 64
+// for N = 1200) multiply the A re-reads and the wave count.
+int pick_bn(int N, int m_tiles, int sms) {
   int best = 256;
   long best_cost = -1;
-  for (int bn = 64; bn <= 256; bn += 32) {
-    int tiles = (N + bn - 1) / bn;
-    long cost = (long)tiles * bn * 1000 + tiles;  // padded width first, then fewer tiles
+  for (int bn = 96; bn <= 256; bn += 32) {
+    const long tiles = (long)m_tiles * ((N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    const long mma = 4L * std::max(88, bn / 2), ingest = (16384 + 128L * bn) / 64;
+    const long cost = waves * std::max(mma, ingest) * 16 + bn / 32;   // ties -> narrower tile (less padding work)
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -390,7 +399,10 @@ int sm100_gemm_tn(const nbasr_gemm* g, cudaStream_t st) {
   NBASR_REQUIRE(g->K % 8 == 0, "K must keep 16-byte row alignment");
   TnArgs a{};
   a.nb = g->nb; a.nr = g->nr; a.K = g->K; a.N = g->N;
-  a.BN = pick_bn(g->N);
+  a.mt_per_utt = (g->nr + BM - 1) / BM;
+  a.BN = pick_bn(g->N, a.mt_per_utt * g->nb, nbasr_sm_count());
+  static const char* env_bn = getenv("NBASR_GEMM_BN");      // tuning override (tools/bench_gemm.py)
+  if (env_bn) a.BN = std::max(32, std::min(256, atoi(env_bn) / 32 * 32));
   a.mt_per_utt = (g->nr + BM - 1) / BM;
   a.n_tiles = (g->N + a.BN - 1) / a.BN;
   a.total_tiles = a.mt_per_utt * g->nb * a.n_tiles;
@@ -412,7 +424,7 @@ int sm100_gemm_tn(const nbasr_gemm* g, cudaStream_t st) {
     attr = true;
   }
   int grid = std::min(a.total_tiles, nbasr_sm_count());
-  gemm_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
+  gemm_tn_kernel<<<grid, TN_THREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
   NBASR_CHECK_LAUNCH();
   return 0;
 }

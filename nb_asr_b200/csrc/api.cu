@@ -31,7 +31,11 @@ int nbasr_sm_count(void) {
 
 int nbasr_gemm_tn(const nbasr_gemm* p, void* stream) {
   if (p->nb <= 0 || p->nr <= 0 || p->N <= 0) return 0;
-  if (p->dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT")) return sm100_gemm_tn(p, as_stream(stream));
+  if (p->dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT")) {
+    // default: CTA-pair (cta_group::2) kernel; NBASR_GEMM_1CTA=1 selects the single-CTA kernel
+    static const bool one_cta = getenv("NBASR_GEMM_1CTA") != nullptr;
+    return one_cta ? sm100_gemm_tn(p, as_stream(stream)) : sm100_gemm_tn_pair(p, as_stream(stream));
+  }
   SimtGemmArgs a{};
   a.a = p->a; a.a_dtype = p->dtype; a.a_ib = p->a_bs; a.a_ir = p->a_rs; a.a_kb = 0; a.a_kr = 1;
   a.nib = p->nb; a.nir = p->nr;

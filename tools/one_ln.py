@@ -7,7 +7,7 @@ from nb_asr_b200 import _lib
 from nb_asr_b200._lib import BF16
 import gpu_utils as U
 lib = _lib.load()
-B, T = 64, 500
+B, T = int(os.environ.get("B", 64)), 500
 once = bool(os.environ.get('ONCE'))
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=U.DEV)
 for Cc in ((800,) if once else (600, 800, 1000, 1200)):

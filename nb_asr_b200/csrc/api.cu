@@ -48,7 +48,10 @@ int nbasr_gemm_tn(const nbasr_gemm* p, void* stream) {
 
 int nbasr_gemm_wgrad(const nbasr_wgrad* p, void* stream) {
   if (p->nb <= 0 || p->nr <= 0 || p->N <= 0 || p->M <= 0) return 0;
-  if (p->dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT")) return sm100_gemm_wgrad(p, as_stream(stream));
+  if (p->dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT")) {
+    static const bool one_cta = getenv("NBASR_GEMM_1CTA") != nullptr;
+    return one_cta ? sm100_gemm_wgrad(p, as_stream(stream)) : sm100_gemm_wgrad_pair(p, as_stream(stream));
+  }
   SimtGemmArgs a{};
   a.a = p->dy; a.a_dtype = p->dtype; a.a_ib = 0; a.a_ir = 1; a.a_kb = p->dy_bs; a.a_kr = p->dy_rs;
   a.nib = 1; a.nir = p->M;

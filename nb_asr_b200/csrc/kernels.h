@@ -25,6 +25,7 @@ int simt_gemm_launch(const SimtGemmArgs& a, cudaStream_t st);
 int sm100_gemm_tn(const nbasr_gemm* p, cudaStream_t st);
 int sm100_gemm_tn_pair(const nbasr_gemm* p, cudaStream_t st);   // cta_group::2 (gemm2_sm100.cu)
 int sm100_gemm_wgrad(const nbasr_wgrad* p, cudaStream_t st);
+int sm100_gemm_wgrad_pair(const nbasr_wgrad* p, cudaStream_t st);   // cta_group::2 (gemm2_sm100.cu)
 
 // cached bf16 TMA descriptor (rank 2/3, 128B swizzle); strides in elements for dims 1..rank-1
 struct CUtensorMap_st;

@@ -241,12 +241,18 @@ def main():
     else:
         achieved = dom['bytes'] / dom['ms'] / 1e6
         peak, unit = pk['hbm'], 'GB/s'
+    # DRAM traffic of the dominant kernel: per-launch dram read+write bytes of an `ncu --set full` capture of this same
+    # command (profiles/r1_ncu_step_full.json, written by tools/ncu_summary.py); null when no capture is committed
     traffic, traffic_note = None, None
-    ncu_path = os.path.join(ROOT, 'profiles', 'r1_ncu_gconv_fwd_v5.json')
-    if dom_name == 'gconv' and os.path.exists(ncu_path):
-        nc = json.load(open(ncu_path))
-        traffic = nc['avg_dram_bytes_per_launch']
-        traffic_note = f"dram read+write per launch, ncu --set full over {nc['launches']} launches of {nc['kernel']} (profiles/r1_ncu_gconv_fwd_v5.json)"
+    fam_kernel = {'gconv': 'gconv_mma_fwd_kernel', 'gconv_wgrad': 'gconv_mma_wgrad_kernel', 'gemm_tn': 'gemm_tn_pair_kernel',
+                  'gemm_wgrad': 'gemm_wgrad_pair_kernel', 'ln_bwd': 'layernorm_bwd_bf16_kernel', 'ln_fwd': 'layernorm_fwd_bf16_kernel'}
+    ncu_path = os.path.join(ROOT, 'profiles', 'r1_ncu_step_full.json')
+    if os.path.exists(ncu_path) and dom_name in fam_kernel:
+        nc = json.load(open(ncu_path)).get('kernels', {}).get(fam_kernel[dom_name])
+        if nc and 'avg_dram_bytes_per_launch' in nc:
+            traffic = nc['avg_dram_bytes_per_launch']
+            traffic_note = (f"dram read+write bytes per launch, ncu --set full over {nc['launches']} launches of "
+                            f"{fam_kernel[dom_name]} (profiles/r1_ncu_step_full.json)")
     roofline = {'kernel': dom_name, 'bound': 'tensor' if tensor_bound else 'hbm', 'achieved': achieved, 'peak': peak, 'unit': unit,
                 'frac': achieved / peak, 'traffic': traffic, 'traffic_note': traffic_note,
                 'algorithmic_bytes_per_launch': dom['bytes'] / max(dom['n'], 1), 'algorithmic_flops_per_launch': dom['flops'] / max(dom['n'], 1), 'peak_source': pk['src'] + (' sustained' if tensor_bound else ''),

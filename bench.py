@@ -224,6 +224,17 @@ def main():
     # ---- live per-kernel timing (CUDA events on the launching stream) for the roofline entry
     pl = eng.plan(B, T, True)
     prof = profiling.profile_ops(eng, pl.fwd + pl.bwd, iters=3)
+    # optimiser tail (regulariser + clip + Adam + operand re-pack), timed as one unit on the launching stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    eng._optimizer_launch()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(3):
+        eng._optimizer_launch()
+    ev[1].record()
+    torch.cuda.synchronize()
+    n_par = float(eng.n_flat)
+    prof['optim+repack'] = dict(ms=ev[0].elapsed_time(ev[1]) / 3, flops=0.0, bytes=n_par * (4 * 7 + 2 * 2), n=1.0)
     if args.profile:
         sys.stderr.write(profiling.format_profile(prof) + '\n')
     fam = {}

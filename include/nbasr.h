@@ -189,6 +189,12 @@ int nbasr_head_bwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B
                    const float* w, const float* dlogits, float* dh, int64_t dh_bs, int64_t dh_rs,
                    float* dw, float* db, void* stream);
 
+/* Input-gradient half of the classifier backward only: dh = dlogits W (fp32, same addressing as nbasr_head_bwd), plus
+ * (optional) dl16 = dlogits as bf16 padded to 64 columns, (B*T, 64): the dY operand with which nbasr_gemm_wgrad then
+ * computes dW (and db) on the tensor cores against the bf16 h_seq. */
+int nbasr_head_bwd_dh(int B, int T, int K, int V, const float* w, const float* dlogits, float* dh, int64_t dh_bs,
+                      int64_t dh_rs, void* dl16, void* stream);
+
 /* CTC (trainer.py:36-44: F.ctc_loss(reduction='none', zero_infinity=True) / output_len, mean).
  * logp (B,T,V) fp32, blank 0; targets (B,S) int32 zero padded; lens int64 (audio_len is the INPUT
  * length; output_len = audio_len / len_div, trainer.py:219 uses 4).  Outputs: nll[b] (already
@@ -220,8 +226,11 @@ int nbasr_optim_step(float* param, float* grad, float* m, float* v, int64_t n, c
 
 /* Batched operand refresh: ONE launch executes a device-resident table of pack jobs (what
  * nbasr_convert / nbasr_pack_weight / nbasr_pack_gconv_mma / nbasr_pack_gconv_dgrad do one at a time).
- * jobs: device array of n nbasr_pack_job; blockmap: device int32 pairs (job, chunk) for each of the `blocks`
- * 4096-element chunks (blocks = sum_j ceil(n_out_j / 4096)). */
+ * jobs: device array of n nbasr_pack_job; blockmap: device int32 pairs (job, chunk), one per thread block.  A chunk is
+ * 4096 consecutive output elements (ceil(n_out / 4096) chunks per job), except for kind 1 (transposes), where a chunk is
+ * one 64 x 64 (m, n) tile of one tap: nq * ceil(M / 64) * ceil(N / 64) chunks, tile_n fastest, then tile_m, then q;
+ * and for kind 2, where chunks walk the C * cpg * ktaps SOURCE weights and only the diagonal blocks of the pack are
+ * rewritten (the caller zero-fills the pack buffer once). */
 typedef struct nbasr_pack_job {
   int32_t kind;          /* 0 convert, 1 pack_weight, 2 pack_gconv_mma, 3 pack_gconv_dgrad, 4 LSTM W_hh cluster pack (a[0]=H) */
   int32_t out_dtype;

@@ -18,28 +18,67 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const nbasr_pack_job* _
   const int64_t blk = bm.y;
   if (j >= n) return;
   const nbasr_pack_job J = jobs[j];
+  if (J.kind == 1) {
+    // transpose job: chunk = one 64 (m) x 64 (n) tile of tap q, staged through shared memory so that both the fp32 reads
+    // (along n, ws_n == 1) and the writes (along m) are coalesced.  chunk -> (q, tile_m, tile_n), tile_n fastest.
+    __shared__ float tile[64][65];
+    const int M = J.a[0], N = J.a[1], nq = J.a[2], t0 = J.a[3], ts = J.a[4];
+    const int tn = (N + 63) >> 6, tm = (M + 63) >> 6;
+    const int q = (int)(blk / ((int64_t)tm * tn));
+    const int m0 = (int)((blk / tn) % tm) * 64, n0 = (int)(blk % tn) * 64;
+    const float* src = J.src + (int64_t)(t0 + q * ts) * J.s[2];
+    const int c = threadIdx.x & 63, r4 = threadIdx.x >> 6;
+    for (int r = r4; r < 64; r += 4)
+      tile[r][c] = (m0 + r < M && n0 + c < N) ? src[(int64_t)(m0 + r) * J.s[0] + (int64_t)(n0 + c) * J.s[1]] : 0.f;
+    __syncthreads();
+    for (int r = r4; r < 64; r += 4) {          // r = n within the tile, c = m within the tile
+      if (n0 + r < N && m0 + c < M) {
+        const int64_t o = (int64_t)(n0 + r) * nq * M + (int64_t)q * M + m0 + c;
+        if (J.out_dtype == NBASR_BF16) put<bf16>(J.dst, o, tile[c][r]);
+        else put<float>(J.dst, o, tile[c][r]);
+      }
+    }
+    return;
+  }
+  if (J.kind == 2) {
+    // block-diagonal grouped-conv operand: only the C*cpg*ktaps weights are (re)written -- the off-diagonal zeros of the
+    // [slab][tap][48][64] pack are written once when the buffer is allocated.  idx walks the SOURCE tensor (co, i, tap).
+    const int Cc = J.a[0], cpg = J.a[1], ktaps = J.a[2], tr = J.a[3];
+    const int OUT = cpg == 10 ? 40 : 48;
+    const int64_t nsrc = (int64_t)Cc * cpg * ktaps;
+    const int64_t s0 = blk * PB_CHUNK, s1 = min(nsrc, s0 + PB_CHUNK);
+    bf16* dst = reinterpret_cast<bf16*>(J.dst);
+    for (int64_t idx = s0 + threadIdx.x; idx < s1; idx += blockDim.x) {
+      const int jt = (int)(idx % ktaps);
+      const int i = (int)((idx / ktaps) % cpg);
+      const int co = (int)(idx / ((int64_t)ktaps * cpg));
+      const int ci = (co / cpg) * cpg + i;
+      const int sl = co / OUT;
+      const int row = (tr ? ci : co) - sl * OUT, col = (tr ? co : ci) - sl * OUT, tap = tr ? ktaps - 1 - jt : jt;
+      dst[(((int64_t)sl * ktaps + tap) * 48 + row) * 64 + col] = __float2bfloat16(J.src[idx]);
+    }
+    return;
+  }
+  if (J.kind == 0 && J.out_dtype == NBASR_BF16 && (J.n_out & 3) == 0) {      // fp32 -> bf16 copy, 4 elements per thread
+    const int64_t s0 = blk * (PB_CHUNK / 4), s1 = min(J.n_out >> 2, s0 + PB_CHUNK / 4);
+    const float4* src = reinterpret_cast<const float4*>(J.src);
+    uint2* dst = reinterpret_cast<uint2*>(J.dst);
+    for (int64_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
+      const float4 f = src[i];
+      __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      dst[i] = o;
+    }
+    return;
+  }
   const int64_t start = blk * PB_CHUNK;
   const int64_t end = min(J.n_out, start + PB_CHUNK);
   for (int64_t idx = start + threadIdx.x; idx < end; idx += blockDim.x) {
     float v = 0.f;
     if (J.kind == 0) {
       v = J.src[idx];
-    } else if (J.kind == 1) {           // out[n][q*M + m] = w[m*ws_m + n*ws_n + (t0 + q*tstep)*ws_t]
-      const int M = J.a[0], nq = J.a[2], t0 = J.a[3], ts = J.a[4];
-      int m = (int)(idx % M);
-      int q = (int)((idx / M) % nq);
-      int nn = (int)(idx / ((int64_t)M * nq));
-      v = J.src[m * J.s[0] + nn * J.s[1] + (int64_t)(t0 + q * ts) * J.s[2]];
-    } else if (J.kind == 2) {           // block-diagonal [slab][tap][48][64] (gconv_sm100.cu)
-      const int Cc = J.a[0], cpg = J.a[1], ktaps = J.a[2], tr = J.a[3];
-      const int OUT = cpg == 10 ? 40 : 48;
-      int kk = (int)(idx % 64);
-      int nn = (int)((idx / 64) % 48);
-      int jt = (int)((idx / (64 * 48)) % ktaps);
-      int s = (int)(idx / ((int64_t)64 * 48 * ktaps));
-      int c0 = s * OUT, cn = c0 + nn, ck = c0 + kk;
-      if (nn < OUT && cn < Cc && ck < Cc && kk < 48 && (cn / cpg) == (ck / cpg))
-        v = tr ? J.src[((int64_t)ck * cpg + (cn % cpg)) * ktaps + (ktaps - 1 - jt)] : J.src[((int64_t)cn * cpg + (ck % cpg)) * ktaps + jt];
     } else if (J.kind == 4) {           // LSTM W_hh for the cluster kernel: [cta 16][row = gate*32 + unit][k 512] (lstm_sm100.cu)
       const int H = J.a[0];
       int k = (int)(idx % 512);

@@ -2,6 +2,8 @@
 // Levenshtein PER.  Small, latency-bound kernels; all arithmetic in fp32 (fp64 for the PER mean).
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -135,6 +137,147 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(int h_dtype, const void* 
   __syncthreads();
   if (db && tid < V) atomicAdd(db + tid, dbacc);
   if (dw) for (int i = tid; i < V * K; i += blockDim.x) atomicAdd(dw + i, sdw[i]);
+}
+
+
+// ---------------------------------------------------------------- head forward / dh, register-tiled (K <= 600)
+// logits[r][v] = sum_k h[r][k] W[v][k] + b[v] with W resident in shared memory (fp32) and h streamed in 64-wide K
+// chunks; a thread owns 4 rows x up to 8 classes (v = c8 + 8 i), so every shared-memory operand feeds 4..8 FMAs and
+// no dot product needs a warp reduction.  The 8 threads of a row group finish log-softmax with three shuffles.
+constexpr int HT_ROWS = 128;
+constexpr int HT_KC = 64;
+__global__ void __launch_bounds__(256, 1) head_fwd_tiled_kernel(int h_dtype, const void* __restrict__ h, int64_t h_bs, int64_t h_rs,
+                                                                int B, int T, int K, int V, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ logits,
+                                                                float* __restrict__ logp) {
+  extern __shared__ float sm[];
+  float* ws = sm;                       // V x K
+  float* hs = ws + V * K;               // HT_ROWS x (HT_KC + 1)
+  const int tid = threadIdx.x, rg = tid >> 3, c8 = tid & 7;
+  for (int i = tid; i < V * K; i += blockDim.x) ws[i] = w[i];
+  const int64_t nrows = (int64_t)B * T;
+  const int ntiles = (int)((nrows + HT_ROWS - 1) / HT_ROWS);
+  int vcls[8];
+  float bv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int v = c8 + 8 * i;
+    vcls[i] = min(v, V - 1);            // clamped duplicates are computed and dropped
+    bv[i] = bias[vcls[i]];
+  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = (int64_t)tile * HT_ROWS;
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += HT_KC) {
+      __syncthreads();
+      for (int i = tid; i < HT_ROWS * HT_KC; i += blockDim.x) {
+        const int rr = i >> 6, kk = i & 63;
+        const int64_t r = r0 + rr;
+        float v = 0.f;
+        if (r < nrows && k0 + kk < K) v = ld_dt(h, h_dtype, (r / T) * h_bs + (r % T) * h_rs + k0 + kk);
+        hs[rr * (HT_KC + 1) + kk] = v;
+      }
+      __syncthreads();
+      const int kn = min(HT_KC, K - k0);
+      for (int kk = 0; kk < kn; ++kk) {
+        float hv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hv[j] = hs[(4 * rg + j) * (HT_KC + 1) + kk];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float wv = ws[vcls[i] * K + k0 + kk];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(hv[j], wv, acc[j][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r = r0 + 4 * rg + j;
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[j][i] += bv[i];
+        if (c8 + 8 * i < V) m = fmaxf(m, acc[j][i]);
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float e = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (c8 + 8 * i < V) e += __expf(acc[j][i] - m);
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+      const float lse = m + __logf(e);
+      if (r < nrows) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int v = c8 + 8 * i;
+          if (v < V) {
+            if (logits) logits[r * V + v] = acc[j][i];
+            if (logp) logp[r * V + v] = acc[j][i] - lse;
+          }
+        }
+      }
+    }
+  }
+}
+
+// dh[r][k] = sum_v dl[r][v] W[v][k] (fp32), plus a bf16 copy of dl padded to 64 columns: the operand of the
+// tensor-core weight-gradient GEMM that computes dW and db (nbasr_gemm_wgrad) instead of this kernel.
+constexpr int HD_ROWS = 64;
+__global__ void __launch_bounds__(256, 1) head_bwd_dh_kernel(int B, int T, int K, int V, const float* __restrict__ w,
+                                                             const float* __restrict__ dl, float* __restrict__ dh, int64_t dh_bs,
+                                                             int64_t dh_rs, bf16* __restrict__ dl16) {
+  extern __shared__ float sm[];
+  float* ws = sm;                       // V x K
+  float* ds = ws + V * K;               // HD_ROWS x 65
+  const int tid = threadIdx.x;
+  for (int i = tid; i < V * K; i += blockDim.x) ws[i] = w[i];
+  const int64_t nrows = (int64_t)B * T;
+  const int ntiles = (int)((nrows + HD_ROWS - 1) / HD_ROWS);
+  const int k0 = tid, k1 = tid + 256, k2 = tid + 512;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = (int64_t)tile * HD_ROWS;
+    __syncthreads();
+    for (int i = tid; i < HD_ROWS * 64; i += blockDim.x) {
+      const int rr = i >> 6, v = i & 63;
+      const int64_t r = r0 + rr;
+      const float d = (v < V && r < nrows) ? dl[r * V + v] : 0.f;
+      ds[rr * 65 + v] = d;
+      if (dl16 && r < nrows) dl16[r * 64 + v] = __float2bfloat16(d);
+    }
+    __syncthreads();
+    for (int r8 = 0; r8 < HD_ROWS; r8 += 8) {
+      float acc[8][3];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
+      for (int v = 0; v < V; ++v) {
+        const float w0 = k0 < K ? ws[v * K + k0] : 0.f, w1 = k1 < K ? ws[v * K + k1] : 0.f, w2 = k2 < K ? ws[v * K + k2] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = ds[(r8 + j) * 65 + v];
+          acc[j][0] = fmaf(d, w0, acc[j][0]);
+          acc[j][1] = fmaf(d, w1, acc[j][1]);
+          acc[j][2] = fmaf(d, w2, acc[j][2]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t r = r0 + r8 + j;
+        if (r < nrows) {
+          float* o = dh + (r / T) * dh_bs + (r % T) * dh_rs;
+          if (k0 < K) o[k0] = acc[j][0];
+          if (k1 < K) o[k1] = acc[j][1];
+          if (k2 < K) o[k2] = acc[j][2];
+        }
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------- CTC
@@ -358,6 +501,15 @@ int nbasr_head_fwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B
   NBASR_REQUIRE(V <= 64 && K <= 32 * HEAD_MAXK32, "head shape");
   int64_t rows = (int64_t)B * T;
   if (rows == 0) return 0;
+  const size_t smt = sizeof(float) * ((size_t)V * K + HT_ROWS * (HT_KC + 1));
+  if (smt <= 200 * 1024 && rows >= 4 * HT_ROWS && !getenv("NBASR_HEAD_V1")) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(head_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    int grid = (int)std::min<int64_t>((rows + HT_ROWS - 1) / HT_ROWS, nbasr_sm_count());
+    head_fwd_tiled_kernel<<<grid, 256, smt, as_stream(stream)>>>(h_dtype, h, h_bs, h_rs, B, T, K, V, w, bias, logits, logp);
+    NBASR_CHECK_LAUNCH();
+    return 0;
+  }
   int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 8);
   head_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(h_dtype, h, h_bs, h_rs, B, T, K, V, w, bias, logits, logp);
   NBASR_CHECK_LAUNCH();
@@ -389,6 +541,21 @@ int nbasr_head_bwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B
     a.epi.out = dw; a.epi.out_dtype = NBASR_F32; a.epi.ld_out = K; a.epi.accumulate = 1;
     return simt_gemm_launch(a, as_stream(stream));
   }
+  return 0;
+}
+
+int nbasr_head_bwd_dh(int B, int T, int K, int V, const float* w, const float* dlogits, float* dh, int64_t dh_bs, int64_t dh_rs,
+                      void* dl16, void* stream) {
+  NBASR_REQUIRE(V <= 64 && K <= 768, "head shape");
+  int64_t rows = (int64_t)B * T;
+  if (rows == 0) return 0;
+  const size_t smt = sizeof(float) * ((size_t)V * K + HD_ROWS * 65);
+  NBASR_REQUIRE(smt <= 200 * 1024, "head too wide for head_bwd_dh");
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(head_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  int grid = (int)std::min<int64_t>((rows + HD_ROWS - 1) / HD_ROWS, nbasr_sm_count());
+  head_bwd_dh_kernel<<<grid, 256, smt, as_stream(stream)>>>(B, T, K, V, w, dlogits, dh, dh_bs, dh_rs, (bf16*)dl16);
+  NBASR_CHECK_LAUNCH();
   return 0;
 }
 

@@ -189,7 +189,8 @@ class Engine:
                         if self.dt == BF16:
                             # block-diagonal bf16 operands of the tcgen05 grouped-conv kernel (forward / input-gradient)
                             ne = int(lib.nbasr_gconv_mma_pack_elems(cout, cpg, k))
-                            bf_, bt = (torch.empty(ne, dtype=tdt, device=dev) for _ in range(2))
+                            # zeros: the batched refresh only rewrites the diagonal blocks (pack_batch.cu kind 2)
+                            bf_, bt = (torch.zeros(ne, dtype=tdt, device=dev) for _ in range(2))
                             for buf, tr_ in ((bf_, 0), (bt, 1)):
                                 self.pack_ops.append((lib.nbasr_pack_gconv_mma, (self.P(pn + '.conv.weight'), buf.data_ptr(), cout, cpg, k, tr_)))
                             self.wf[pn] = bf_
@@ -234,7 +235,7 @@ class Engine:
             if fn == 'lstm_whh':
                 j.kind, j.src, j.dst, j.out_dtype, j.n_out = 4, a[0], a[1], BF16, 16 * 128 * 512
                 j.a[0] = a[2]
-                blocks += (j.n_out + 4095) // 4096
+                blocks += self._pack_chunks(j)
                 continue
             j.kind = kinds[fn.__name__]
             if j.kind == 0:
@@ -254,15 +255,25 @@ class Engine:
                 src, dst, Cc, cpg, k = a
                 j.src, j.dst, j.out_dtype, j.n_out = src, dst, F32, Cc * cpg * k
                 j.a[0], j.a[1], j.a[2] = Cc, cpg, k
-            blocks += (j.n_out + 4095) // 4096
+            blocks += self._pack_chunks(j)
         raw = bytes(jobs)
         self.pack_jobs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
         bmap = []
         for ji, j in enumerate(jobs):
-            nch = (j.n_out + 4095) // 4096
+            nch = self._pack_chunks(j)
             bmap.append(torch.stack([torch.full((nch,), ji, dtype=torch.int32), torch.arange(nch, dtype=torch.int32)], 1))
         self.pack_blockmap = torch.cat(bmap).contiguous().to(self.device)
         self.pack_njobs, self.pack_blocks = len(self.pack_ops), blocks
+
+    @staticmethod
+    def _pack_chunks(j):
+        """blocks of one pack job: 64x64 transpose tiles per tap for kind 1, 4096-element chunks otherwise"""
+        if j.kind == 1:
+            M, N, nq = j.a[0], j.a[1], j.a[2]
+            return nq * ((M + 63) // 64) * ((N + 63) // 64)
+        if j.kind == 2:
+            return (j.a[0] * j.a[1] * j.a[2] + 4095) // 4096      # walks the source weights (C * cpg * ktaps)
+        return (j.n_out + 4095) // 4096
 
     def _param_version(self):
         return sum(p._version for p in self.params)
@@ -512,9 +523,17 @@ class Engine:
             ln = self.lstm_name
             H4 = 4 * HIDDEN
             dh = zbuf(B * Tq, HIDDEN, torch.float32)
-            call(bwd, lib.nbasr_head_bwd, dt, _ptr(head['hseq'], PAD_L * HP), head['gh'].Tp * HP, HP, B, Tq, HIDDEN, V,
-                 self.P(hn + '.weight'), pl.dlogits.data_ptr(), dh.data_ptr(), Tq * HIDDEN, HIDDEN, self.G(hn + '.weight'),
-                 self.G(hn + '.bias'))
+            if dt == BF16:
+                # dh on CUDA cores (fp32 W), dW / db on the tensor cores from a bf16 copy of dlogits and the bf16 h_seq
+                dl16 = zbuf(B * Tq, 64)
+                call(bwd, lib.nbasr_head_bwd_dh, B, Tq, HIDDEN, V, self.P(hn + '.weight'), pl.dlogits.data_ptr(), dh.data_ptr(),
+                     Tq * HIDDEN, HIDDEN, dl16.data_ptr())
+                wgrad(bwd, dl16.data_ptr(), Tq * 64, 64, _ptr(head['hseq'], PAD_L * HP), head['gh'].Tp * HP, HP, B, Tq, V, HIDDEN,
+                      self.G(hn + '.weight'), HIDDEN, dbias=self.G(hn + '.bias'))
+            else:
+                call(bwd, lib.nbasr_head_bwd, dt, _ptr(head['hseq'], PAD_L * HP), head['gh'].Tp * HP, HP, B, Tq, HIDDEN, V,
+                     self.P(hn + '.weight'), pl.dlogits.data_ptr(), dh.data_ptr(), Tq * HIDDEN, HIDDEN, self.G(hn + '.weight'),
+                     self.G(hn + '.bias'))
             dgx = zbuf(B * Tq, H4, torch.float32)
             dgx_a = zbuf(B * Tq, H4) if dt == BF16 else dgx     # bf16 copy written by the cluster kernel itself
             call(bwd, lib.nbasr_lstm_bwd, dh.data_ptr(), Tq * HIDDEN, HIDDEN, HIDDEN, self.P(ln + '.weight_hh_l0'),

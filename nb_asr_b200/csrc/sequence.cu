@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(256, 1) head_fwd_tiled_kernel(int h_dtype, con
   extern __shared__ float sm[];
   float* ws = sm;                       // V x K
   float* hs = ws + V * K;               // HT_ROWS x (HT_KC + 1)
-  const int tid = threadIdx.x, rg = tid >> 3, c8 = tid & 7;
+  __shared__ int64_t rbase[HT_ROWS];    // element offset of each row of the tile (-1: past the end)
+  const int tid = threadIdx.x, rg = tid >> 3, c8 = tid & 7, lane = tid & 31, wrp = tid >> 5;
   for (int i = tid; i < V * K; i += blockDim.x) ws[i] = w[i];
   const int64_t nrows = (int64_t)B * T;
   const int ntiles = (int)((nrows + HT_ROWS - 1) / HT_ROWS);
@@ -172,27 +173,57 @@ __global__ void __launch_bounds__(256, 1) head_fwd_tiled_kernel(int h_dtype, con
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+    __syncthreads();
+    if (tid < HT_ROWS) {
+      const int64_t r = r0 + tid;
+      rbase[tid] = r < nrows ? (r / T) * h_bs + (r % T) * h_rs : -1;
+    }
     for (int k0 = 0; k0 < K; k0 += HT_KC) {
       __syncthreads();
-      for (int i = tid; i < HT_ROWS * HT_KC; i += blockDim.x) {
-        const int rr = i >> 6, kk = i & 63;
-        const int64_t r = r0 + rr;
-        float v = 0.f;
-        if (r < nrows && k0 + kk < K) v = ld_dt(h, h_dtype, (r / T) * h_bs + (r % T) * h_rs + k0 + kk);
-        hs[rr * (HT_KC + 1) + kk] = v;
+      // warp w stages rows w, w + 8, ...: one coalesced 128-byte (bf16) / 256-byte (fp32) row segment per pass
+      for (int rr = wrp; rr < HT_ROWS; rr += 8) {
+        const int64_t base = rbase[rr];
+        const int k = k0 + 2 * lane;
+        float v0 = 0.f, v1 = 0.f;
+        if (base >= 0) {
+          if (h_dtype == NBASR_BF16) {
+            // the dispatcher guarantees even strides and a 4-byte aligned base, so (base + k) is a bf16x2 boundary
+            if (k + 1 < K) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const bf16*>(h) + base + k));
+              v0 = f.x; v1 = f.y;
+            } else if (k < K) {
+              v0 = __bfloat162float(reinterpret_cast<const bf16*>(h)[base + k]);
+            }
+          } else {
+            if (k < K) v0 = reinterpret_cast<const float*>(h)[base + k];
+            if (k + 1 < K) v1 = reinterpret_cast<const float*>(h)[base + k + 1];
+          }
+        }
+        hs[rr * (HT_KC + 1) + 2 * lane] = v0;
+        hs[rr * (HT_KC + 1) + 2 * lane + 1] = v1;
       }
       __syncthreads();
       const int kn = min(HT_KC, K - k0);
-      for (int kk = 0; kk < kn; ++kk) {
-        float hv[4];
+      const float* hp = hs + (4 * rg) * (HT_KC + 1);
+      const float* wp[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) hv[j] = hs[(4 * rg + j) * (HT_KC + 1) + kk];
+      for (int i = 0; i < 8; ++i) wp[i] = ws + vcls[i] * K + k0;
+      auto step = [&](int kk) {
+        float hv[4], wv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float wv = ws[vcls[i] * K + k0 + kk];
+        for (int j = 0; j < 4; ++j) hv[j] = hp[j * (HT_KC + 1) + kk];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(hv[j], wv, acc[j][i]);
-        }
+        for (int i = 0; i < 8; ++i) wv[i] = wp[i][kk];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(hv[j], wv[i], acc[j][i]);
+      };
+      if (kn == HT_KC) {
+#pragma unroll 8
+        for (int kk = 0; kk < HT_KC; ++kk) step(kk);
+      } else {
+        for (int kk = 0; kk < kn; ++kk) step(kk);
       }
     }
 #pragma unroll
@@ -502,7 +533,8 @@ int nbasr_head_fwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B
   int64_t rows = (int64_t)B * T;
   if (rows == 0) return 0;
   const size_t smt = sizeof(float) * ((size_t)V * K + HT_ROWS * (HT_KC + 1));
-  if (smt <= 200 * 1024 && rows >= 4 * HT_ROWS && !getenv("NBASR_HEAD_V1")) {
+  const bool aligned = h_dtype != NBASR_BF16 || (((h_bs | h_rs) & 1) == 0 && ((uintptr_t)h & 3) == 0);
+  if (smt <= 200 * 1024 && rows >= 4 * HT_ROWS && aligned && !getenv("NBASR_HEAD_V1")) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(head_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     int grid = (int)std::min<int64_t>((rows + HT_ROWS - 1) / HT_ROWS, nbasr_sm_count());

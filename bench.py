@@ -147,7 +147,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = os.environ.get('NBASR_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL's banner / warnings go to stderr
+        os.environ['NCCL_DEBUG'] = os.environ.get('NBASR_NCCL_DEBUG', 'WARN')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     B, T = args.batch, args.frames
     nb.set_seed(1235)

@@ -242,6 +242,17 @@ typedef struct nbasr_pack_job {
 } nbasr_pack_job;
 int nbasr_pack_batch(const nbasr_pack_job* jobs, int n, const int32_t* blockmap, int64_t blocks, void* stream);
 
+/* Log-mel front end (training/torch/timit.py:90-95: torchaudio MelSpectrogram(16 kHz, n_fft = win = 400, hop 160,
+ * 80 mels) -> log -> (x - mean) / (var + eps), then the zero padding of collate_fn, timit.py:104).
+ * wav (B, L) fp32 zero padded, len[b] samples (> 200); dft (402, 400) fp32 = Hann-windowed cos | -sin rows,
+ * melfb (80, 208) fp32 = transposed HTK filterbank (201 bins, zero padded); mean / var (80).
+ * out (B, 80, T) fp32 with T >= 1 + L / 160: frames t < 1 + len[b] / 160 hold the features, the rest 0.
+ * work: nbasr_logmel_work_floats(B, L) floats. */
+int nbasr_logmel(const float* wav, const int64_t* len, int B, int64_t L, const float* dft, const float* melfb,
+                 const float* mean, const float* var, float eps, float* out, int T, float* work, int64_t work_floats,
+                 void* stream);
+int64_t nbasr_logmel_work_floats(int B, int64_t L);
+
 /* misc */
 int nbasr_fill_u32(uint32_t* p, uint32_t val, int64_t n, void* stream);
 int nbasr_version(void);

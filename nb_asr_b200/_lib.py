@@ -64,6 +64,8 @@ _SIGS = {
     'nbasr_greedy_per': [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp, _vp],
     'nbasr_optim_step': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, C.c_int, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp],
+    'nbasr_logmel': [_vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _f32, _vp, C.c_int, _vp, _i64, _vp],
+    'nbasr_logmel_work_floats': [C.c_int, _i64],
     'nbasr_pack_batch': [_vp, C.c_int, _vp, _i64, _vp],
     'nbasr_fill_u32': [_vp, C.c_uint32, _i64, _vp],
     'nbasr_version': [],
@@ -100,6 +102,7 @@ def load():
         fn.argtypes = args
         fn.restype = C.c_int
     lib.nbasr_gconv_mma_pack_elems.restype = C.c_int64
+    lib.nbasr_logmel_work_floats.restype = C.c_int64
     lib.nbasr_last_error.restype = C.c_char_p
     lib.nbasr_last_error.argtypes = []
     _lib = lib

@@ -214,6 +214,13 @@ __device__ __forceinline__ void epilogue_chunk(const nbasr_epilogue& e, int64_t 
   else epilogue_cols<32, false>(e, rho, c0, ncol - c0, v);
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still draining; it must call pdl_wait() before its first access to global memory (the wait returns when the
+// predecessor has completed and flushed), and calls pdl_launch_dependents() at its start so that ITS successor's
+// prologue (barrier init, TMEM allocation, descriptor prefetch) and launch latency overlap its own tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

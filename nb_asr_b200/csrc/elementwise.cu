@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(512, 1) layernorm_bwd_bf16_kernel(
   const int64_t nrows = (int64_t)B * Tt;
   float* gs = reinterpret_cast<float*>(lnsm);
   uint8_t* wbuf = lnsm + C * 4 + (size_t)wib * 4 * rowb;     // [2 buffers][x row | dy row]
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < C; i += blockDim.x) gs[i] = gamma[i];
   __syncthreads();
 
@@ -326,6 +328,8 @@ __global__ void __launch_bounds__(512, 1) layernorm_fwd_bf16_kernel(const bf16* 
   const int64_t nrows = (int64_t)B * Tt;
   float* gs = reinterpret_cast<float*>(lnsm);          // gamma | beta
   uint8_t* wbuf = lnsm + C * 8 + (size_t)wib * LNF_D * rowb;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < C; i += blockDim.x) { gs[i] = gamma[i]; gs[C + i] = beta[i]; }
   __syncthreads();
   auto rho_of = [&](int64_t r) { return (r / Tt) * Tp + NBASR_PAD_L + (r % Tt); };
@@ -523,7 +527,7 @@ int nbasr_layernorm_fwd(int dtype, const void* x, void* y, int B, int T, int Tp,
       cudaFuncSetAttribute(layernorm_fwd_bf16_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr2 = true;
     }
-#define NBASR_LNF(Q) layernorm_fwd_bf16_kernel<Q><<<grid, 512, smb, as_stream(stream)>>>((const bf16*)x, (bf16*)y, B, T, Tp, C, gamma, beta, eps, mean, rstd)
+#define NBASR_LNF(Q) launch_pdl(layernorm_fwd_bf16_kernel<Q>, dim3(grid), dim3(512), smb, as_stream(stream), 1, (const bf16*)x, (bf16*)y, B, T, Tp, C, gamma, beta, eps, mean, rstd)
     if (QN <= 3) NBASR_LNF(3);
     else if (QN == 4) NBASR_LNF(4);
     else NBASR_LNF(5);
@@ -561,7 +565,7 @@ int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* m
       cudaFuncSetAttribute(layernorm_bwd_bf16_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
       attr2 = true;
     }
-#define NBASR_LNB(Q) layernorm_bwd_bf16_kernel<Q><<<grid, 512, smb, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, B, T, Tp, C, (bf16*)dx, (bf16*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta)
+#define NBASR_LNB(Q) launch_pdl(layernorm_bwd_bf16_kernel<Q>, dim3(grid), dim3(512), smb, as_stream(stream), 1, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma, B, T, Tp, C, (bf16*)dx, (bf16*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta)
     if (QN <= 3) NBASR_LNB(3);
     else if (QN == 4) NBASR_LNB(4);
     else NBASR_LNB(5);

@@ -115,10 +115,12 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tptr), 256);
+  pdl_launch_dependents();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tm = *tptr;
+  pdl_wait();                                  // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -310,10 +312,12 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tptr), 256);
+  pdl_launch_dependents();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tm = *tptr;
+  pdl_wait();
   const bool has_work = lane_id < p.nunits;
 
   if (warp == 0) {
@@ -469,8 +473,8 @@ int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st) {
     if (e != cudaSuccess) return nbasr_fail("gconv_mma_fwd smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  gconv_mma_fwd_kernel<<<a.nslabs * a.nlanes, FWD_THREADS, smem, st>>>(tmX, tmW, tmO, tmO2, a);
-  NBASR_CHECK_LAUNCH();
+  cudaError_t le = launch_pdl(gconv_mma_fwd_kernel, dim3(a.nslabs * a.nlanes), dim3(FWD_THREADS), smem, st, 1, tmX, tmW, tmO, tmO2, a);
+  if (le != cudaSuccess) return nbasr_fail("gconv_mma_fwd launch: %s", cudaGetErrorString(le));
   return 0;
 }
 
@@ -499,8 +503,8 @@ int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C
     if (e != cudaSuccess) return nbasr_fail("gconv_mma_wgrad smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  gconv_mma_wgrad_kernel<<<a.nslabs * a.nlanes, GC_THREADS, WG_SMEM, st>>>(tmDZ, tmX, a);
-  NBASR_CHECK_LAUNCH();
+  cudaError_t le = launch_pdl(gconv_mma_wgrad_kernel, dim3(a.nslabs * a.nlanes), dim3(GC_THREADS), (size_t)WG_SMEM, st, 1, tmDZ, tmX, a);
+  if (le != cudaSuccess) return nbasr_fail("gconv_mma_wgrad launch: %s", cudaGetErrorString(le));
   return 0;
 }
 

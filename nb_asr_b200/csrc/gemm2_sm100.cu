@@ -136,11 +136,13 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
+  pdl_launch_dependents();
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();                  // both CTAs' barriers are initialised before any remote arrive / multicast
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -280,11 +282,13 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
+  pdl_launch_dependents();
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (u_begin < u_end) {
     if (warp == 0) {
@@ -413,20 +417,20 @@ int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
     if (e != cudaSuccess) return nbasr_fail("gemm_tn_pair smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
   // persistent pairs: never launch more clusters than can be co-resident (a second wave would double the time)
   static int max_pairs = 0;
   if (!max_pairs) {
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
     cfg.gridDim = dim3(sms);
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, gemm_tn_pair_kernel, &cfg) != cudaSuccess || n < 1) n = sms / 2;
@@ -434,8 +438,7 @@ int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
     if (getenv("NBASR_DEBUG")) fprintf(stderr, "[nbasr] gemm_tn_pair: %d co-resident CTA pairs on %d SMs\n", max_pairs, sms);
   }
   const int npairs = std::max(1, std::min(a.pair_tiles, max_pairs));
-  cfg.gridDim = dim3(2 * npairs);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_pair_kernel, tmA, tmB, a);
+  cudaError_t e = launch_pdl(gemm_tn_pair_kernel, dim3(2 * npairs), dim3(THREADS), (size_t)SMEM_BYTES, st, 2, tmA, tmB, a);
   if (e != cudaSuccess) return nbasr_fail("gemm_tn_pair launch: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -482,19 +485,7 @@ int sm100_gemm_wgrad_pair(const nbasr_wgrad* g, cudaStream_t st) {
     if (e != cudaSuccess) return nbasr_fail("gemm_wgrad_pair smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(ctas, splits);
-  cfg.blockDim = dim3(WG2_THREADS);
-  cfg.dynamicSmemBytes = WG2_SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_wgrad_pair_kernel, tmDY, tmX, a);
+  cudaError_t e = launch_pdl(gemm_wgrad_pair_kernel, dim3(ctas, splits), dim3(WG2_THREADS), (size_t)WG2_SMEM_BYTES, st, 2, tmDY, tmX, a);
   if (e != cudaSuccess) return nbasr_fail("gemm_wgrad_pair launch: %s", cudaGetErrorString(e));
   return 0;
 }

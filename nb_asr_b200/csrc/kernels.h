@@ -5,6 +5,34 @@
 
 #include "../../include/nbasr.h"
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait() in common.cuh) and an optional cluster
+// width.  NBASR_NO_PDL=1 disables the attribute (plain stream ordering).
+#ifdef __CUDACC__
+#include <cstdlib>
+#include <utility>
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  static const bool pdl = getenv("NBASR_NO_PDL") == nullptr;
+  if (pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#endif
+
 // C[i, j] = sum_{kb, kr} A[ib*a_ib + ir*a_ir + kb*a_kb + kr*a_kr] * B[j*b_j + kb*b_kb + kr*b_kr]
 // with i = (ib, ir); output row rho = o_r0 + ib*o_bs + ir*o_rs.
 struct SimtGemmArgs {

@@ -214,6 +214,15 @@ int nbasr_greedy_per(const float* logp, int B, int T, int V, const int64_t* audi
                      int32_t* hyp, int32_t* hyp_len, int32_t* dist, double* per, int32_t* work,
                      void* stream);
 
+/* CTC prefix beam search + fold + Levenshtein PER: what Trainer.decode calls in the reference (trainer.py:71,236:
+ * ctcdecode.CTCBeamDecoder(labels, beam_width=12, log_probs_input=True), defaults cutoff_top_n=40, no LM).  Same
+ * arguments as nbasr_greedy_per plus beam_width (<= 16) and cutoff_top_n (<= 0: all classes); raw (B,T) / raw_len (B)
+ * receive the unfolded best prefix of every utterance. */
+int nbasr_beam_per(const float* logp, int B, int T, int V, const int64_t* audio_len, int len_div, int beam_width,
+                   int cutoff_top_n, const int32_t* targets, int S, const int64_t* targets_len, const int32_t* lut,
+                   int32_t* raw, int32_t* raw_len, int32_t* hyp, int32_t* hyp_len, int32_t* dist, double* per,
+                   int32_t* work, void* stream);
+
 /* Optimiser tail of Trainer.step (trainer.py:221-225): regulariser 0.01*sum_i ||W_i||_F over the
  * PadConvRelu weights (segments), clip_grad_norm_(5), Adam(eps=1e-7).  Flat fp32 buffers of n
  * elements.  seg_off/seg_len (nseg, int64, device) delimit the regularised tensors.

@@ -430,12 +430,160 @@ __global__ void ctc_kernel(const float* __restrict__ logp, int B, int T, int V, 
   }
 }
 
-// ---------------------------------------------------------------- greedy decode + PER
+// ---------------------------------------------------------------- CTC prefix beam search (width <= 16)
+// What Trainer.decode actually calls (trainer.py:71,236): ctcdecode.CTCBeamDecoder(labels, beam_width=12,
+// log_probs_input=True) with its defaults -- no language model, cutoff_top_n = 40, cutoff_prob = 1, blank 0.  The
+// library (parlance/ctcdecode @9a20e00f, not under /root/reference) implements the prefix beam search of the
+// PaddlePaddle DeepSpeech decoder; restated here (and in oracle/decode_np.py:beam_search) as:
+//   per frame: keep the 40 most probable classes; for every beam prefix l (p_b, p_nb = log-prob of l ending in blank /
+//   non-blank, score = logaddexp):  blank -> p_b'(l) += lp[0] + score(l);  c = last(l) -> p_nb'(l) += lp[c] + p_nb(l);
+//   extension l+c -> p_nb'(l+c) += lp[c] + (c == last(l) ? p_b(l) : score(l)), merged with l+c if that prefix is in the
+//   beam already; keep the `width` best prefixes by score'.  Scores are fp64 here and in the oracle (ctcdecode uses
+//   fp32); ties break on (last label, slot).  Output: best prefix per utterance.  One CTA per utterance.
+constexpr int BS_MAXW = 16;
+constexpr int BS_MAXV = 64;
+constexpr int BS_MAXC = BS_MAXW * BS_MAXV + BS_MAXW;       // candidate slots per frame
+
+__device__ __forceinline__ double bs_logadd(double a, double b) {
+  if (a == -CUDART_INF) return b;
+  if (b == -CUDART_INF) return a;
+  const double m = fmax(a, b);
+  return m + log(exp(a - m) + exp(b - m));
+}
+
+__global__ void __launch_bounds__(256) beam_search_kernel(const float* __restrict__ logp, int B, int T, int V,
+                                                          const int64_t* __restrict__ audio_len, int len_div, int width, int top_n,
+                                                          int32_t* __restrict__ out, int32_t* __restrict__ out_len) {
+  extern __shared__ int16_t bs_seq[];               // [2][width][T]
+  __shared__ double lp[BS_MAXV];
+  __shared__ int keep[BS_MAXV];
+  __shared__ double pb[BS_MAXW], pnb[BS_MAXW], sc[BS_MAXW];      // current beam (previous frame's p_b, p_nb, score)
+  __shared__ int blen[BS_MAXW], blast[BS_MAXW];
+  __shared__ unsigned long long bhash[BS_MAXW];
+  __shared__ double c_pb[BS_MAXC], c_pnb[BS_MAXC], c_sc[BS_MAXC];
+  __shared__ int c_par[BS_MAXC], c_chr[BS_MAXC], c_ok[BS_MAXC];
+  __shared__ int win[BS_MAXW];
+  __shared__ int s_n;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  int Tb = (int)(audio_len[b] / len_div);
+  if (Tb > T) Tb = T;
+  const float* lpg = logp + (int64_t)b * T * V;
+  int cur = 0;
+  if (tid == 0) {           // root prefix: empty, p_b = 0 (log 1), p_nb = -inf
+    s_n = 1; pb[0] = 0.0; pnb[0] = -CUDART_INF; sc[0] = 0.0; blen[0] = 0; blast[0] = -1; bhash[0] = 1469598103934665603ull;
+  }
+  __syncthreads();
+  for (int t = 0; t < Tb; ++t) {
+    const int n = s_n;
+    if (tid < V) lp[tid] = (double)lpg[(int64_t)t * V + tid];
+    __syncthreads();
+    if (tid < V) {          // rank among the frame's classes (larger first, ties by index): keep the top_n
+      int r = 0;
+      const double me = lp[tid];
+      for (int c = 0; c < V; ++c) r += (lp[c] > me || (lp[c] == me && c < tid)) ? 1 : 0;
+      keep[tid] = r < top_n;
+    }
+    const int nslots = n + n * V;
+    for (int s = tid; s < nslots; s += blockDim.x) c_ok[s] = 0;
+    __syncthreads();
+    // existing prefixes: slot i
+    if (tid < n) {
+      const int i = tid;
+      c_pb[i] = keep[0] ? sc[i] + lp[0] : -CUDART_INF;
+      c_pnb[i] = (blast[i] > 0 && keep[blast[i]]) ? lp[blast[i]] + pnb[i] : -CUDART_INF;
+      c_par[i] = i; c_chr[i] = -1; c_ok[i] = 1;
+    }
+    __syncthreads();
+    // extensions: slot n + i*V + c
+    for (int e = tid; e < n * V; e += blockDim.x) {
+      const int i = e / V, c = e - i * V;
+      if (c == 0 || !keep[c]) continue;
+      const double l = (c == blast[i]) ? (pb[i] == -CUDART_INF ? -CUDART_INF : lp[c] + pb[i]) : lp[c] + sc[i];
+      if (l == -CUDART_INF) continue;
+      // is prefix_i + c already in the beam?  (len, last, hash, then the labels themselves)
+      const unsigned long long h = bhash[i] * 1099511628211ull + (unsigned long long)c;
+      int j_same = -1;
+      for (int j = 0; j < n; ++j) {
+        if (blen[j] == blen[i] + 1 && blast[j] == c && bhash[j] == h) {
+          const int16_t* a = bs_seq + ((size_t)cur * width + i) * T;
+          const int16_t* q = bs_seq + ((size_t)cur * width + j) * T;
+          bool eq = true;
+          for (int k = 0; k < blen[i]; ++k) eq = eq && (a[k] == q[k]);
+          if (eq) { j_same = j; break; }
+        }
+      }
+      const int s = n + e;
+      c_pb[s] = -CUDART_INF; c_pnb[s] = l; c_par[s] = i; c_chr[s] = c;
+      c_ok[s] = j_same < 0 ? 1 : -(j_same + 1);          // negative: merge into existing slot j_same
+    }
+    __syncthreads();
+    // merges: at most one parent per existing prefix, so slot j is updated by exactly one thread
+    for (int s = n + tid; s < nslots; s += blockDim.x)
+      if (c_ok[s] < 0) { const int j = -c_ok[s] - 1; c_pnb[j] = bs_logadd(c_pnb[j], c_pnb[s]); c_ok[s] = 0; }
+    __syncthreads();
+    for (int s = tid; s < nslots; s += blockDim.x)
+      if (c_ok[s]) {
+        c_sc[s] = bs_logadd(c_pb[s], c_pnb[s]);
+        if (c_sc[s] == -CUDART_INF) c_ok[s] = 0;         // dead prefix (possible when blank / last label were cut off)
+      }
+    __syncthreads();
+    // top `width` by (score desc, last label asc, slot asc): rank by counting
+    if (tid < BS_MAXW) win[tid] = -1;
+    __syncthreads();
+    for (int s = tid; s < nslots; s += blockDim.x) {
+      if (!c_ok[s]) continue;
+      const double me = c_sc[s];
+      const int mc = c_chr[s] >= 0 ? c_chr[s] : blast[c_par[s]];
+      int r = 0;
+      for (int u = 0; u < nslots; ++u) {
+        if (!c_ok[u] || u == s) continue;
+        const double ot = c_sc[u];
+        const int oc = c_chr[u] >= 0 ? c_chr[u] : blast[c_par[u]];
+        if (ot > me || (ot == me && (oc < mc || (oc == mc && u < s)))) ++r;
+      }
+      if (r < width) win[r] = s;
+    }
+    __syncthreads();
+    int nn = 0;
+    for (int r = 0; r < width; ++r) nn += win[r] >= 0 ? 1 : 0;      // winners fill ranks 0..nn-1 contiguously
+    // new beam into the other half of the label store
+    for (int r = 0; r < nn; ++r) {
+      const int s = win[r], i = c_par[s];
+      const int16_t* a = bs_seq + ((size_t)cur * width + i) * T;
+      int16_t* q = bs_seq + ((size_t)(cur ^ 1) * width + r) * T;
+      for (int k = tid; k < blen[i]; k += blockDim.x) q[k] = a[k];
+      if (tid == 0 && c_chr[s] >= 0) q[blen[i]] = (int16_t)c_chr[s];
+    }
+    __syncthreads();
+    double npb = 0, npnb = 0, nsc = 0; int nlen = 0, nlast = 0; unsigned long long nh = 0;
+    if (tid < nn) {
+      const int s = win[tid], i = c_par[s];
+      npb = c_pb[s]; npnb = c_pnb[s]; nsc = c_sc[s];
+      nlen = blen[i] + (c_chr[s] >= 0 ? 1 : 0);
+      nlast = c_chr[s] >= 0 ? c_chr[s] : blast[i];
+      nh = c_chr[s] >= 0 ? bhash[i] * 1099511628211ull + (unsigned long long)c_chr[s] : bhash[i];
+    }
+    __syncthreads();
+    if (tid < nn) { pb[tid] = npb; pnb[tid] = npnb; sc[tid] = nsc; blen[tid] = nlen; blast[tid] = nlast; bhash[tid] = nh; }
+    if (tid == 0) s_n = nn;
+    cur ^= 1;
+    __syncthreads();
+  }
+  // best prefix = rank 0 of the last selection (the root if there were no frames)
+  const int L = s_n > 0 ? blen[0] : 0;
+  const int16_t* a = bs_seq + ((size_t)cur * width + 0) * T;
+  for (int k = tid; k < T; k += blockDim.x) out[(int64_t)b * T + k] = k < L ? (int32_t)a[k] : 0;
+  if (tid == 0) out_len[b] = L;
+}
+
+// ---------------------------------------------------------------- greedy decode (or a given hypothesis) + PER
+// pre_hyp / pre_len (optional): unfolded label sequences from beam_search_kernel, used instead of the argmax path.
 __global__ void greedy_per_kernel(const float* __restrict__ logp, int B, int T, int V, const int64_t* __restrict__ audio_len,
                                   int len_div, const int32_t* __restrict__ targets, int S,
                                   const int64_t* __restrict__ targets_len, const int32_t* __restrict__ lut,
                                   int32_t* __restrict__ hyp, int32_t* __restrict__ hyp_len, int32_t* __restrict__ dist,
-                                  double* __restrict__ per, int32_t* __restrict__ work) {
+                                  double* __restrict__ per, int32_t* __restrict__ work, const int32_t* __restrict__ pre_hyp,
+                                  const int32_t* __restrict__ pre_len) {
   extern __shared__ int smi[];
   int* best = smi;              // T
   int* hy = best + T;           // T
@@ -448,7 +596,7 @@ __global__ void greedy_per_kernel(const float* __restrict__ logp, int B, int T, 
   int Tb = (int)(audio_len[b] / len_div);
   if (Tb > T) Tb = T;
   const float* lp = logp + (int64_t)b * T * V;
-  for (int t = threadIdx.x; t < Tb; t += blockDim.x) {
+  for (int t = threadIdx.x; t < Tb && !pre_hyp; t += blockDim.x) {
     const float* row = lp + (int64_t)t * V;
     float bv = row[0];
     int bi = 0;
@@ -461,13 +609,22 @@ __global__ void greedy_per_kernel(const float* __restrict__ logp, int B, int T, 
   __syncthreads();
   if (threadIdx.x == 0) {
     int n = 0, prev = -1;
-    for (int t = 0; t < Tb; ++t) {
-      int c = best[t];
-      if (c != prev && c != 0) {
+    if (pre_hyp) {
+      const int L = min(pre_len[b], T);
+      for (int k = 0; k < L; ++k) {
+        int c = pre_hyp[(int64_t)b * T + k];
         int f = lut ? lut[c] : c;
         if (f != 0) hy[n++] = f;
       }
-      prev = c;
+    } else {
+      for (int t = 0; t < Tb; ++t) {
+        int c = best[t];
+        if (c != prev && c != 0) {
+          int f = lut ? lut[c] : c;
+          if (f != 0) hy[n++] = f;
+        }
+        prev = c;
+      }
     }
     s_n = n;
     int m = 0;
@@ -613,7 +770,31 @@ int nbasr_greedy_per(const float* logp, int B, int T, int V, const int64_t* audi
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(greedy_per_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   greedy_per_kernel<<<B, 256, sm, as_stream(stream)>>>(logp, B, T, V, audio_len, len_div, targets, S, targets_len, lut, hyp,
-                                                       hyp_len, dist, per, work);
+                                                       hyp_len, dist, per, work, nullptr, nullptr);
+  NBASR_CHECK_LAUNCH();
+  return 0;
+}
+
+int nbasr_beam_per(const float* logp, int B, int T, int V, const int64_t* audio_len, int len_div, int beam_width, int cutoff_top_n,
+                   const int32_t* targets, int S, const int64_t* targets_len, const int32_t* lut, int32_t* raw, int32_t* raw_len,
+                   int32_t* hyp, int32_t* hyp_len, int32_t* dist, double* per, int32_t* work, void* stream) {
+  if (B == 0) return 0;
+  NBASR_REQUIRE(beam_width >= 1 && beam_width <= BS_MAXW && V <= BS_MAXV && T < 32768, "beam search shape");
+  const size_t smb = (size_t)2 * beam_width * T * sizeof(int16_t);
+  NBASR_REQUIRE(smb <= 150 * 1024, "sequence too long for the beam-search kernel");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
+    cudaFuncSetAttribute(greedy_per_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  beam_search_kernel<<<B, 256, smb, as_stream(stream)>>>(logp, B, T, V, audio_len, len_div, beam_width,
+                                                         cutoff_top_n > 0 ? cutoff_top_n : V, raw, raw_len);
+  NBASR_CHECK_LAUNCH();
+  size_t sm = sizeof(int) * ((size_t)2 * T + S + 3 * (S + 1));
+  NBASR_REQUIRE(sm <= 200 * 1024, "sequence too long for the decode kernel");
+  greedy_per_kernel<<<B, 256, sm, as_stream(stream)>>>(logp, B, T, V, audio_len, len_div, targets, S, targets_len, lut, hyp,
+                                                       hyp_len, dist, per, work, raw, raw_len);
   NBASR_CHECK_LAUNCH();
   return 0;
 }

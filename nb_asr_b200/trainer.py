@@ -346,8 +346,11 @@ class Trainer:
         from .distributed import allreduce_mean_
         allreduce_mean_(eng.flat_g)
 
-    def decode(self, output, output_len, val_inputs):
-        """Greedy CTC decode + 48->39 fold + PER (batch mean of edit_distance / ref_len)."""
+    def decode(self, output, output_len, val_inputs, beam_width=None):
+        """CTC decode + 48->39 fold + PER (batch mean of edit_distance / ref_len).
+
+        Default (north_star): greedy decode.  ``beam_width=12`` (or ``trainer.beam_width = 12``) runs the prefix beam
+        search the reference's CTCBeamDecoder performs (trainer.py:71,236) -- see nbasr_beam_per."""
         _, (targets, targets_len) = val_inputs
         dev = self.device
         targets = targets.to(device=dev, dtype=torch.int32).contiguous()
@@ -359,10 +362,20 @@ class Trainer:
         ws = _ws.get(dev, B, T, V, S)
         lib = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.nbasr_greedy_per(output.data_ptr(), B, T, V, output_len.data_ptr(), 1, targets.data_ptr(), S,
-                                        targets_len.data_ptr(), self._lut.data_ptr() if self._lut is not None else None,
-                                        ws.hyp.data_ptr(), ws.hyp_len.data_ptr(), ws.dist.data_ptr(), ws.per.data_ptr(),
-                                        ws.iwork.data_ptr(), st), 'greedy_per')
+        bw = beam_width if beam_width is not None else getattr(self, 'beam_width', None)
+        lut = self._lut.data_ptr() if self._lut is not None else None
+        if bw:
+            raw = torch.empty((B, T), dtype=torch.int32, device=dev)
+            raw_len = torch.empty((B,), dtype=torch.int32, device=dev)
+            _lib.check(lib.nbasr_beam_per(output.data_ptr(), B, T, V, output_len.data_ptr(), 1, int(bw), 40, targets.data_ptr(), S,
+                                          targets_len.data_ptr(), lut, raw.data_ptr(), raw_len.data_ptr(), ws.hyp.data_ptr(),
+                                          ws.hyp_len.data_ptr(), ws.dist.data_ptr(), ws.per.data_ptr(), ws.iwork.data_ptr(), st),
+                       'beam_per')
+            self.last_beam = (raw, raw_len)
+        else:
+            _lib.check(lib.nbasr_greedy_per(output.data_ptr(), B, T, V, output_len.data_ptr(), 1, targets.data_ptr(), S,
+                                            targets_len.data_ptr(), lut, ws.hyp.data_ptr(), ws.hyp_len.data_ptr(),
+                                            ws.dist.data_ptr(), ws.per.data_ptr(), ws.iwork.data_ptr(), st), 'greedy_per')
         self.last_hyp = (ws.hyp, ws.hyp_len, ws.dist)
         return ws.per[0].clone()
 

@@ -132,3 +132,93 @@ class AvgMeter:
 
     def get(self):
         return self.avg
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CTC prefix beam search -- what Trainer.decode really calls (trainer.py:71,236): ctcdecode.CTCBeamDecoder(labels,
+# beam_width=12, log_probs_input=True).  The library is a third-party dependency that is NOT under /root/reference
+# (parlance/ctcdecode, git 9a20e00f34d8f605f4a8501cc42b1a53231f1597, setup.py:49); its published algorithm (the
+# PaddlePaddle DeepSpeech prefix beam search without a language model: defaults cutoff_top_n=40, cutoff_prob=1.0,
+# blank_id=0) is restated below.  PARITY UNPINNED: the reference holds no test or golden vector for this boundary and
+# the library cannot be run here.  Deliberate differences, shared with the CUDA kernel so the two agree bit-exactly:
+# scores are fp64 (ctcdecode: fp32), ties are broken on (last label, candidate slot), and an extension whose
+# probability is exactly zero is not created.
+# ---------------------------------------------------------------------------------------------------------------------
+def _logadd(a, b):
+    if a == -np.inf:
+        return b
+    if b == -np.inf:
+        return a
+    m = max(a, b)
+    return m + np.log(np.exp(a - m) + np.exp(b - m))
+
+
+def beam_search(logp, out_len, beam_width=12, cutoff_top_n=40):
+    """logp (B,T,V) log-probs, out_len (B,) -> list of int32 label arrays (best prefix per utterance, unfolded)."""
+    logp = np.asarray(logp, dtype=np.float64)
+    B, T, V = logp.shape
+    top_n = cutoff_top_n if cutoff_top_n and cutoff_top_n > 0 else V
+    res = []
+    for b in range(B):
+        # beam entry: (labels tuple, p_b, p_nb, score)
+        beam = [((), 0.0, -np.inf, 0.0)]
+        for t in range(int(out_len[b])):
+            lp = logp[b, t]
+            rank = np.array([sum(1 for c in range(V) if lp[c] > lp[v] or (lp[c] == lp[v] and c < v)) for v in range(V)])
+            keep = rank < top_n
+            n = len(beam)
+            slots = {}                                   # slot index -> [labels, p_b, p_nb, parent, char]
+            for i, (lab, pb, pnb, sc) in enumerate(beam):
+                last = lab[-1] if lab else -1
+                npb = sc + lp[0] if keep[0] else -np.inf
+                npnb = lp[last] + pnb if (last > 0 and keep[last]) else -np.inf
+                slots[i] = [lab, npb, npnb, i, -1]
+            index = {e[0]: i for i, e in enumerate(beam)}
+            for i, (lab, pb, pnb, sc) in enumerate(beam):
+                last = lab[-1] if lab else -1
+                for c in range(1, V):
+                    if not keep[c]:
+                        continue
+                    if c == last:
+                        l = -np.inf if pb == -np.inf else lp[c] + pb
+                    else:
+                        l = lp[c] + sc
+                    if l == -np.inf:
+                        continue
+                    new = lab + (c,)
+                    j = index.get(new)
+                    if j is not None:                    # prefix already in the beam: merge
+                        slots[j][2] = _logadd(slots[j][2], l)
+                    else:
+                        slots[n + i * V + c] = [new, -np.inf, l, i, c]
+            cand = []
+            for s, (lab, pb, pnb, par, ch) in slots.items():
+                sc = _logadd(pb, pnb)
+                if sc == -np.inf:
+                    continue
+                lastc = ch if ch >= 0 else (beam[par][0][-1] if beam[par][0] else -1)
+                cand.append((-sc, lastc, s, lab, pb, pnb, sc))
+            cand.sort(key=lambda x: (x[0], x[1], x[2]))
+            beam = [(x[3], x[4], x[5], x[6]) for x in cand[:beam_width]]
+        res.append(np.array(beam[0][0] if beam else (), dtype=np.int32))
+    return res
+
+
+def per_from_hyps(hyps, targets, targets_len, fold=True):
+    """PER of given (unfolded) hypotheses; same conventions as per_batch."""
+    dists, rlens, fh = [], [], []
+    for b, h in enumerate(hyps):
+        ref = np.asarray(targets[b, :int(targets_len[b])], dtype=np.int32)
+        h = np.asarray(h, dtype=np.int32)
+        if fold:
+            h = FOLD_LUT[h]
+            ref = FOLD_LUT[ref]
+        h = h[h != 0]
+        ref = ref[ref != 0]
+        dists.append(levenshtein(h, ref))
+        rlens.append(int(targets_len[b]))
+        fh.append(h)
+    acc = 0.0
+    for d, r in zip(dists, rlens):
+        acc += float(d) / float(r)
+    return acc / len(dists), np.array(dists, np.int32), np.array(rlens, np.int32), fh

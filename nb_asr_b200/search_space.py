@@ -1,8 +1,7 @@
 """Search-space helpers needed by the model builder and the sweep driver.
 
 Mirrors the public names of nasbench_asr/search_space.py (all_ops :6, get_search_space :11-18,
-get_all_architectures :32-47, arch_vec_to_names :77-93). Graph hashing / dedupe
-(graph_utils.py) is out of scope.
+get_all_architectures :32-47, arch_vec_to_names :77-93, get_model_hash :21-29 -> graph_utils.py).
 """
 import itertools
 
@@ -33,6 +32,12 @@ def get_all_architectures(ops=None, nodes=None):
 def arch_vec_to_names(arch_vec, ops=None):
     # NB: the reference ignores `ops` and always indexes the global table (search_space.py:93).
     return [[all_ops[node[0]]] + list(node[1:]) for node in arch_vec]
+
+
+def get_model_hash(arch_vec, ops=None, minimize=True):
+    """search_space.py:21-29"""
+    from .graph_utils import get_model_hash as _h
+    return _h(arch_vec, ops=ops, minimize=minimize)
 
 
 def validate_arch(arch_vec):

@@ -4,8 +4,10 @@ reported as one row.  Candidates are independent: rank r evaluates its shard (nb
 no collective touches the data path, rows are gathered on rank 0.
 
     torchrun --nproc-per-node 8 -m nb_asr_b200.sweep --limit 64
-The reference has no sweep driver; enumeration follows search_space.get_all_architectures.
-Graph-isomorphism dedupe (graph_utils.py) is out of scope: pass an explicit --arch-file to evaluate unique archs only.
+The reference has no sweep driver; enumeration follows search_space.get_all_architectures and, by
+default, keeps the first arch_vec of every graph-isomorphism class (graph_utils.get_model_hash: 13 824 -> 8 242).
+``--out-pickle`` writes an nb-asr style table (README "Dataset format": pickle.dump(header) then pickle.dump(rows),
+row order = header['columns']).
 """
 import argparse
 import json
@@ -14,7 +16,9 @@ import time
 
 import torch
 
-from . import PhonemeEncoder, data, distributed, get_loss, get_model, get_trainer, search_space, set_seed
+import pickle
+
+from . import PhonemeEncoder, data, distributed, get_loss, get_model, get_trainer, graph_utils, search_space, set_seed
 
 
 def evaluate_arch(arch, batches, gpu, precision='bf16', seed=1235):
@@ -44,6 +48,8 @@ def main():
     ap.add_argument('--precision', default='bf16')
     ap.add_argument('--balance', default='lpt', choices=['lpt', 'rr'])
     ap.add_argument('--out', default=None)
+    ap.add_argument('--out-pickle', default=None, help='nb-asr style table: header, then rows')
+    ap.add_argument('--all', action='store_true', help='evaluate every arch_vec, not one per isomorphism class')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -53,8 +59,10 @@ def main():
         torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local))
     if args.arch_file:
         archs = json.load(open(args.arch_file))
-    else:
+    elif args.all:
         archs = list(search_space.get_all_architectures())
+    else:
+        archs = [a for _, a in graph_utils.get_unique_architectures()]
     archs = archs[:args.limit] if args.limit else archs
     mine = distributed.shard_archs(archs, rank, world, balance=args.balance, frames=args.frames)
     batches = [data.make_batch(args.batch, args.frames, seed=100 + i, min_len=args.frames // 3) for i in range(args.n_batches)]
@@ -65,6 +73,7 @@ def main():
     for i in mine:
         r = evaluate_arch(archs[i], batches, local, args.precision)
         r['index'] = i
+        r['hash'] = graph_utils.get_model_hash(archs[i])
         rows.append(r)
     torch.cuda.synchronize()
     dt = time.time() - t0
@@ -76,6 +85,14 @@ def main():
         print(json.dumps(summary))
         if args.out:
             json.dump(dict(summary=summary, rows=rows), open(args.out, 'w'))
+        if args.out_pickle:
+            header = dict(dataset_type='b200-sweep-eval', version=1, search_space=search_space.get_search_space(),
+                          ops=search_space.all_ops, columns=['model_hash', 'arch_vec', 'ctc_loss', 'per'], seed=1235,
+                          precision=args.precision, batch=args.batch, frames=args.frames, n_batches=args.n_batches,
+                          data='synthetic', decode='greedy')
+            with open(args.out_pickle, 'wb') as f:
+                pickle.dump(header, f)
+                pickle.dump([[r['hash'], r['arch'], r['loss'], r['per']] for r in rows], f)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -81,3 +81,19 @@ def test_avg_meter_matches_reference_formula():
     for n, v in enumerate(vals[1:], 1):
         ref = ref * (n / (n + 1)) + v / (n + 1)
     assert m.get() == ref
+
+
+def test_graph_hash_matches_reference_golden_and_kats():
+    """graph_utils.get_model_hash vs hashes produced by the real reference (oracle/make_golden_graph.py) + README KATs"""
+    import json
+    import os
+    from nb_asr_b200 import graph_utils as G
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'graph_hashes.json')))
+    for row in gold['rows']:
+        assert G.get_model_hash(row['arch']) == row['hash'], row['arch']
+    assert G.get_model_hash([[1, 0], [1, 0, 0], [1, 0, 0, 0]]) == '36855332a5778e0df5114305bc3ce238'      # README.md:61
+    uniq = G.get_unique_architectures()
+    assert gold['n_all'] == 13824 and len(uniq) == gold['n_unique'] == 8242                                # graph_utils.py:365-379
+    assert sum(1 for _, a in uniq if all(n[0] != 5 for n in a)) == 8000
+    # isomorphic pair: a `zero` node cuts the chain, the skip keeps the path -> same graph as dropping that node's op
+    assert G.get_model_hash([[5, 1], [1, 0, 0], [1, 0, 0, 0]]) != G.get_model_hash([[1, 0], [1, 0, 0], [1, 0, 0, 0]])

@@ -2,7 +2,8 @@
 
 Facade with the names of nasbench_asr/__init__.py:11-52 for the hot path:
     set_default_backend, get_backend_name, set_seed, prepare_devices, get_model, get_loss,
-    get_trainer, get_dataloaders (synthetic stand-in; the TIMIT pipeline is out of scope).
+    get_trainer, get_dataloaders (synthetic stand-in; the TIMIT file readers are out of scope, the log-mel
+    front end is nb_asr_b200.frontend).
 Everything executes through libnbasr.so (hand-written sm_100a CUDA, include/nbasr.h).
 """
 import random
@@ -10,7 +11,7 @@ import random
 import numpy
 import torch
 
-from . import data, search_space
+from . import data, graph_utils, search_space
 from .encoder import PhonemeEncoder
 from .model import ASRModel, PadConvRelu, get_model, print_model_summary
 from .trainer import AvgMeter, Trainer, get_loss, get_trainer, set_time_limit

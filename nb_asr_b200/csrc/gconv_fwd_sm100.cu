@@ -323,7 +323,10 @@ gconv_fwd_merged_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 }  // namespace
 
 int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st);   // per-tap kernel (gconv_sm100.cu)
+int sm100_gconv_fwd_frag(const nbasr_gconv* g, cudaStream_t st); // mma.sync kernel (gconv_frag_sm100.cu)
 extern unsigned long long* g_gconv_dbg;
+int g_gconv_impl = 0;   // 0 = tcgen05 per-tap kernel (default), 1 = warp-level MMA kernel
+extern "C" void nbasr_dbg_gconv_impl(int impl) { g_gconv_impl = impl; }
 
 int sm100_gconv_fwd(const nbasr_gconv* g, cudaStream_t st) {
   // Default = the per-tap kernel.  The tap-merged kernel below is numerically identical (same tests) and cuts the MMA
@@ -331,6 +334,12 @@ int sm100_gconv_fwd(const nbasr_gconv* g, cudaStream_t st) {
   // issue-bound) ends up slower on B200: C=1000 k=5 cold-L2 72.6 us (m=2) / 108 us (m=3) vs 56 us.  NBASR_GCONV_MERGED=1
   // selects it for experiments (tools/bench_gconv.py, tools/trace_gconv.py).
   static const char* merged = getenv("NBASR_GCONV_MERGED");
+  static const char* frag = getenv("NBASR_GCONV_FRAG");
+  // Warp-level MMA kernel (gconv_frag_sm100.cu): correct (same tests) but instruction-issue bound on B200 -- ~6 600 issued
+  // warp instructions per 128 x 48 tile against 4 400 issue slots at HBM speed (ncu, profiles/r1_gconv_frag_experiment.txt):
+  // 75-99 us vs 55 us for C=1000 k=5.  Experimental: NBASR_GCONV_FRAG=1 or nbasr_dbg_gconv_impl(1).
+  if ((frag || g_gconv_impl == 1) && (g->ktaps == 5 || g->ktaps == 7) && g->cpg <= 16 && (g->cpg == 10 ? 40 : 48) % g->cpg == 0 && g->C % 8 == 0)
+    return sm100_gconv_fwd_frag(g, st);
   if (!merged) return sm100_gconv_fwd_v1(g, st);
   Args a{};
   a.B = g->B; a.T = g->T; a.Tp = g->Tp; a.C = g->C; a.OUT = g->cpg == 10 ? 40 : 48;

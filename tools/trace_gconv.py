@@ -40,6 +40,18 @@ for name, kw in (('full', dict(bias=bias, relu=1, out=out, mask_out=mask, mask_w
     t = buf.view(8, 64, 8).cpu()
     t0 = int(t[t > 0].min())
     print('=== variant', name)
+    if os.environ.get('NBASR_GCONV_UMMA') is None:
+        # fragment kernel (gconv_frag_sm100.cu): clock64 stamps of one SM -> cycles
+        for cta in (0, 1):
+            print(f'CTA {cta}: item | prod_issue | wait_begin full_ok mma_done epi_done bar_done store_issued  (cycles since the CTA\'s first stamp)')
+            tc = t[cta]
+            c0 = int(tc[tc > 0].min())
+            for it in range(8, 16):
+                r = tc[it]
+                if r[1] == 0:
+                    break
+                print(f'  {it:3d} | ' + ' '.join(f'{int(v) - c0:8d}' if v > 0 else '     -  ' for v in r[:7]))
+        continue
     for cta in (0, 1):
         print(f'CTA {cta}: item | bar2_done mma_full_ok mma_issued | epi_tfull tmem_released bar1_done staged store_issued  (us since first stamp; v1 kernel: see gconv_sm100.cu)')
         for it in range(10, 16):

@@ -126,7 +126,7 @@ def run_reference(args, arch, rank):
 def workload_config(args, arch, world):
     return {'workload': f'train step (fwd+CTC+bwd+reg+clip+Adam), arch {arch}, batch {args.batch}x{args.frames} frames x80 log-mel per GPU',
             'arch_vec': arch, 'per_gpu_batch': args.batch, 'global_batch': args.batch * world, 'frames': args.frames,
-            'parallelism': f'dp{world} (utterance-sharded, NCCL all-reduce of the flat fp32 gradient)' if world > 1 else 'single GPU',
+            'parallelism': f'dp{world} (utterance-sharded; the flat fp32 gradient is all-reduced by NCCL in 5 buckets overlapped with the backward pass)' if world > 1 else 'single GPU',
             'l2': 'per-step working set (activations + weights) is > 2 GB, far above the 126 MB L2; no flush needed',
             'dropout': args.dropout}
 

@@ -30,6 +30,25 @@ def allreduce_mean_(flat):
     return flat
 
 
+class _Done:
+    def wait(self):
+        return True
+
+
+def allreduce_mean_async(flat):
+    """Start the in-place mean over ranks of one gradient bucket and return a handle whose ``wait()`` orders the CURRENT
+    stream after the collective (NCCL: the reduce runs on the process group's own stream, behind the work already queued on
+    the current stream, so it overlaps whatever is launched next).  gloo has no AVG: sum, then scale."""
+    _, n = world()
+    if n == 1:
+        return _Done()
+    if dist.get_backend() == 'nccl':
+        return dist.all_reduce(flat, op=dist.ReduceOp.AVG, async_op=True)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.mul_(1.0 / n)
+    return _Done()
+
+
 def arch_cost(arch_vec, frames=500):
     """Forward FLOPs per utterance: used to balance the sweep (linear edges are ~6x a conv edge)."""
     T = [frames, frames, (frames + 1) // 2, ((frames + 1) // 2 + 1) // 2]

@@ -562,6 +562,13 @@ class Engine:
             call(bwd, lib.nbasr_eltwise, F32, dhp.data_ptr(), C3, B, Tq, Tp3, C3, C.byref(epi))
             pl.keep.append(epi)
 
+        # Gradient buckets for the data-parallel exchange: (number of backward calls after which the flat-gradient range
+        # [lo, hi) is final).  Parameters are laid out in module order (block 0 .. block 3, LSTM, classifier) and the backward
+        # pass finishes them from the back, so each bucket is one contiguous range: head + LSTM first, then blocks 3..0.
+        blk_lo = [self.slices[self.block_conv[i] + '.weight'][0] for i in range(4)]
+        tail_lo = min(off for n_, (off, _) in self.slices.items() if off > blk_lo[3] and not n_.startswith(tuple(
+            [self.block_conv[3] + '.', self.block_ln[3] + '.'] + [c + '.' for c in self.block_cells[3]])))
+        pl.buckets = [(len(bwd), tail_lo, self.n_flat)]
         for i in (3, 2, 1, 0):
             rec = block_records[i]
             geo = rec['geo']
@@ -648,6 +655,7 @@ class Engine:
                   self.G(cname + '.weight'), rec['K'], dbias=self.G(cname + '.bias') if fuse else None)
             if not fuse:
                 call(bwd, lib.nbasr_colsum, dt, dzc.data_ptr(), B, Ti, Tp, Cc, self.G(cname + '.bias'))
+            pl.buckets.append((len(bwd), blk_lo[i], blk_lo[i + 1] if i < 3 else tail_lo))
             if i > 0:
                 gout = pools[i - 1].pop()
                 Cin, Tin = pgeo.C, pgeo.T

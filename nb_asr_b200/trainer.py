@@ -14,6 +14,8 @@ import pathlib
 import collections.abc as cabc
 
 import numpy as np
+import os
+
 import torch
 
 from . import _lib
@@ -289,14 +291,14 @@ class Trainer:
             ent['alen'].copy_(audio_len); ent['tg'].copy_(targets); ent['tl'].copy_(targets_len)
             pl.audio.copy_(audio)
 
-            def body_main():
+            def body_main(bwd_upto=None):
                 if model.training and eng.training_drop > 0:
                     eng.drop_step.add_(1)
                 eng._run(pl.fwd)
                 self._ctc(eng, pl, ent['tg'], ent['alen'], ent['tl'], training, ws)
                 if training:
                     eng.flat_g.zero_()
-                    eng._run(pl.bwd)
+                    eng._run(pl.bwd if bwd_upto is None else pl.bwd[:bwd_upto])
                     if not multi:
                         eng._optimizer_launch()
 
@@ -326,6 +328,23 @@ class Trainer:
                         eng._optimizer_launch()
                     ent['g2'] = g2
                     ent['n2'] = eng.launches - n0
+                    if os.environ.get('NBASR_DP_BUCKETS', '1') != '0' and len(pl.buckets) > 1:
+                        # bucketed exchange: the backward pass is cut where a contiguous range of the flat gradient becomes
+                        # final (head + LSTM, then blocks 3..0); each range is all-reduced on NCCL's stream while the next
+                        # segment of the backward pass runs ("launched bucket-wise during backward").
+                        marks = [m for m, _, _ in pl.buckets]
+                        segs = []
+                        for k in range(1, len(marks)):
+                            gk = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(gk):
+                                eng._run(pl.bwd[marks[k - 1]:marks[k]])
+                            segs.append(gk)
+                        eng.launches = n0 + ent['n2']          # the segments re-capture calls g1 already counted
+                        g0 = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g0):
+                            body_main(bwd_upto=marks[0])
+                        eng.launches = n0 + ent['n2']
+                        ent['g0'], ent['segs'] = g0, segs
             except Exception as e:  # noqa: BLE001
                 torch.cuda.synchronize()
                 raise _GraphCaptureError(str(e)) from e
@@ -334,6 +353,19 @@ class Trainer:
         ent['tg'].copy_(targets, non_blocking=True)
         ent['tl'].copy_(targets_len, non_blocking=True)
         pl.audio.copy_(audio, non_blocking=True)
+        if training and multi and 'segs' in ent:
+            from .distributed import allreduce_mean_async
+            works = []
+            for k, g in enumerate([ent['g0']] + ent['segs']):
+                g.replay()
+                _, lo, hi = pl.buckets[k]
+                works.append(allreduce_mean_async(eng.flat_g[lo:hi]))
+            for w in works:
+                w.wait()                                   # stream-side wait: the optimiser graph follows the last bucket
+            eng.launches += ent['n1']
+            ent['g2'].replay()
+            eng.launches += ent['n2']
+            return ws.loss[0].clone(), pl.logp.clone(), audio_len // 4
         ent['g1'].replay()
         eng.launches += ent['n1']
         if training and multi:

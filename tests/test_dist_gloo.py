@@ -17,6 +17,12 @@ def _worker(rank, world, port, q):
         g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
         D.allreduce_mean_(g)
         ok_grad = torch.allclose(g, torch.arange(1000, dtype=torch.float32) * (1 + world) / 2)
+        # bucketed exchange (trainer._step_graph): disjoint ranges of one flat buffer, each reduced on its own, waited at the end
+        g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        works = [D.allreduce_mean_async(g[lo:hi]) for lo, hi in ((640, 1000), (192, 640), (0, 192))]
+        for w in works:
+            w.wait()
+        ok_grad = ok_grad and torch.allclose(g, torch.arange(1000, dtype=torch.float32) * (1 + world) / 2)
         # sweep sharding: a partition of the arch list, identical on every rank, balanced by the FLOP model
         archs = list(ss.get_all_architectures())[:97]
         mine = D.shard_archs(archs, rank, world, balance='lpt')

@@ -241,3 +241,44 @@ def test_long_mixed_length_utterances_fp32():
     loss, logp, out_len = tr.step(((audio, alen), (tg, tl)), training=True)
     assert abs(loss.item() - loss_ref.item()) < 1e-4 * abs(loss_ref.item())
     check_grads(model, raw, total)
+
+
+@pytest.mark.parametrize('arch', [[[1, 0], [1, 0, 0], [1, 0, 0, 0]], [[4, 1], [0, 1, 1], [2, 0, 1, 1]]])
+def test_gradient_buckets_partition_the_backward_pass(arch):
+    """Data-parallel exchange: the backward plan is cut into segments after which a contiguous range of the flat
+    gradient is final.  The ranges must tile the buffer, and a range must not change once its segment has run."""
+    model = build(arch, 'bf16').train()
+    eng = model.engine
+    (audio, alen), (tg, tl) = nb.data.make_batch(4, 200, seed=3, min_len=120)
+    tr = trainer(model)
+    pl = eng.forward(audio.to(DEV), training=True)
+    from nb_asr_b200.trainer import _ws
+    ws = _ws.get(torch.device(DEV), 4, pl.Tq, pl.V, tg.shape[1])
+    tr._ctc(eng, pl, tg.to(DEV).int().contiguous(), alen.to(DEV), tl.to(DEV), True, ws)
+    marks = [m for m, _, _ in pl.buckets]
+    assert marks == sorted(marks) and marks[-1] == len(pl.bwd) and len(marks) == 5
+    spans = sorted((lo, hi) for _, lo, hi in pl.buckets)
+    assert spans[0][0] == 0 and spans[-1][1] == eng.n_flat
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    eng.backward(pl)
+    torch.cuda.synchronize()
+    full = eng.flat_g.clone()
+    assert float(full.abs().sum()) > 0
+    # segment by segment: after segment k, bucket k already holds its final value
+    eng.flat_g.zero_()
+    prev = 0
+    for m, lo, hi in pl.buckets:
+        eng._run(pl.bwd[prev:m])
+        prev = m
+        torch.cuda.synchronize()
+        got, ref = eng.flat_g[lo:hi], full[lo:hi]
+        # fp32 atomics make the weight-gradient sums run-to-run different in the last bits
+        assert float((got - ref).norm()) <= 1e-4 * float(ref.norm()) + 1e-12, (m, lo, hi)
+
+
+def test_async_bucket_allreduce_single_process_is_a_noop():
+    from nb_asr_b200.distributed import allreduce_mean_async
+    t = torch.arange(8, dtype=torch.float32, device=DEV)
+    w = allreduce_mean_async(t)
+    w.wait()
+    assert torch.equal(t.cpu(), torch.arange(8, dtype=torch.float32))

@@ -516,6 +516,9 @@ int nbasr_layernorm_fwd(int dtype, const void* x, void* y, int B, int T, int Tp,
   int64_t rows = (int64_t)B * T;
   int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 8);
   if (blocks < 1) return 0;
+  static const bool ln_v1 = getenv("NBASR_LN_V1") != nullptr;
+  if (dtype == NBASR_BF16 && !ln_v1 && rows * (int64_t)C < (int64_t)1 << 40 && (int64_t)B * Tp < (int64_t)1 << 30)
+    return ln2_fwd(x, y, B, T, Tp, C, gamma, beta, eps, mean, rstd, as_stream(stream));   // packed-fp32x2 kernels (layernorm2.cu)
   if (dtype == NBASR_BF16 && !getenv("NBASR_LN_FWD_V1")) {
     const int QN = (C / 8 + 31) / 32;
     const int grid = (int)std::min<int64_t>((rows + 15) / 16, nbasr_sm_count());
@@ -554,6 +557,9 @@ int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* m
     cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr = true;
   }
+  static const bool ln_v1 = getenv("NBASR_LN_V1") != nullptr;
+  if (dtype == NBASR_BF16 && !ln_v1 && (int64_t)B * Tp < (int64_t)1 << 30 && mask_rows * 8 * ((C + 31) / 32 + 1) < (int64_t)1 << 31)
+    return ln2_bwd(dy, x, mean, rstd, gamma, B, T, Tp, C, dx, dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta, as_stream(stream));
   if (dtype == NBASR_BF16 && !getenv("NBASR_LN_BWD_V1")) {
     const int QN = (C / 8 + 31) / 32;
     const int grid = (int)std::min<int64_t>((rows + 15) / 16, nbasr_sm_count());

@@ -34,33 +34,66 @@ __device__ __forceinline__ bool seg_locate(const int64_t* __restrict__ len, int 
   return false;
 }
 
+// (the segment bases are 16-byte aligned in the engine's flat buffer; the scalar loops handle any other caller and the tails)
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 __global__ void seg_sumsq_kernel(const float* __restrict__ p, const int64_t* __restrict__ off, const int64_t* __restrict__ len,
                                  int nseg, float* __restrict__ state) {
   int s; int64_t start;
   if (!seg_locate(len, nseg, blockIdx.x, s, start)) return;
-  const float* x = p + off[s];
-  int64_t end = min(len[s], start + SEG_CHUNK);
+  const float* x = p + off[s] + start;
+  const int n = (int)(min(len[s], start + SEG_CHUNK) - start);
   float acc = 0.f;
-  for (int64_t i = start + threadIdx.x; i < end; i += blockDim.x) acc += x[i] * x[i];
+  int i0 = 0;
+  if (al16(x)) {
+    const int n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    i0 = n4 << 2;
+  }
+  for (int i = i0 + threadIdx.x; i < n; i += blockDim.x) acc += x[i] * x[i];
   acc = block_sum(acc);
   if (threadIdx.x == 0 && acc != 0.f) atomicAdd(state + 4 + s, acc);
 }
 
+// g += k W for one chunk of a regularised segment
 __global__ void reg_grad_kernel(const float* __restrict__ p, float* __restrict__ g, const int64_t* __restrict__ off,
                                 const int64_t* __restrict__ len, int nseg, const float* __restrict__ state, float reg_coef) {
   int s; int64_t start;
   if (!seg_locate(len, nseg, blockIdx.x, s, start)) return;
-  float nrm = sqrtf(state[4 + s]);
-  float k = nrm > 0.f ? reg_coef / nrm : 0.f;
-  const float* x = p + off[s];
-  float* gg = g + off[s];
-  int64_t end = min(len[s], start + SEG_CHUNK);
-  for (int64_t i = start + threadIdx.x; i < end; i += blockDim.x) gg[i] += k * x[i];
+  const float nrm = sqrtf(state[4 + s]);
+  const float k = nrm > 0.f ? reg_coef / nrm : 0.f;
+  const float* x = p + off[s] + start;
+  float* gg = g + off[s] + start;
+  const int n = (int)(min(len[s], start + SEG_CHUNK) - start);
+  int i0 = 0;
+  if (al16(x) && al16(gg)) {
+    const int n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      float4 w = reinterpret_cast<float4*>(gg)[i];
+      w.x += k * v.x; w.y += k * v.y; w.z += k * v.z; w.w += k * v.w;
+      reinterpret_cast<float4*>(gg)[i] = w;
+    }
+    i0 = n4 << 2;
+  }
+  for (int i = i0 + threadIdx.x; i < n; i += blockDim.x) gg[i] += k * x[i];
 }
 
 __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
   float acc = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += g[i] * g[i];
+  int64_t i0 = 0;
+  if (al16(g)) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 v = reinterpret_cast<const float4*>(g)[i];
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    i0 = n4 << 2;
+  }
+  for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += g[i] * g[i];
   acc = block_sum(acc);
   if (threadIdx.x == 0) atomicAdd(out, acc);
 }

@@ -540,14 +540,17 @@ class Engine:
                  head['gates'].data_ptr(), head['cst'].data_ptr(), Tq, B, HIDDEN, dgx.data_ptr(), head['work'].data_ptr(),
                  self.whh_packed.data_ptr() if self.whh_packed is not None else None,
                  dgx_a.data_ptr() if dt == BF16 else None)
-            # biases: column sums of dgx (B*Tq rows, unpadded) -> both bias vectors
-            for bn in ('.bias_ih_l0', '.bias_hh_l0'):
-                call(bwd, lib.nbasr_colsum, F32, dgx.data_ptr() - PAD_L * H4 * 4, 1, B * Tq, B * Tq, H4, self.G(ln + bn))
+            # biases: column sums of dgx (B*Tq rows, unpadded) -> both bias vectors.  bf16: fused into the two tensor-core
+            # weight-gradient GEMMs below (ones operand, like the conv / linear bias gradients); fp32: column-sum kernel
+            fuse_b = dt == BF16
+            if not fuse_b:
+                for bn in ('.bias_ih_l0', '.bias_hh_l0'):
+                    call(bwd, lib.nbasr_colsum, F32, dgx.data_ptr() - PAD_L * H4 * 4, 1, B * Tq, B * Tq, H4, self.G(ln + bn))
             # dW_ih += dgx^T X ; dW_hh += dgx^T H_{t-1} (h_seq shifted one row up; row -1 is a zero pad row)
             wgrad(bwd, dgx_a.data_ptr(), Tq * H4, H4, _ptr(head['lin'], PAD_L * C3), Tp3 * C3, C3, B, Tq, H4, C3,
-                  self.G(ln + '.weight_ih_l0'), C3)
+                  self.G(ln + '.weight_ih_l0'), C3, dbias=self.G(ln + '.bias_ih_l0') if fuse_b else None)
             wgrad(bwd, dgx_a.data_ptr(), Tq * H4, H4, _ptr(head['hseq'], (PAD_L - 1) * HP), head['gh'].Tp * HP, HP, B, Tq, H4,
-                  HIDDEN, self.G(ln + '.weight_hh_l0'), HIDDEN)
+                  HIDDEN, self.G(ln + '.weight_hh_l0'), HIDDEN, dbias=self.G(ln + '.bias_hh_l0') if fuse_b else None)
             # dX = dgx W_ih  (through the input dropout mask if any)
             if head['dmask'] is not None:
                 epi = self._epi(C3, out2=gout.data_ptr(), mask2=head['dmask'], scale2=dscale, mask_rows=geo3.rows)

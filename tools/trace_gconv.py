@@ -40,7 +40,7 @@ for name, kw in (('full', dict(bias=bias, relu=1, out=out, mask_out=mask, mask_w
     t = buf.view(8, 64, 8).cpu()
     t0 = int(t[t > 0].min())
     print('=== variant', name)
-    if os.environ.get('NBASR_GCONV_UMMA') is None:
+    if os.environ.get('NBASR_GCONV_FRAG') is not None:
         # fragment kernel (gconv_frag_sm100.cu): clock64 stamps of one SM -> cycles
         for cta in (0, 1):
             print(f'CTA {cta}: item | prod_issue | wait_begin full_ok mma_done epi_done bar_done store_issued  (cycles since the CTA\'s first stamp)')
@@ -54,7 +54,7 @@ for name, kw in (('full', dict(bias=bias, relu=1, out=out, mask_out=mask, mask_w
         continue
     for cta in (0, 1):
         print(f'CTA {cta}: item | bar2_done mma_full_ok mma_issued | epi_tfull tmem_released bar1_done staged store_issued  (us since first stamp; v1 kernel: see gconv_sm100.cu)')
-        for it in range(10, 16):
+        for it in range(8, 16):
             r = t[cta, it]
             if r[1] == 0:
                 break

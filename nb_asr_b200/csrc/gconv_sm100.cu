@@ -62,7 +62,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 struct GcFwdArgs {
   int B, T, C, OUT, ktaps, dstep, off0;
-  int nslabs, ntiles, tiles_per_utt, nlanes, nstage;
+  int nslabs, ntiles, tiles_per_utt, nlanes, nstage, no_prefetch;
   nbasr_epilogue epi;
   int64_t Tp;
   unsigned long long* dbg;   // optional timeline dump (tools/trace_gconv.py): [cta][tile][8] globaltimer ns
@@ -126,15 +126,50 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (lane == 0) {
       mbar_expect_tx(wbar, p.ktaps * WTAP_BYTES);
       for (int j = 0; j < p.ktaps; ++j) tma_load_2d(wsm + j * WTAP_BYTES, &tmW, wbar, 0, (slab * p.ktaps + j) * NW);
-      int stage = 0, it = 0;
-      uint32_t phase = 0;
-      for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes, ++it) {
-        const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * GT;
+    }
+    // The epilogue's per-thread operands (skip-sum tensors, gate bits of the second output) are loaded AFTER the accumulator
+    // is ready, so their latency sits on the epilogue's critical path (1 skip operand: 55 -> 92 us per launch).  The whole
+    // producer warp therefore L2-prefetches them for each tile at the moment that tile's input load is issued, i.e. NS tiles
+    // ahead of their use (the register prefetch tried earlier spilled).
+    const int esz = p.epi.add_dtype == NBASR_BF16 ? 2 : 4;
+    const bool pf_mask = p.epi.out2 && p.epi.mask2;
+    const int pl2 = pf_mask ? c0 / p.epi.mask2_w : 0;
+    const int eb2 = p.epi.mask2_w == 32 ? 4 : 8;
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes, ++it) {
+      const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * GT;
+      if (lane == 0) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_expect_tx(full_bar(stage), A_BYTES);
         tma_load_3d(asm0 + stage * A_BYTES, &tmX, full_bar(stage), c0, NBASR_PAD_L + t0 + p.off0, b);
-        if (++stage == NS) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (!p.no_prefetch) {
+        const int64_t rho0 = (int64_t)b * p.Tp + NBASR_PAD_L + t0;
+        const int nr = min(GT, p.T - t0);
+        const int ncols = min(p.OUT, p.C - c0);
+        for (int a = 0; a < p.epi.n_add; ++a) {
+          const char* base = reinterpret_cast<const char*>(p.epi.add[a]) + (rho0 * p.epi.ld_out + c0) * esz;
+          for (int r = lane; r < nr; r += 32) {
+            const char* q = base + (int64_t)r * p.epi.ld_out * esz;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q + ncols * esz - 1));
+          }
+        }
+        if (pf_mask) {
+          // this slab's 8 column groups may straddle two mask planes when the widths differ: prefetch both row ranges
+          const char* m0 = reinterpret_cast<const char*>(p.epi.mask2) + ((int64_t)pl2 * p.epi.mask_rows + rho0) * eb2;
+          const char* m1 = reinterpret_cast<const char*>(p.epi.mask2) +
+                           ((int64_t)((c0 + ncols - 1) / p.epi.mask2_w) * p.epi.mask_rows + rho0) * eb2;
+          const int nb = nr * eb2;
+          for (int o = lane * 128; o < nb + 127; o += 32 * 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(m0 + min(o, nb - 1)));
+            if (m1 != m0) asm volatile("prefetch.global.L2 [%0];" ::"l"(m1 + min(o, nb - 1)));
+          }
+        }
+      }
+      if (++stage == NS) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -450,6 +485,8 @@ int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st) {
   int slots = 2 * nbasr_sm_count();
   a.nlanes = std::max(1, std::min(a.ntiles, slots / a.nslabs));
   a.epi = g->epi;
+  static const bool no_pf = getenv("NBASR_GCONV_NO_PREFETCH") != nullptr;
+  a.no_prefetch = no_pf ? 1 : 0;
   a.dbg = g_gconv_dbg;
   CUtensorMap tmX, tmW, tmO, tmO2;
   uint64_t dx[3] = {(uint64_t)g->C, (uint64_t)g->Tp, (uint64_t)g->B};

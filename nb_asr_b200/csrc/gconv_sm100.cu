@@ -218,6 +218,15 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const uint32_t aphase = (it / NACC) & 1;
       const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * GT;
       const int t = t0 + row;
+      // gate bits of the second output (input gradient: dZ of the previous node): requested BEFORE waiting for the
+      // accumulator so that their latency overlaps the MMAs instead of sitting between the epilogue's two barriers
+      uint32_t w2[3] = {0xffu, 0xffu, 0xffu};
+      if (epi.out2 && epi.mask2 && t < p.T) {
+        const int64_t rho2 = (int64_t)b * p.Tp + NBASR_PAD_L + t;
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+          if (g * 8 < nvalid) w2[g] = reinterpret_cast<const uint8_t*>(epi.mask2)[mask_byte_addr(rho2, cbeg + g * 8, epi.mask2_w, epi.mask_rows)];
+      }
       mbar_wait(tfull_bar(as), aphase);
       if (etid == 0) GC_STAMP(4);
       tcgen05_fence_after();
@@ -274,8 +283,7 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (g * 8 < nvalid) {
           if (epi.out) store8(reinterpret_cast<bf16*>(orow + g * 16), v + g * 8);
           if (epi.out2) {
-            uint32_t w = 0xffu;
-            if (epi.mask2 && rowok) w = reinterpret_cast<const uint8_t*>(epi.mask2)[mask_byte_addr(rho, cbeg + g * 8, epi.mask2_w, epi.mask_rows)];
+            const uint32_t w = w2[g];
             float t2[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) t2[i] = ((w >> i) & 1u) ? v[g * 8 + i] * epi.scale2 : 0.f;

@@ -146,13 +146,14 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(int h_dtype, const void* 
 // no dot product needs a warp reduction.  The 8 threads of a row group finish log-softmax with three shuffles.
 constexpr int HT_ROWS = 128;
 constexpr int HT_KC = 64;
+constexpr int HT_HP = 68;                    // staged h row pitch in floats (16-byte aligned rows)
 __global__ void __launch_bounds__(256, 1) head_fwd_tiled_kernel(int h_dtype, const void* __restrict__ h, int64_t h_bs, int64_t h_rs,
                                                                 int B, int T, int K, int V, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, float* __restrict__ logits,
                                                                 float* __restrict__ logp) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* ws = sm;                       // V x K
-  float* hs = ws + V * K;               // HT_ROWS x (HT_KC + 1)
+  float* hs = ws + V * K;               // HT_ROWS x HT_HP (V * K is a multiple of 4 on the float4 path)
   __shared__ int64_t rbase[HT_ROWS];    // element offset of each row of the tile (-1: past the end)
   const int tid = threadIdx.x, rg = tid >> 3, c8 = tid & 7, lane = tid & 31, wrp = tid >> 5;
   for (int i = tid; i < V * K; i += blockDim.x) ws[i] = w[i];
@@ -180,38 +181,46 @@ __global__ void __launch_bounds__(256, 1) head_fwd_tiled_kernel(int h_dtype, con
     }
     for (int k0 = 0; k0 < K; k0 += HT_KC) {
       __syncthreads();
-      // warp w stages rows w, w + 8, ...: one coalesced 128-byte (bf16) / 256-byte (fp32) row segment per pass
-      for (int rr = wrp; rr < HT_ROWS; rr += 8) {
-        const int64_t base = rbase[rr];
+      // warp w stages rows w, w + 8, ...: one coalesced 128-byte (bf16) / 256-byte (fp32) row segment per pass.  All 16 row
+      // loads of a warp are issued before the first shared-memory store (one after the other they cost 16 global-memory
+      // latencies per K chunk, 128 per tile: that, not the FMAs, was the time of this kernel)
+      {
+        float sv0[HT_ROWS / 8], sv1[HT_ROWS / 8];
         const int k = k0 + 2 * lane;
-        float v0 = 0.f, v1 = 0.f;
-        if (base >= 0) {
-          if (h_dtype == NBASR_BF16) {
-            // the dispatcher guarantees even strides and a 4-byte aligned base, so (base + k) is a bf16x2 boundary
-            if (k + 1 < K) {
-              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const bf16*>(h) + base + k));
-              v0 = f.x; v1 = f.y;
-            } else if (k < K) {
-              v0 = __bfloat162float(reinterpret_cast<const bf16*>(h)[base + k]);
+#pragma unroll
+        for (int i = 0; i < HT_ROWS / 8; ++i) {
+          const int64_t base = rbase[wrp + 8 * i];
+          float v0 = 0.f, v1 = 0.f;
+          if (base >= 0) {
+            if (h_dtype == NBASR_BF16) {
+              // the dispatcher guarantees even strides and a 4-byte aligned base, so (base + k) is a bf16x2 boundary
+              if (k + 1 < K) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const bf16*>(h) + base + k));
+                v0 = f.x; v1 = f.y;
+              } else if (k < K) {
+                v0 = __bfloat162float(reinterpret_cast<const bf16*>(h)[base + k]);
+              }
+            } else {
+              if (k < K) v0 = reinterpret_cast<const float*>(h)[base + k];
+              if (k + 1 < K) v1 = reinterpret_cast<const float*>(h)[base + k + 1];
             }
-          } else {
-            if (k < K) v0 = reinterpret_cast<const float*>(h)[base + k];
-            if (k + 1 < K) v1 = reinterpret_cast<const float*>(h)[base + k + 1];
           }
+          sv0[i] = v0; sv1[i] = v1;
         }
-        hs[rr * (HT_KC + 1) + 2 * lane] = v0;
-        hs[rr * (HT_KC + 1) + 2 * lane + 1] = v1;
+#pragma unroll
+        for (int i = 0; i < HT_ROWS / 8; ++i)
+          *reinterpret_cast<float2*>(hs + (wrp + 8 * i) * HT_HP + 2 * lane) = make_float2(sv0[i], sv1[i]);
       }
       __syncthreads();
       const int kn = min(HT_KC, K - k0);
-      const float* hp = hs + (4 * rg) * (HT_KC + 1);
+      const float* hp = hs + (4 * rg) * HT_HP;
       const float* wp[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) wp[i] = ws + vcls[i] * K + k0;
       auto step = [&](int kk) {
         float hv[4], wv[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) hv[j] = hp[j * (HT_KC + 1) + kk];
+        for (int j = 0; j < 4; ++j) hv[j] = hp[j * HT_HP + kk];
 #pragma unroll
         for (int i = 0; i < 8; ++i) wv[i] = wp[i][kk];
 #pragma unroll
@@ -219,7 +228,30 @@ __global__ void __launch_bounds__(256, 1) head_fwd_tiled_kernel(int h_dtype, con
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(hv[j], wv[i], acc[j][i]);
       };
-      if (kn == HT_KC) {
+      // four k at a time with 128-bit shared loads (W rows and staged h rows are 16-byte aligned when K % 4 == 0): the
+      // scalar version issued 12 shared-memory wavefronts per 32 FMAs and was LSU-bound
+      auto step4 = [&](int kk) {
+        float4 hv[4], wv[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hv[j] = *reinterpret_cast<const float4*>(hp + j * HT_HP + kk);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wv[i] = *reinterpret_cast<const float4*>(wp[i] + kk);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[j][i] = fmaf(hv[j].x, wv[i].x, acc[j][i]);
+            acc[j][i] = fmaf(hv[j].y, wv[i].y, acc[j][i]);
+            acc[j][i] = fmaf(hv[j].z, wv[i].z, acc[j][i]);
+            acc[j][i] = fmaf(hv[j].w, wv[i].w, acc[j][i]);
+          }
+      };
+      if ((K & 3) == 0) {
+        const int k4 = kn & ~3;
+#pragma unroll 4
+        for (int kk = 0; kk < k4; kk += 4) step4(kk);
+        for (int kk = k4; kk < kn; ++kk) step(kk);
+      } else if (kn == HT_KC) {
 #pragma unroll 8
         for (int kk = 0; kk < HT_KC; ++kk) step(kk);
       } else {
@@ -689,7 +721,7 @@ int nbasr_head_fwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B
   NBASR_REQUIRE(V <= 64 && K <= 32 * HEAD_MAXK32, "head shape");
   int64_t rows = (int64_t)B * T;
   if (rows == 0) return 0;
-  const size_t smt = sizeof(float) * ((size_t)V * K + HT_ROWS * (HT_KC + 1));
+  const size_t smt = sizeof(float) * ((size_t)V * K + HT_ROWS * HT_HP);
   const bool aligned = h_dtype != NBASR_BF16 || (((h_bs | h_rs) & 1) == 0 && ((uintptr_t)h & 3) == 0);
   if (smt <= 200 * 1024 && rows >= 4 * HT_ROWS && aligned && !getenv("NBASR_HEAD_V1")) {
     static bool attr = false;

@@ -364,9 +364,16 @@ __global__ void ctc_kernel(const float* __restrict__ logp, int B, int T, int V, 
   int Sb = (int)targets_len[b];
   if (Sb > S) Sb = S;
   const int L = 2 * Sb + 1;
-  float* prev = sm;            // Lmax
-  float* cur = sm + Lmax;      // Lmax
-  int* ext = reinterpret_cast<int*>(sm + 2 * Lmax);
+  // The alpha and beta recursions are independent chains of Tb - 1 latency-bound steps (shared-memory neighbours, two
+  // logadds, one emission, a barrier): the first half of the CTA walks alpha forward while the second half walks beta
+  // backward, sharing the per-step barrier; the emission of the NEXT step is requested before this step's arithmetic.
+  const int half = blockDim.x >> 1;
+  const bool do_beta = dlogits != nullptr;
+  const bool is_b = threadIdx.x >= half;
+  const int tid = threadIdx.x - (is_b ? half : 0);
+  float* prev = sm + (is_b ? 2 * Lmax : 0);      // [alpha prev | alpha cur | beta prev | beta cur]
+  float* cur = prev + Lmax;
+  int* ext = reinterpret_cast<int*>(sm + 4 * Lmax);
   float* alpha = work + (int64_t)b * T * Lmax;
   float* beta = work + (int64_t)B * T * Lmax + (int64_t)b * T * Lmax;
   const float* lp = logp + (int64_t)b * T * V;
@@ -374,30 +381,81 @@ __global__ void ctc_kernel(const float* __restrict__ logp, int B, int T, int V, 
   for (int s = threadIdx.x; s < Lmax; s += blockDim.x) ext[s] = (s < L && (s & 1)) ? targets[(int64_t)b * S + (s >> 1)] : 0;
   __syncthreads();
   __shared__ float s_nll;
-  // ---- alpha
-  for (int s = threadIdx.x; s < L; s += blockDim.x) {
-    float a = NEG;
-    if (Tb > 0) {
-      if (s == 0) a = lp[0];
-      else if (s == 1) a = lp[ext[1]];
+  if (!is_b) {
+    for (int s = tid; s < L; s += half) {
+      float a = NEG;
+      if (Tb > 0) {
+        if (s == 0) a = lp[0];
+        else if (s == 1) a = lp[ext[1]];
+      }
+      prev[s] = a;
+      if (Tb > 0) alpha[s] = a;
     }
-    prev[s] = a;
-    if (Tb > 0) alpha[s] = a;
+  } else if (do_beta && Tb > 0) {
+    for (int s = tid; s < L; s += half) {
+      float bv = NEG;
+      if (s == L - 1) bv = lp[(int64_t)(Tb - 1) * V];
+      else if (s == L - 2) bv = lp[(int64_t)(Tb - 1) * V + ext[L - 2]];
+      prev[s] = bv;
+      beta[(int64_t)(Tb - 1) * Lmax + s] = bv;
+    }
   }
   __syncthreads();
-  for (int t = 1; t < Tb; ++t) {
-    for (int s = threadIdx.x; s < L; s += blockDim.x) {
-      float a = prev[s];
-      if (s >= 1) a = logadd(a, prev[s - 1]);
-      if (s >= 2 && ext[s] != 0 && ext[s] != ext[s - 2]) a = logadd(a, prev[s - 2]);
-      if (a != NEG) a += lp[(int64_t)t * V + ext[s]];
-      cur[s] = a;
-      alpha[(int64_t)t * Lmax + s] = a;
+  if (L <= half) {
+    // common case: one state per thread, emission software-pipelined
+    const int s = tid;
+    const bool on = s < L && (!is_b || do_beta);
+    const int es = on ? ext[s] : 0;
+    const bool skip_ok = on && (is_b ? (s + 2 < L && ext[s + 2] != 0 && ext[s + 2] != es) : (s >= 2 && es != 0 && es != ext[s - 2]));
+    float e_next = 0.f;
+    if (on && Tb > 1) e_next = lp[(int64_t)(is_b ? Tb - 2 : 1) * V + es];
+    for (int k = 1; k < Tb; ++k) {
+      const int t = is_b ? Tb - 1 - k : k;
+      const float e = e_next;
+      if (on && k + 1 < Tb) e_next = lp[(int64_t)(is_b ? t - 1 : t + 1) * V + es];
+      if (on) {
+        float a = prev[s];
+        if (!is_b) {
+          if (s >= 1) a = logadd(a, prev[s - 1]);
+          if (skip_ok) a = logadd(a, prev[s - 2]);
+        } else {
+          if (s + 1 < L) a = logadd(a, prev[s + 1]);
+          if (skip_ok) a = logadd(a, prev[s + 2]);
+        }
+        if (a != NEG) a += e;
+        cur[s] = a;
+        (is_b ? beta : alpha)[(int64_t)t * Lmax + s] = a;
+      }
+      __syncthreads();
+      float* tmp = prev; prev = cur; cur = tmp;
     }
-    __syncthreads();
-    float* tmp = prev; prev = cur; cur = tmp;
+  } else {
+    for (int k = 1; k < Tb; ++k) {
+      const int t = is_b ? Tb - 1 - k : k;
+      if (!is_b) {
+        for (int s = tid; s < L; s += half) {
+          float a = prev[s];
+          if (s >= 1) a = logadd(a, prev[s - 1]);
+          if (s >= 2 && ext[s] != 0 && ext[s] != ext[s - 2]) a = logadd(a, prev[s - 2]);
+          if (a != NEG) a += lp[(int64_t)t * V + ext[s]];
+          cur[s] = a;
+          alpha[(int64_t)t * Lmax + s] = a;
+        }
+      } else if (do_beta) {
+        for (int s = tid; s < L; s += half) {
+          float bv = prev[s];
+          if (s + 1 < L) bv = logadd(bv, prev[s + 1]);
+          if (s + 2 < L && ext[s + 2] != 0 && ext[s + 2] != ext[s]) bv = logadd(bv, prev[s + 2]);
+          if (bv != NEG) bv += lp[(int64_t)t * V + ext[s]];
+          cur[s] = bv;
+          beta[(int64_t)t * Lmax + s] = bv;
+        }
+      }
+      __syncthreads();
+      float* tmp = prev; prev = cur; cur = tmp;
+    }
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {          // an alpha thread: its `prev` is the last alpha row
     float ll = NEG;
     if (Tb > 0) {
       ll = prev[L - 1];
@@ -418,28 +476,6 @@ __global__ void ctc_kernel(const float* __restrict__ logp, int B, int T, int V, 
     for (int i = threadIdx.x; i < T * V; i += blockDim.x) dl[i] = 0.f;
     return;
   }
-  // ---- beta
-  for (int s = threadIdx.x; s < L; s += blockDim.x) {
-    float bv = NEG;
-    if (s == L - 1) bv = lp[(int64_t)(Tb - 1) * V];
-    else if (s == L - 2) bv = lp[(int64_t)(Tb - 1) * V + ext[L - 2]];
-    prev[s] = bv;
-    beta[(int64_t)(Tb - 1) * Lmax + s] = bv;
-  }
-  __syncthreads();
-  for (int t = Tb - 2; t >= 0; --t) {
-    for (int s = threadIdx.x; s < L; s += blockDim.x) {
-      float bv = prev[s];
-      if (s + 1 < L) bv = logadd(bv, prev[s + 1]);
-      if (s + 2 < L && ext[s + 2] != 0 && ext[s + 2] != ext[s]) bv = logadd(bv, prev[s + 2]);
-      if (bv != NEG) bv += lp[(int64_t)t * V + ext[s]];
-      cur[s] = bv;
-      beta[(int64_t)t * Lmax + s] = bv;
-    }
-    __syncthreads();
-    float* tmp = prev; prev = cur; cur = tmp;
-  }
-  __syncthreads();
   // ---- gradient wrt logits (log-softmax backward folded in); thread per frame
   const float scale = 1.f / ((float)Tb * (float)B);
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -786,8 +822,9 @@ int nbasr_ctc(const float* logp, int B, int T, int V, const int32_t* targets, in
   cudaStream_t st = as_stream(stream);
   if (loss) cudaMemsetAsync(loss, 0, sizeof(float), st);
   int Lmax = 2 * S + 1;
-  int threads = std::min(1024, std::max(64, ((Lmax + 31) / 32) * 32));
-  size_t sm = sizeof(float) * 3 * Lmax;
+  // two halves: alpha threads | beta threads (one state per thread when 2S+1 <= 512)
+  int threads = 2 * std::min(512, std::max(32, ((Lmax + 31) / 32) * 32));
+  size_t sm = sizeof(float) * 5 * Lmax;
   ctc_kernel<<<B, threads, sm, st>>>(logp, B, T, V, targets, S, audio_len, len_div, targets_len, nll, loss, dlogits, work);
   NBASR_CHECK_LAUNCH();
   return 0;

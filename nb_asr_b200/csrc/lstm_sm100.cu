@@ -63,6 +63,30 @@ struct LstmCArgs {
   float* cstate;       // (B, T, H)
 };
 
+// A operand from tensor memory: D[tmem] (+)= A[tmem] * B[smem].  Lane r of the A region holds row r, K packed two bf16 per
+// 32-bit column (16 K elements = 8 columns), i.e. exactly what the row's owner thread writes with tcgen05.st.32x32b.x8.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+constexpr int LC_A_COL = 32;             // first TMEM column of the resident W slice (TS variant): 256 columns
+
+// TS = true: the W slice is copied ONCE from shared memory into tensor memory and every step's 32 MMAs read their A
+// operand from there.  With both operands in shared memory an MMA costs >= 88 cycles whatever its N (the 128 x 16 A tile
+// is streamed through the ~46 B/clk operand port: 2 816 cycles = 1.43 us of the ~3.7 us step); from tensor memory the
+// N = 16 MMA is bounded by its tiny B operand only.
+template <bool TS>
 __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LstmCArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -75,6 +99,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const _
   const uint32_t bar0 = stg + 2 * LC_SLICE + 128 * LC_PRE_LD * 4;
   const uint32_t wbar = bar0, mma_bar = bar0 + 8;
   auto hfull = [&](int b) { return bar0 + 16 + 8u * b; };
+  const uint32_t aready = bar0 + 32;           // TS: the W slice is resident in tensor memory
   uint32_t* tptr = reinterpret_cast<uint32_t*>(al + LC_W_BYTES + 2 * LC_H_BYTES + 2 * LC_SLICE + 128 * LC_PRE_LD * 4 + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t j = cluster_ctarank();
@@ -90,9 +115,10 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const _
     mbar_init(mma_bar, 1);
     mbar_init(hfull(0), 1);
     mbar_init(hfull(1), 1);
+    mbar_init(aready, 128);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(tptr), 32);
+  if (warp == 0) tmem_alloc(smem_u32(tptr), TS ? 512 : 32);
   fence_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -105,7 +131,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const _
       mbar_expect_tx(wbar, LC_W_BYTES);
       for (int kb = 0; kb < 8; ++kb) tma_load_2d(wsm + kb * 16384, &tmW, wbar, kb * 64, (int)j * 128);
       const uint32_t idesc = make_idesc(128, LC_BG, 0, 0);
-      mbar_wait(wbar, 0);
+      mbar_wait(TS ? aready : wbar, 0);
       for (int t = 0; t < p.T; ++t) {
         const int pb = t & 1;
         if (t + 1 < p.T) mbar_expect_tx(hfull(pb ^ 1), LC_H_BYTES);        // arm the buffer that receives h_t
@@ -114,10 +140,14 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const _
         const uint32_t hb = hsm + pb * LC_H_BYTES;
 #pragma unroll 4
         for (int k = 0; k < LC_KP / 16; ++k) {
-          uint64_t ad = make_smem_desc(wsm + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
           // un-swizzled K-major operand: LBO = stride between K-adjacent core matrices (256 B), SBO = row groups (128 B)
           uint64_t bd = make_smem_desc(hb + k * 512, 256, 128) & ~((uint64_t)7 << 61);
-          umma_bf16(tm, ad, bd, idesc, k != 0);
+          if (TS) {
+            umma_bf16_ts(tm, tm + LC_A_COL + 8 * k, bd, idesc, k != 0);
+          } else {
+            uint64_t ad = make_smem_desc(wsm + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+            umma_bf16(tm, ad, bd, idesc, k != 0);
+          }
         }
         umma_commit(mma_bar);
       }
@@ -135,6 +165,25 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const _
       const int b = b0 + bq * 4 + i;
 #pragma unroll
       for (int g = 0; g < 4; ++g) gxr[i][g] = (unit_ok && b < p.B && p.T > 0) ? __ldg(p.gx + ((int64_t)b * p.T) * H4 + g * H + u) : 0.f;
+    }
+    if (TS) {
+      // row r = q*32 + lane of the W slice: shared memory (128B-swizzled K-major, 8 K blocks of 64) -> registers -> the
+      // thread's own TMEM lane, 16 K elements (8 columns) at a time
+      mbar_wait(wbar, 0);
+      const int r = q * 32 + lane;
+      const uint8_t* wrow = al + r * 128;
+#pragma unroll 4
+      for (int k = 0; k < LC_KP / 16; ++k) {
+        const uint8_t* kb = wrow + (k >> 2) * 16384;
+        const int c0 = (k & 3) * 2;
+        const uint4 lo = *reinterpret_cast<const uint4*>(kb + (((c0) ^ (r & 7)) << 4));
+        const uint4 hi = *reinterpret_cast<const uint4*>(kb + (((c0 + 1) ^ (r & 7)) << 4));
+        const uint32_t regs[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tmem_st8(tm + ((uint32_t)(q * 32) << 16) + LC_A_COL + 8 * k, regs);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_arrive(aready);
     }
     for (int t = 0; t < p.T; ++t) {
       mbar_wait(mma_bar, t & 1);
@@ -189,7 +238,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const _
   cluster_sync_all();                     // nobody leaves while a peer may still write into its shared memory
   if (warp == 0) {
     tcgen05_fence_after();
-    tmem_dealloc(tm, 32);
+    tmem_dealloc(tm, TS ? 512 : 32);
   }
 }
 
@@ -392,10 +441,13 @@ int sm100_lstm_fwd(const float* gx, const void* w_packed, int T, int B, int H, v
   int64_t sw[2] = {1, LC_KP};
   uint32_t bw[2] = {64, 128};
   if (sm100_get_map(w_packed, 2, dw, sw, bw, &tmW)) return 1;
+  static const bool ts = getenv("NBASR_LSTM_SS") == nullptr;      // default: W slice resident in tensor memory
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_cluster_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaFuncSetAttribute(lstm_cluster_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_cluster_fwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_cluster_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_cluster_fwd_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return nbasr_fail("lstm_cluster attr: %s", cudaGetErrorString(e));
     attr = true;
   }
@@ -412,7 +464,8 @@ int sm100_lstm_fwd(const float* gx, const void* w_packed, int T, int B, int H, v
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_cluster_fwd_kernel, tmW, a);
+  cudaError_t e = ts ? cudaLaunchKernelEx(&cfg, lstm_cluster_fwd_kernel<true>, tmW, a)
+                     : cudaLaunchKernelEx(&cfg, lstm_cluster_fwd_kernel<false>, tmW, a);
   if (e != cudaSuccess) return nbasr_fail("lstm_cluster_fwd launch: %s", cudaGetErrorString(e));
   return 0;
 }

@@ -1,7 +1,8 @@
 // Grouped conv edges (ops.py:73-76, groups=100, cpg = C/100 in {6,8,10,12}): forward and input-gradient on the
 // warp-level tensor path (mma.sync m16n8k16 / m16n8k8, bf16 x bf16 -> fp32) fed by ldmatrix from a TMA-loaded tile.
 //
-// Why not tcgen05 here (gconv_sm100.cu, kept as NBASR_GCONV_UMMA=1): a grouped conv is HBM-bound (15-42 FLOP/B), but a
+// EXPERIMENT (NBASR_GCONV_FRAG=1 / nbasr_dbg_gconv_impl(1)); the product path is the tcgen05 kernel in gconv_sm100.cu -- measured
+// result at the end of this comment.  Why try it: a grouped conv is HBM-bound (15-42 FLOP/B), but a
 // tcgen05.mma with both operands in shared memory costs >= 88 cycles per instruction whatever its N (tools/dbg_bench.py),
 // and the block-diagonal formulation needs 3*k of them per 128 x 48 tile = 1 320 cycles against ~1 100 cycles of HBM
 // time: that kernel runs at its MMA issue floor.  The warp-level MMA has no such floor (measured 2.15 cycles per
@@ -22,6 +23,10 @@
 //     the accumulator fragments in registers; results are staged as a dense bf16 tile (double-buffered) and leave by TMA
 //     store, gate bits as one coalesced 8-byte entry per row.  Same mask-plane format / slab width as the tcgen05
 //     kernel: drop-in.
+//
+// Measured on B200 (profiles/r1_gconv_frag_experiment.txt): correct on all 16 shapes, but ~6 600 issued warp instructions per
+// 128 x 48 tile against 4 400 issue slots at HBM speed -- the fragment-layout epilogue (~9 instructions per output element) and
+// the ldmatrix/MMA stream share the same warps -- so it is 1.35-1.8x SLOWER than the tcgen05 kernel and stays an experiment.
 #include <cuda.h>
 
 #include "common.cuh"

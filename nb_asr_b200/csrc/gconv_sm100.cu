@@ -28,6 +28,8 @@
 
 using namespace sm100;
 
+extern int g_gconv_slots;
+
 namespace {
 
 constexpr int GT = 128;                    // frames per tile
@@ -476,6 +478,8 @@ __global__ void pack_gconv_mma_kernel(const float* __restrict__ w, bf16* __restr
 }  // namespace
 
 unsigned long long* g_gconv_dbg = nullptr;
+int g_gconv_slots = 2;   // resident CTAs per SM the grouped-conv kernels size their persistent grids for (experiments: 1)
+extern "C" void nbasr_dbg_gconv_slots(int n) { g_gconv_slots = n < 1 ? 1 : (n > 2 ? 2 : n); }
 extern "C" void nbasr_dbg_gconv_trace(unsigned long long* buf) { g_gconv_dbg = buf; }
 
 int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st) {
@@ -490,7 +494,7 @@ int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st) {
   a.tiles_per_utt = (g->T + GT - 1) / GT;
   a.ntiles = a.tiles_per_utt * g->B;
   a.nstage = fwd_nstage(a.ktaps);
-  int slots = 2 * nbasr_sm_count();
+  int slots = g_gconv_slots * nbasr_sm_count();
   a.nlanes = std::max(1, std::min(a.ntiles, slots / a.nslabs));
   a.epi = g->epi;
   static const bool no_pf = getenv("NBASR_GCONV_NO_PREFETCH") != nullptr;
@@ -531,7 +535,7 @@ int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C
   a.nslabs = (C + a.OUT - 1) / a.OUT;
   a.nchunks = (T + dstep + GT - 1) / GT;
   a.nunits = a.nchunks * B;
-  int slots = 2 * nbasr_sm_count();
+  int slots = g_gconv_slots * nbasr_sm_count();
   a.nlanes = std::max(1, std::min(a.nunits, slots / a.nslabs));
   a.dw = dw;
   a.dbias = dbias;

@@ -241,9 +241,9 @@ def main():
         sys.stderr.write(profiling.format_profile(prof) + '\n')
     fam = {}
     for tag, d in prof.items():
-        f = fam.setdefault(tag.split(' ')[0], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
-        for k in ('ms', 'flops', 'bytes', 'n'):
-            f[k] += d[k]
+        f = fam.setdefault(tag.split(' ')[0], dict(ms=0.0, flops=0.0, bytes=0.0, n=0, floor_cycles=0.0))
+        for k in ('ms', 'flops', 'bytes', 'n', 'floor_cycles'):
+            f[k] += d.get(k, 0.0)
     tot_ms = sum(f['ms'] for f in fam.values())
     dom_name, dom = max(fam.items(), key=lambda kv: kv[1]['ms'])
     pk = peaks()
@@ -271,6 +271,14 @@ def main():
                 'algorithmic_bytes_per_launch': dom['bytes'] / max(dom['n'], 1), 'algorithmic_flops_per_launch': dom['flops'] / max(dom['n'], 1), 'peak_source': pk['src'] + (' sustained' if tensor_bound else ''),
                 'launches_per_step': dom['n'], 'avg_launch_ms': dom['ms'] / max(dom['n'], 1),
                 'share_of_step_kernel_time': dom['ms'] / tot_ms,
+                # the grouped-conv kernel is bound by tensor-pipe ISSUE, not by HBM or FLOPs: time of its
+                # 3k MMAs per tile at 88 cycles each on every SM at the sampled clock, against the measured time
+                'mma_issue_floor': ({'ms': dom['floor_cycles'] / torch.cuda.get_device_properties(dev).multi_processor_count /
+                                     ((clocks or {}).get('sm_mhz') or 1965.0) / 1e3,
+                                     'frac_of_measured': dom['floor_cycles'] / torch.cuda.get_device_properties(dev).multi_processor_count /
+                                     ((clocks or {}).get('sm_mhz') or 1965.0) / 1e3 / dom['ms'],
+                                     'note': '3k tcgen05.mma (N=48, operands in shared memory, >= 88 cycles each) per 128x48 tile'}
+                                    if dom.get('floor_cycles') else None),
                 'families': {k: {'ms': round(v['ms'], 4), 'n': v['n'],
                                  'tflops': round(v['flops'] / v['ms'] / 1e9, 1) if v['ms'] else 0,
                                  'gbs': round(v['bytes'] / v['ms'] / 1e6, 0) if v['ms'] else 0} for k, v in fam.items()}}

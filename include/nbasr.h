@@ -112,12 +112,16 @@ int nbasr_gemm_wgrad(const nbasr_wgrad* p, void* stream);
  * off0 + j*dstep (j < ktaps):  ops.py:73-76 conv5/conv5d2/conv7/conv7d2 (groups=100).
  * w is (C, cpg, ktaps) fp32 in the reference layout (forward) or the group-transposed pack
  * made by nbasr_pack_gconv_dgrad (input gradient, with negated offsets). */
+#define NBASR_W_STABLE 2
 typedef struct nbasr_gconv {
   int32_t dtype;
   const void* x;          /* (B, Tp, C) padded activation, pointer to row 0 of the buffer */
   int32_t B, T, Tp, C, cpg, ktaps, off0, dstep;
   const void* w;          /* w_packed = 0: fp32 (C, cpg, ktaps)  -> SIMT kernel (any dtype)
-                             w_packed = 1: bf16 block-diagonal pack of nbasr_pack_gconv_mma -> tcgen05 kernel (BF16) */
+                             w_packed & 1: bf16 block-diagonal pack of nbasr_pack_gconv_mma -> tcgen05 kernel (BF16)
+                             w_packed & 2 (NBASR_W_STABLE): the pack was not written by the launch immediately before this
+                             one on the stream; the kernel may then fetch it before its programmatic launch dependency
+                             resolves (never set it right after nbasr_pack_gconv_mma on the same stream) */
   int32_t w_packed;
   nbasr_epilogue epi;     /* rows rho = b*Tp + PAD_L + t */
 } nbasr_gconv;

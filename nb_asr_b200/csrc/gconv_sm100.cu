@@ -64,7 +64,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 struct GcFwdArgs {
   int B, T, C, OUT, ktaps, dstep, off0;
-  int nslabs, ntiles, tiles_per_utt, nlanes, nstage, no_prefetch;
+  int nslabs, ntiles, tiles_per_utt, nlanes, nstage, no_prefetch, w_stable;
   nbasr_epilogue epi;
   int64_t Tp;
   unsigned long long* dbg;   // optional timeline dump (tools/trace_gconv.py): [cta][tile][8] globaltimer ns
@@ -122,13 +122,18 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tm = *tptr;
+  // w_packed bit 1 (NBASR_W_STABLE): the caller states that the weight pack was NOT written by the launch this one depends
+  // on (the engine re-packs in the optimiser tail of the previous step, many launches earlier), so its load may start before
+  // the dependency wait and overlap the previous kernel's tail.
+  auto load_weights = [&]() {
+    mbar_expect_tx(wbar, p.ktaps * WTAP_BYTES);
+    for (int j = 0; j < p.ktaps; ++j) tma_load_2d(wsm + j * WTAP_BYTES, &tmW, wbar, 0, (slab * p.ktaps + j) * NW);
+  };
+  if (p.w_stable && warp == 0 && lane == 0) load_weights();
   pdl_wait();                                  // everything above overlapped the previous kernel's tail
+  if (!p.w_stable && warp == 0 && lane == 0) load_weights();
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(wbar, p.ktaps * WTAP_BYTES);
-      for (int j = 0; j < p.ktaps; ++j) tma_load_2d(wsm + j * WTAP_BYTES, &tmW, wbar, 0, (slab * p.ktaps + j) * NW);
-    }
     // The epilogue's per-thread operands (skip-sum tensors, gate bits of the second output) are loaded AFTER the accumulator
     // is ready, so their latency sits on the epilogue's critical path (1 skip operand: 55 -> 92 us per launch).  The whole
     // producer warp therefore L2-prefetches them for each tile at the moment that tile's input load is issued, i.e. NS tiles
@@ -499,6 +504,7 @@ int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st) {
   a.epi = g->epi;
   static const bool no_pf = getenv("NBASR_GCONV_NO_PREFETCH") != nullptr;
   a.no_prefetch = no_pf ? 1 : 0;
+  a.w_stable = (g->w_packed & 2) ? 1 : 0;
   a.dbg = g_gconv_dbg;
   CUtensorMap tmX, tmW, tmO, tmO2;
   uint64_t dx[3] = {(uint64_t)g->C, (uint64_t)g->Tp, (uint64_t)g->B};

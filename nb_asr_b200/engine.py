@@ -440,7 +440,7 @@ class Engine:
                             gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = dt, src.data_ptr(), B, Ti, Tp, Cc, Cc // 100
                             gc.ktaps, gc.off0, gc.dstep = k, -lp, d
                             if dt == BF16:
-                                gc.w, gc.w_packed = self.wf[pn].data_ptr(), 1
+                                gc.w, gc.w_packed = self.wf[pn].data_ptr(), 3     # packed | stable (re-packed by the optimiser tail)
                             else:
                                 gc.w, gc.w_packed = self.P(pn + '.conv.weight'), 0
                             gc.epi = self._epi(Cc, bias=self.P(pn + '.conv.bias'), relu=1, drop_p=drop_p, salt=sl, adds=adds,
@@ -638,7 +638,7 @@ class Engine:
                         gc = GConv()
                         gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = dt, d.data_ptr(), B, Ti, Tp, Cc, Cc // 100
                         gc.ktaps, gc.off0, gc.dstep, gc.w = k, lp - (k - 1) * dd, dd, self.wt[pn].data_ptr()
-                        gc.w_packed = 1 if dt == BF16 else 0
+                        gc.w_packed = 3 if dt == BF16 else 0      # packed | stable
                         gc.epi = epi
                         call(bwd, lib.nbasr_gconv_fwd, C.byref(gc))
                         pl.keep.append(gc)

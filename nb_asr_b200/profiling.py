@@ -61,6 +61,17 @@ def op_work(fn_name, args, es):
     return fn_name.replace('nbasr_', ''), 0.0, 0.0
 
 
+def gconv_issue_floor_cycles(fn_name, args):
+    """Structural floor of the tcgen05 grouped-conv forward / input-gradient kernel: 3*k MMAs of N = 48 per
+    128-frame x 48-channel tile, each >= 88 cycles of tensor-pipe issue (both operands in shared memory), on one SM."""
+    if fn_name != 'nbasr_gconv_fwd':
+        return 0.0
+    g = _struct_of(args[0], GConv)
+    out = 40 if g.cpg == 10 else 48
+    tiles = -(-g.C // out) * g.B * -(-g.T // 128)
+    return tiles * 3.0 * g.ktaps * 88.0
+
+
 def profile_ops(engine, ops, iters=3):
     """Time every entry of a plan op list. Returns {tag: dict(n, ms, flops, bytes)} averaged over iters."""
     st = torch.cuda.current_stream()
@@ -78,7 +89,8 @@ def profile_ops(engine, ops, iters=3):
             continue   # warm-up pass
         for i, (fn, args) in enumerate(ops):
             tag, fl, by = op_work(fn.__name__, args, es)
-            d = acc.setdefault(tag, dict(n=0, ms=0.0, flops=0.0, bytes=0.0))
+            d = acc.setdefault(tag, dict(n=0, ms=0.0, flops=0.0, bytes=0.0, floor_cycles=0.0))
+            d['floor_cycles'] += gconv_issue_floor_cycles(fn.__name__, args)
             d['n'] += 1
             d['ms'] += evs[i].elapsed_time(evs[i + 1])
             d['flops'] += fl

@@ -33,6 +33,9 @@ for name, kw in (('full', dict(bias=bias, relu=1, out=out, mask_out=mask, mask_w
         _lib.check(lib.nbasr_gconv_fwd(C.byref(gc), U.stream()))
     torch.cuda.synchronize()
     buf = torch.zeros(8 * 64 * 8, dtype=torch.int64, device=U.DEV)
+    if os.environ.get('COLD'):
+        torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=U.DEV).zero_()     # evict the inputs from L2
+        torch.cuda.synchronize()
     lib.nbasr_dbg_gconv_trace(buf.data_ptr())
     _lib.check(lib.nbasr_gconv_fwd(C.byref(gc), U.stream()))
     torch.cuda.synchronize()
@@ -54,7 +57,7 @@ for name, kw in (('full', dict(bias=bias, relu=1, out=out, mask_out=mask, mask_w
         continue
     for cta in (0, 1):
         print(f'CTA {cta}: item | bar2_done mma_full_ok mma_issued | epi_tfull tmem_released bar1_done staged store_issued  (us since first stamp; v1 kernel: see gconv_sm100.cu)')
-        for it in range(8, 16):
+        for it in range(0, 24):
             r = t[cta, it]
             if r[1] == 0:
                 break

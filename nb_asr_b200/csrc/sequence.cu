@@ -140,6 +140,30 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(int h_dtype, const void* 
 }
 
 
+// global fp32 array -> shared memory with 8 independent 16-byte loads in flight per thread (a load-then-store loop pays one
+// global-memory latency per iteration)
+__device__ __forceinline__ void fill_smem_f32(float* dst, const float* __restrict__ src, int n) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int n4 = n >> 2;
+    for (int i0 = tid; i0 < n4; i0 += 8 * nt) {
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * nt;
+        t[u] = i < n4 ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * nt;
+        if (i < n4) reinterpret_cast<float4*>(dst)[i] = t[u];
+      }
+    }
+  } else {
+    for (int i = tid; i < n; i += nt) dst[i] = src[i];
+  }
+}
+
 // ---------------------------------------------------------------- head forward / dh, register-tiled (K <= 600)
 // logits[r][v] = sum_k h[r][k] W[v][k] + b[v] with W resident in shared memory (fp32) and h streamed in 64-wide K
 // chunks; a thread owns 4 rows x up to 8 classes (v = c8 + 8 i), so every shared-memory operand feeds 4..8 FMAs and
@@ -156,7 +180,7 @@ __global__ void __launch_bounds__(256, 1) head_fwd_tiled_kernel(int h_dtype, con
   float* hs = ws + V * K;               // HT_ROWS x HT_HP (V * K is a multiple of 4 on the float4 path)
   __shared__ int64_t rbase[HT_ROWS];    // element offset of each row of the tile (-1: past the end)
   const int tid = threadIdx.x, rg = tid >> 3, c8 = tid & 7, lane = tid & 31, wrp = tid >> 5;
-  for (int i = tid; i < V * K; i += blockDim.x) ws[i] = w[i];
+  fill_smem_f32(ws, w, V * K);            // classifier weights -> shared memory
   const int64_t nrows = (int64_t)B * T;
   const int ntiles = (int)((nrows + HT_ROWS - 1) / HT_ROWS);
   int vcls[8];
@@ -187,6 +211,25 @@ __global__ void __launch_bounds__(256, 1) head_fwd_tiled_kernel(int h_dtype, con
       {
         float sv0[HT_ROWS / 8], sv1[HT_ROWS / 8];
         const int k = k0 + 2 * lane;
+        if (h_dtype == NBASR_BF16 && (K & 1) == 0) {
+          // branch-free: every lane loads (a clamped address when its row / column pair is out of range), so the 16 loads are
+          // independent instructions the compiler can issue back to back.  The dispatcher guarantees even strides and a
+          // 4-byte aligned base, so (base + k) is a bf16x2 boundary.
+          __nv_bfloat162 raw[HT_ROWS / 8];
+          bool okv[HT_ROWS / 8];
+#pragma unroll
+          for (int i = 0; i < HT_ROWS / 8; ++i) {
+            const int64_t base = rbase[wrp + 8 * i];
+            okv[i] = base >= 0 && k < K;
+            raw[i] = *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const bf16*>(h) + (okv[i] ? base + k : 0));
+          }
+#pragma unroll
+          for (int i = 0; i < HT_ROWS / 8; ++i) {
+            const float2 f = __bfloat1622float2(raw[i]);
+            sv0[i] = okv[i] ? f.x : 0.f;
+            sv1[i] = okv[i] ? f.y : 0.f;
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < HT_ROWS / 8; ++i) {
           const int64_t base = rbase[wrp + 8 * i];
@@ -206,6 +249,7 @@ __global__ void __launch_bounds__(256, 1) head_fwd_tiled_kernel(int h_dtype, con
             }
           }
           sv0[i] = v0; sv1[i] = v1;
+        }
         }
 #pragma unroll
         for (int i = 0; i < HT_ROWS / 8; ++i)
@@ -296,23 +340,39 @@ constexpr int HD_ROWS = 64;
 __global__ void __launch_bounds__(256, 1) head_bwd_dh_kernel(int B, int T, int K, int V, const float* __restrict__ w,
                                                              const float* __restrict__ dl, float* __restrict__ dh, int64_t dh_bs,
                                                              int64_t dh_rs, bf16* __restrict__ dl16) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* ws = sm;                       // V x K
   float* ds = ws + V * K;               // HD_ROWS x 65
   const int tid = threadIdx.x;
-  for (int i = tid; i < V * K; i += blockDim.x) ws[i] = w[i];
+  fill_smem_f32(ws, w, V * K);
   const int64_t nrows = (int64_t)B * T;
   const int ntiles = (int)((nrows + HD_ROWS - 1) / HD_ROWS);
   const int k0 = tid, k1 = tid + 256, k2 = tid + 512;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t r0 = (int64_t)tile * HD_ROWS;
     __syncthreads();
-    for (int i = tid; i < HD_ROWS * 64; i += blockDim.x) {
-      const int rr = i >> 6, v = i & 63;
-      const int64_t r = r0 + rr;
-      const float d = (v < V && r < nrows) ? dl[r * V + v] : 0.f;
-      ds[rr * 65 + v] = d;
-      if (dl16 && r < nrows) dl16[r * 64 + v] = __float2bfloat16(d);
+    // 8 independent loads per thread before the first store (same reason as fill_smem_f32)
+    for (int i0 = tid; i0 < HD_ROWS * 64; i0 += 8 * blockDim.x) {
+      float dv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        const int rr = i >> 6, v = i & 63;
+        const int64_t r = r0 + rr;
+        const bool ok = i < HD_ROWS * 64 && v < V && r < nrows;
+        dv[u] = __ldg(dl + (ok ? r * V + v : 0));
+        if (!ok) dv[u] = 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < HD_ROWS * 64) {
+          const int rr = i >> 6, v = i & 63;
+          const int64_t r = r0 + rr;
+          ds[rr * 65 + v] = dv[u];
+          if (dl16 && r < nrows) dl16[r * 64 + v] = __float2bfloat16(dv[u]);
+        }
+      }
     }
     __syncthreads();
     for (int r8 = 0; r8 < HD_ROWS; r8 += 8) {

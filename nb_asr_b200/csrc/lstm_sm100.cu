@@ -29,7 +29,9 @@ constexpr int LC_W_BYTES = 128 * LC_KP * 2;      // 131072
 constexpr int LC_H_BYTES = LC_BG * LC_KP * 2;    // 16384
 constexpr int LC_SLICE = LC_U * LC_BG * 2;       // 1024: one CTA's h slice
 constexpr int LC_PRE_LD = 17;
-constexpr int LC_THREADS = 160;                  // warp 0: control (TMA, MMA), warps 1-4: epilogue
+constexpr int LC_THREADS = 160;                  // backward: warp 0 control (TMA, MMA), warps 1-4 epilogue
+constexpr int LC_FWD_EPI = 512;                  // forward: 16 epilogue warps, one cell per thread
+constexpr int LC_FWD_THREADS = 32 + LC_FWD_EPI;
 constexpr int LC_SMEM = LC_W_BYTES + 2 * LC_H_BYTES + 2 * LC_SLICE + 128 * LC_PRE_LD * 4 + 1024 + 256;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -87,7 +89,7 @@ constexpr int LC_A_COL = 32;             // first TMEM column of the resident W 
 // is streamed through the ~46 B/clk operand port: 2 816 cycles = 1.43 us of the ~3.7 us step); from tensor memory the
 // N = 16 MMA is bounded by its tiny B operand only.
 template <bool TS>
-__global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LstmCArgs p) {
+__global__ void __launch_bounds__(LC_FWD_THREADS, 1) lstm_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const LstmCArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
@@ -153,20 +155,21 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const _
       }
     }
   } else {
-    const int q = warp & 3;                       // TMEM lane quadrant this warp may read = gate index (rows are gate-major)
-    const int etid = threadIdx.x - 32;            // 0..127
-    const int ul = etid & 31, bq = etid >> 5;     // pair role: unit ul, utterances bq*4 .. bq*4+3
+    // 16 epilogue warps: warps 1-4 additionally read the accumulator (their TMEM lane quadrant = gate index, rows are
+    // gate-major); every thread owns ONE cell (unit ul, utterance bl), so the gate arithmetic of a step -- three sigmoids
+    // and two tanh per cell, part of the step's serial latency chain -- is 4x shorter than with 4 cells per thread.
+    const int q = warp & 3;
+    const bool reader = warp <= 4;
+    const int etid = threadIdx.x - 32;            // 0..511
+    const int ul = etid & 31, bl = etid >> 5;     // unit ul of this CTA, utterance bl of the cluster's 16
     const int u = (int)j * LC_U + ul;
-    const bool unit_ok = u < H;
-    float c_reg[4] = {0.f, 0.f, 0.f, 0.f};
-    float gxr[4][4];
+    const int b = b0 + bl;
+    const bool ok = u < H && b < p.B;
+    float c_reg = 0.f;
+    float gxr[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int b = b0 + bq * 4 + i;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) gxr[i][g] = (unit_ok && b < p.B && p.T > 0) ? __ldg(p.gx + ((int64_t)b * p.T) * H4 + g * H + u) : 0.f;
-    }
-    if (TS) {
+    for (int g = 0; g < 4; ++g) gxr[g] = (ok && p.T > 0) ? __ldg(p.gx + ((int64_t)b * p.T) * H4 + g * H + u) : 0.f;
+    if (TS && reader) {
       // row r = q*32 + lane of the W slice: shared memory (128B-swizzled K-major, 8 K blocks of 64) -> registers -> the
       // thread's own TMEM lane, 16 K elements (8 columns) at a time
       mbar_wait(wbar, 0);
@@ -186,26 +189,25 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const _
       mbar_arrive(aready);
     }
     for (int t = 0; t < p.T; ++t) {
-      mbar_wait(mma_bar, t & 1);
-      tcgen05_fence_after();
-      float v[16];
-      tmem_ld16_nowait(tm + ((uint32_t)(q * 32) << 16), v);
-      tmem_ld_wait();
-      tcgen05_fence_before();
+      if (reader) {
+        mbar_wait(mma_bar, t & 1);
+        tcgen05_fence_after();
+        float v[16];
+        tmem_ld16_nowait(tm + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld_wait();
+        tcgen05_fence_before();
 #pragma unroll
-      for (int b = 0; b < 16; ++b) pre_s[(q * 32 + lane) * LC_PRE_LD + b] = v[b];
-      named_bar_sync(1, 128);
+        for (int bb = 0; bb < 16; ++bb) pre_s[(q * 32 + lane) * LC_PRE_LD + bb] = v[bb];
+      }
+      named_bar_sync(1, LC_FWD_EPI);
       uint8_t* hs = stg_p + (t & 1) * LC_SLICE;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int bl = bq * 4 + i, b = b0 + bl;
-        const bool ok = unit_ok && b < p.B;
+      {
         float pre[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) pre[g] = pre_s[(g * 32 + ul) * LC_PRE_LD + bl] + gxr[i][g];
+        for (int g = 0; g < 4; ++g) pre[g] = pre_s[(g * 32 + ul) * LC_PRE_LD + bl] + gxr[g];
         const float ig = sigmoid_(pre[0]), fg = sigmoid_(pre[1]), gg = tanhf(pre[2]), og = sigmoid_(pre[3]);
-        c_reg[i] = fg * c_reg[i] + ig * gg;
-        const float h = ok ? og * tanhf(c_reg[i]) : 0.f;
+        c_reg = fg * c_reg + ig * gg;
+        const float h = ok ? og * tanhf(c_reg) : 0.f;
         // own slice in the destination layout: [chunk = ul/8][row group = bl/8][row = bl%8][elem = ul%8]
         reinterpret_cast<bf16*>(hs)[(((ul >> 3) * 2 + (bl >> 3)) * 8 + (bl & 7)) * 8 + (ul & 7)] = __float2bfloat16(h);
         if (ok) {
@@ -215,16 +217,16 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_fwd_kernel(const _
           if (p.gates) {
             float* gr = p.gates + ((int64_t)b * p.T + t) * H4;
             gr[u] = ig; gr[H + u] = fg; gr[2 * H + u] = gg; gr[3 * H + u] = og;
-            p.cstate[((int64_t)b * p.T + t) * H + u] = c_reg[i];
+            p.cstate[((int64_t)b * p.T + t) * H + u] = c_reg;
           }
           if (t + 1 < p.T) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) gxr[i][g] = __ldg(p.gx + ((int64_t)b * p.T + t + 1) * H4 + g * H + u);
+            for (int g = 0; g < 4; ++g) gxr[g] = __ldg(p.gx + ((int64_t)b * p.T + t + 1) * H4 + g * H + u);
           }
         }
       }
       fence_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, LC_FWD_EPI);
       if (etid < LC_NCTA && t + 1 < p.T) {
         // push the 1-KB slice into CTA `etid`'s buffer for step t+1; its mbarrier counts the bytes
         const uint32_t dst = mapa(hsm + ((t & 1) ^ 1) * LC_H_BYTES + j * LC_SLICE, etid);
@@ -454,7 +456,7 @@ int sm100_lstm_fwd(const float* gx, const void* w_packed, int T, int B, int H, v
   const int nclusters = (B + LC_BG - 1) / LC_BG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nclusters * LC_NCTA);
-  cfg.blockDim = dim3(LC_THREADS);
+  cfg.blockDim = dim3(LC_FWD_THREADS);
   cfg.dynamicSmemBytes = LC_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute at[1];

@@ -29,8 +29,7 @@ constexpr int LC_W_BYTES = 128 * LC_KP * 2;      // 131072
 constexpr int LC_H_BYTES = LC_BG * LC_KP * 2;    // 16384
 constexpr int LC_SLICE = LC_U * LC_BG * 2;       // 1024: one CTA's h slice
 constexpr int LC_PRE_LD = 17;
-constexpr int LC_THREADS = 160;                  // backward: warp 0 control (TMA, MMA), warps 1-4 epilogue
-constexpr int LC_FWD_EPI = 512;                  // forward: 16 epilogue warps, one cell per thread
+constexpr int LC_FWD_EPI = 512;                  // both kernels: warp 0 control (TMA, MMA) + 16 epilogue warps, one cell per thread
 constexpr int LC_FWD_THREADS = 32 + LC_FWD_EPI;
 constexpr int LC_SMEM = LC_W_BYTES + 2 * LC_H_BYTES + 2 * LC_SLICE + 128 * LC_PRE_LD * 4 + 1024 + 256;
 
@@ -266,7 +265,7 @@ struct LstmCBwdArgs {
   bf16* dgx_bf16;      // optional bf16 copy for the tensor-core GEMMs that follow
 };
 
-__global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LstmCBwdArgs p) {
+__global__ void __launch_bounds__(LC_FWD_THREADS, 1) lstm_cluster_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const LstmCBwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
@@ -290,7 +289,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_bwd_kernel(const _
     prefetch_tmap(&tmW);
     mbar_init(wbar, 1);
     mbar_init(mma_bar, 1);
-    mbar_init(dg_bar, 128);
+    mbar_init(dg_bar, LC_FWD_EPI);
     mbar_init(rfull(0), 1);
     mbar_init(rfull(1), 1);
     fence_barrier_init();
@@ -325,27 +324,28 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_bwd_kernel(const _
       }
     }
   } else {
+    // 16 epilogue warps, one cell (unit ul, utterance bl) per thread; warp w drains ONE of the four accumulator m-tiles
+    // (its TMEM lane quadrant is w % 4, its m-tile (w - 1) / 4) -- both used to be 4 sequential items per thread inside the
+    // step's latency chain.
     const int q = warp & 3;
-    const int etid = threadIdx.x - 32;
-    const int ul = etid & 31, bq = etid >> 5;
+    const int mt_own = (warp - 1) >> 2;
+    const int etid = threadIdx.x - 32;            // 0..511
+    const int ul = etid & 31, bl = etid >> 5;
     const int u = (int)j * LC_U + ul;
-    const bool unit_ok = u < H;
-    float dc_next[4] = {0.f, 0.f, 0.f, 0.f}, dh_rec[4] = {0.f, 0.f, 0.f, 0.f};
-    float nx[4][7];
+    const int b = b0 + bl;
+    const bool ok = u < H && b < p.B;
+    float dc_next = 0.f, dh_rec = 0.f;
+    float nx[7];
     auto prefetch = [&](int t) {
+      if (ok) {
+        nx[0] = __ldg(p.dh_seq + (int64_t)b * p.dh_bs + (int64_t)t * p.dh_rs + u);
+        const float* gr = p.gates + ((int64_t)b * p.T + t) * H4;
+        nx[1] = __ldg(gr + u); nx[2] = __ldg(gr + H + u); nx[3] = __ldg(gr + 2 * H + u); nx[4] = __ldg(gr + 3 * H + u);
+        nx[5] = __ldg(p.cstate + ((int64_t)b * p.T + t) * H + u);
+        nx[6] = t > 0 ? __ldg(p.cstate + ((int64_t)b * p.T + t - 1) * H + u) : 0.f;
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int b = b0 + bq * 4 + i;
-        if (unit_ok && b < p.B) {
-          nx[i][0] = __ldg(p.dh_seq + (int64_t)b * p.dh_bs + (int64_t)t * p.dh_rs + u);
-          const float* gr = p.gates + ((int64_t)b * p.T + t) * H4;
-          nx[i][1] = __ldg(gr + u); nx[i][2] = __ldg(gr + H + u); nx[i][3] = __ldg(gr + 2 * H + u); nx[i][4] = __ldg(gr + 3 * H + u);
-          nx[i][5] = __ldg(p.cstate + ((int64_t)b * p.T + t) * H + u);
-          nx[i][6] = t > 0 ? __ldg(p.cstate + ((int64_t)b * p.T + t - 1) * H + u) : 0.f;
-        } else {
-#pragma unroll
-          for (int z = 0; z < 7; ++z) nx[i][z] = 0.f;
-        }
+        for (int z = 0; z < 7; ++z) nx[z] = 0.f;
       }
     };
     if (p.T > 0) prefetch(p.T - 1);
@@ -355,25 +355,19 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_bwd_kernel(const _
         // partial sums of dh_t for the own units from all 16 CTAs (sent during step s-1)
         mbar_wait(rfull((s - 1) & 1), ((s - 1) >> 1) & 1);
         const bf16* rb = reinterpret_cast<const bf16*>(rcv_p + ((s - 1) & 1) * LB_SEND_BYTES);
+        float acc = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float acc = 0.f;
-#pragma unroll
-          for (int src = 0; src < LC_NCTA; ++src) acc += __bfloat162float(rb[(src * 32 + ul) * LC_BG + bq * 4 + i]);
-          dh_rec[i] = acc;
-        }
+        for (int src = 0; src < LC_NCTA; ++src) acc += __bfloat162float(rb[(src * 32 + ul) * LC_BG + bl]);
+        dh_rec = acc;
       }
       bf16* dgo = reinterpret_cast<bf16*>(dsm_p);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int bl = bq * 4 + i, b = b0 + bl;
-        const bool ok = unit_ok && b < p.B;
-        const float dh = nx[i][0] + dh_rec[i];
-        const float ig = nx[i][1], fg = nx[i][2], gg = nx[i][3], og = nx[i][4], c = nx[i][5], cprev = nx[i][6];
+      {
+        const float dh = nx[0] + dh_rec;
+        const float ig = nx[1], fg = nx[2], gg = nx[3], og = nx[4], c = nx[5], cprev = nx[6];
         const float tc = tanhf(c);
         const float dov = dh * tc;
-        const float dc = dc_next[i] + dh * og * (1.f - tc * tc);
-        dc_next[i] = dc * fg;
+        const float dc = dc_next + dh * og * (1.f - tc * tc);
+        dc_next = dc * fg;
         float d[4];
         d[0] = dc * gg * ig * (1.f - ig);
         d[1] = dc * cprev * fg * (1.f - fg);
@@ -394,17 +388,16 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_bwd_kernel(const _
       if (t == 0) break;
       prefetch(t - 1);
       fence_async_smem();
-      mbar_arrive(dg_bar);                                   // 128 arrivals -> the MMA thread may read the dg operand
+      mbar_arrive(dg_bar);                                   // 512 arrivals -> the MMA thread may read the dg operand
       mbar_wait(mma_bar, s & 1);
       tcgen05_fence_after();
       uint8_t* sb = snd_p + (s & 1) * LB_SEND_BYTES;
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
+      {
         float v[16];
-        tmem_ld16_nowait(tm + ((uint32_t)(q * 32) << 16) + mt * 16, v);
+        tmem_ld16_nowait(tm + ((uint32_t)(q * 32) << 16) + mt_own * 16, v);
         tmem_ld_wait();
         // lane l of quadrant q holds k = mt*128 + q*32 + l -> unit l of CTA (4*mt + q)
-        bf16* dst = reinterpret_cast<bf16*>(sb + (4 * mt + q) * LC_SLICE) + lane * LC_BG;
+        bf16* dst = reinterpret_cast<bf16*>(sb + (4 * mt_own + q) * LC_SLICE) + lane * LC_BG;
         uint4 pk[2];
         __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
@@ -414,7 +407,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) lstm_cluster_bwd_kernel(const _
       }
       tcgen05_fence_before();
       fence_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, LC_FWD_EPI);
       if (etid < LC_NCTA) {
         const uint32_t dst = mapa(rcv + (s & 1) * LB_SEND_BYTES + j * LC_SLICE, etid);
         const uint32_t bar = mapa(rfull(s & 1), etid);
@@ -491,7 +484,7 @@ int sm100_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, const void
   const int nclusters = (B + LC_BG - 1) / LC_BG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nclusters * LC_NCTA);
-  cfg.blockDim = dim3(LC_THREADS);
+  cfg.blockDim = dim3(LC_FWD_THREADS);
   cfg.dynamicSmemBytes = LB_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute at[1];

@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting, device queries and the GEMM dispatch (bf16 -> tcgen05, fp32 -> SIMT).
 #include <cstdarg>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -13,6 +14,28 @@ int nbasr_fail(const char* fmt, ...) {
   va_end(ap);
   return 1;
 }
+
+// ---- environment switches, read once at load time
+namespace {
+struct EnvState {
+  bool flag[NBASR_ENV_COUNT];
+  int gemm_bn;
+  double wgrad_epi_us;
+  EnvState() {
+    static const char* names[NBASR_ENV_COUNT] = {"NBASR_FORCE_SIMT", "NBASR_NO_PDL", "NBASR_GCONV_NO_PREFETCH", "NBASR_LSTM_SS",
+                                                 "NBASR_DEBUG"};
+    for (int i = 0; i < NBASR_ENV_COUNT; ++i) flag[i] = getenv(names[i]) != nullptr;
+    const char* bn = getenv("NBASR_GEMM_BN");
+    gemm_bn = bn ? atoi(bn) : 0;
+    const char* eu = getenv("NBASR_WGRAD_EPI_US");
+    wgrad_epi_us = eu ? atof(eu) : 3.0;
+  }
+};
+const EnvState g_env;
+}  // namespace
+bool nbasr_env_flag(int which) { return g_env.flag[which]; }
+int nbasr_env_gemm_bn() { return g_env.gemm_bn; }
+double nbasr_env_wgrad_epi_us() { return g_env.wgrad_epi_us; }
 
 extern "C" {
 
@@ -31,11 +54,7 @@ int nbasr_sm_count(void) {
 
 int nbasr_gemm_tn(const nbasr_gemm* p, void* stream) {
   if (p->nb <= 0 || p->nr <= 0 || p->N <= 0) return 0;
-  if (p->dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT")) {
-    // default: CTA-pair (cta_group::2) kernel; NBASR_GEMM_1CTA=1 selects the single-CTA kernel
-    static const bool one_cta = getenv("NBASR_GEMM_1CTA") != nullptr;
-    return one_cta ? sm100_gemm_tn(p, as_stream(stream)) : sm100_gemm_tn_pair(p, as_stream(stream));
-  }
+  if (p->dtype != NBASR_F32 && !nbasr_env_flag(NBASR_ENV_FORCE_SIMT)) return sm100_gemm_tn_pair(p, as_stream(stream));
   SimtGemmArgs a{};
   a.a = p->a; a.a_dtype = p->dtype; a.a_ib = p->a_bs; a.a_ir = p->a_rs; a.a_kb = 0; a.a_kr = 1;
   a.nib = p->nb; a.nir = p->nr;
@@ -48,10 +67,7 @@ int nbasr_gemm_tn(const nbasr_gemm* p, void* stream) {
 
 int nbasr_gemm_wgrad(const nbasr_wgrad* p, void* stream) {
   if (p->nb <= 0 || p->nr <= 0 || p->N <= 0 || p->M <= 0) return 0;
-  if (p->dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT")) {
-    static const bool one_cta = getenv("NBASR_GEMM_1CTA") != nullptr;
-    return one_cta ? sm100_gemm_wgrad(p, as_stream(stream)) : sm100_gemm_wgrad_pair(p, as_stream(stream));
-  }
+  if (p->dtype != NBASR_F32 && !nbasr_env_flag(NBASR_ENV_FORCE_SIMT)) return sm100_gemm_wgrad_pair(p, as_stream(stream));
   SimtGemmArgs a{};
   a.a = p->dy; a.a_dtype = p->dtype; a.a_ib = 0; a.a_ir = 1; a.a_kb = p->dy_bs; a.a_kr = p->dy_rs;
   a.nib = 1; a.nir = p->M;

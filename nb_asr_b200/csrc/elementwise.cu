@@ -152,253 +152,6 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
 }
 
 
-// bf16 LayerNorm backward, one warp per frame row, 16 warps / SM (one persistent CTA per SM).
-//  * each lane streams its own 16-byte slices of the next row's x and dy into a private shared-memory slot with
-//    cp.async while it works on the current row (no cross-lane sharing -> no barriers, only cp.async.wait_group);
-//    ~70 KB of loads are in flight per SM without costing registers;
-//  * dgamma / dbeta partials stay in registers for the whole kernel (QN x 8 x 2 floats per lane) and are reduced
-//    once per CTA at the end (shared memory, then one atomic per channel and CTA).
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void unpack8(const uint4& r, float* v) {
-  const uint32_t* u = reinterpret_cast<const uint32_t*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[2 * i] = __uint_as_float(u[i] << 16);
-    v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
-  }
-}
-
-__device__ __forceinline__ void lds8f(const float* p, float* v) {      // two forced 128-bit shared loads
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a));
-}
-
-template <int QN>
-__global__ void __launch_bounds__(512, 1) layernorm_bwd_bf16_kernel(
-    const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_i, const float* __restrict__ rstd_i,
-    const float* __restrict__ gamma, int B, int Tt, int Tp, int C, bf16* __restrict__ dx, bf16* __restrict__ dx2,
-    const uint32_t* __restrict__ mask2, float scale2, int64_t mask_rows, int mask2_w, float* __restrict__ dgamma,
-    float* __restrict__ dbeta) {
-  extern __shared__ __align__(16) uint8_t lnsm[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int gw = blockIdx.x * 16 + wib, nW = gridDim.x * 16;
-  const int ngroups = C >> 3;
-  const int rowb = C * 2;
-  const int64_t nrows = (int64_t)B * Tt;
-  float* gs = reinterpret_cast<float*>(lnsm);
-  uint8_t* wbuf = lnsm + C * 4 + (size_t)wib * 4 * rowb;     // [2 buffers][x row | dy row]
-  pdl_launch_dependents();
-  pdl_wait();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) gs[i] = gamma[i];
-  __syncthreads();
-
-  float dg[QN][8], db[QN][8];
-#pragma unroll
-  for (int q = 0; q < QN; ++q)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dg[q][i] = db[q][i] = 0.f;
-  int64_t moff[QN];
-  const int meb = (mask2_w == 32) ? 4 : 8;
-#pragma unroll
-  for (int q = 0; q < QN; ++q) moff[q] = mask_byte_addr(0, (lane + 32 * q) * 8, mask2_w, mask_rows);
-
-  auto rho_of = [&](int64_t r) { return (r / Tt) * Tp + NBASR_PAD_L + (r % Tt); };
-  auto issue = [&](int64_t r, int buf) {
-    if (r < nrows) {
-      const int64_t rho = rho_of(r);
-      uint8_t* xb = wbuf + buf * 2 * rowb;
-#pragma unroll
-      for (int q = 0; q < QN; ++q) {
-        const int g = lane + 32 * q;
-        if (g < ngroups) {
-          cp_async16(xb + g * 16, x + rho * C + g * 8);
-          cp_async16(xb + rowb + g * 16, dy + rho * C + g * 8);
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  int64_t r = gw;
-  issue(r, 0);
-  float mean_n = 0.f, rstd_n = 0.f;
-  if (r < nrows) { const int64_t rho = rho_of(r); mean_n = mean_i[rho]; rstd_n = rstd_i[rho]; }
-  int buf = 0;
-  const float invC = 1.f / C;
-  for (; r < nrows; r += nW, buf ^= 1) {
-    const int64_t rho = rho_of(r);
-    const float mean = mean_n, rstd = rstd_n;
-    const int64_t rn = r + nW;
-    issue(rn, buf ^ 1);
-    if (rn < nrows) { const int64_t rhon = rho_of(rn); mean_n = mean_i[rhon]; rstd_n = rstd_i[rhon]; }
-    // gate bits of this row: issued before any arithmetic so their latency hides behind pass 1
-    uint32_t mw[QN];
-#pragma unroll
-    for (int q = 0; q < QN; ++q)
-      mw[q] = (dx2 && mask2 && lane + 32 * q < ngroups) ? reinterpret_cast<const uint8_t*>(mask2)[moff[q] + rho * meb] : 0xffu;
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    const uint8_t* xb = wbuf + buf * 2 * rowb;
-    const float nm = -mean * rstd;
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int q = 0; q < QN; ++q) {
-      const int g = lane + 32 * q;
-      if (g < ngroups) {
-        float xv[8], dv[8], ga[8];
-        unpack8(*reinterpret_cast<const uint4*>(xb + g * 16), xv);
-        unpack8(*reinterpret_cast<const uint4*>(xb + rowb + g * 16), dv);
-        lds8f(gs + g * 8, ga);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = fmaf(xv[i], rstd, nm);
-          const float gy = dv[i] * ga[i];
-          s1 += gy;
-          s2 = fmaf(gy, xh, s2);
-          dg[q][i] = fmaf(dv[i], xh, dg[q][i]);
-          db[q][i] += dv[i];
-        }
-      }
-    }
-    s1 = warp_sum(s1) * invC;
-    s2 = warp_sum(s2) * invC;
-    // dx = rstd (gy - s1 - xh s2) = gy rstd + x k1 + k0   (xh = x rstd + nm)
-    const float k1 = -rstd * rstd * s2, k0 = -rstd * (s1 + nm * s2);
-#pragma unroll
-    for (int q = 0; q < QN; ++q) {
-      const int g = lane + 32 * q;
-      if (g < ngroups) {
-        float xv[8], dv[8], ga[8], o[8];
-        unpack8(*reinterpret_cast<const uint4*>(xb + g * 16), xv);
-        unpack8(*reinterpret_cast<const uint4*>(xb + rowb + g * 16), dv);
-        lds8f(gs + g * 8, ga);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaf(xv[i], k1, fmaf(dv[i] * ga[i], rstd, k0));
-        if (dx) store8(dx + rho * C + g * 8, o);
-        if (dx2) {
-          const uint32_t w = mw[q];
-          float o2[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o2[i] = ((w >> i) & 1u) ? o[i] * scale2 : 0.f;
-          store8(dx2 + rho * C + g * 8, o2);
-        }
-      }
-    }
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  // CTA reduction over the 16 warps (the row buffers are dead now), then one atomic per channel
-  float* red = reinterpret_cast<float*>(lnsm + C * 4);
-  const int CP = QN * 256;
-#pragma unroll
-  for (int q = 0; q < QN; ++q) {
-    float* d0 = red + ((size_t)wib * 2) * CP + (lane + 32 * q) * 8;
-    store8(d0, dg[q]);
-    store8(d0 + CP, db[q]);
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, bsum = 0.f;
-#pragma unroll
-    for (int w = 0; w < 16; ++w) {
-      a += red[((size_t)w * 2) * CP + c];
-      bsum += red[((size_t)w * 2 + 1) * CP + c];
-    }
-    atomicAdd(dgamma + c, a);
-    atomicAdd(dbeta + c, bsum);
-  }
-}
-
-// bf16 LayerNorm forward with the same per-lane cp.async row prefetch as the backward kernel: 16 warps / SM, each lane
-// keeps its 16-byte slices of the next LNF_D rows in flight into a private shared-memory ring.  (With one row in flight
-// a warp turns a row around once per memory latency: measured 2.9 TB/s; the ring makes the kernel issue-bound instead.)
-constexpr int LNF_D = 4;
-template <int QN>
-__global__ void __launch_bounds__(512, 1) layernorm_fwd_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int Tt,
-                                                                    int Tp, int C, const float* __restrict__ gamma,
-                                                                    const float* __restrict__ beta, float eps,
-                                                                    float* __restrict__ mean_o, float* __restrict__ rstd_o) {
-  extern __shared__ __align__(16) uint8_t lnsm[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int gw = blockIdx.x * 16 + wib, nW = gridDim.x * 16;
-  const int ngroups = C >> 3;
-  const int rowb = C * 2;
-  const int64_t nrows = (int64_t)B * Tt;
-  float* gs = reinterpret_cast<float*>(lnsm);          // gamma | beta
-  uint8_t* wbuf = lnsm + C * 8 + (size_t)wib * LNF_D * rowb;
-  pdl_launch_dependents();
-  pdl_wait();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { gs[i] = gamma[i]; gs[C + i] = beta[i]; }
-  __syncthreads();
-  auto rho_of = [&](int64_t r) { return (r / Tt) * Tp + NBASR_PAD_L + (r % Tt); };
-  auto issue = [&](int64_t r, int buf) {
-    if (r < nrows) {
-      const int64_t rho = rho_of(r);
-#pragma unroll
-      for (int q = 0; q < QN; ++q) {
-        const int g = lane + 32 * q;
-        if (g < ngroups) cp_async16(wbuf + buf * rowb + g * 16, x + rho * C + g * 8);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  int64_t r = gw;
-#pragma unroll
-  for (int d = 0; d < LNF_D; ++d) issue(r + (int64_t)d * nW, d);
-  int buf = 0;
-  const float invC = 1.f / C;
-  for (; r < nrows; r += nW, buf = (buf + 1 == LNF_D) ? 0 : buf + 1) {
-    const int64_t rho = rho_of(r);
-    asm volatile("cp.async.wait_group %0;" ::"n"(LNF_D - 1) : "memory");
-    const uint8_t* xb = wbuf + buf * rowb;
-    float v[QN][8];
-    float s = 0.f;
-#pragma unroll
-    for (int q = 0; q < QN; ++q) {
-      const int g = lane + 32 * q;
-      if (g < ngroups) {
-        unpack8(*reinterpret_cast<const uint4*>(xb + g * 16), v[q]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[q][i];
-      }
-    }
-    const float mean = warp_sum(s) * invC;
-    float ss = 0.f;
-#pragma unroll
-    for (int q = 0; q < QN; ++q) {
-      if (lane + 32 * q < ngroups) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float d = v[q][i] - mean;
-          ss = fmaf(d, d, ss);
-        }
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(ss) * invC + eps);
-    if (lane == 0 && mean_o) {
-      mean_o[rho] = mean;
-      rstd_o[rho] = rstd;
-    }
-    const float nm = -mean * rstd;
-#pragma unroll
-    for (int q = 0; q < QN; ++q) {
-      const int g = lane + 32 * q;
-      if (g < ngroups) {
-        float ga[8], be[8], o[8];
-        lds8f(gs + g * 8, ga);
-        lds8f(gs + C + g * 8, be);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaf(fmaf(v[q][i], rstd, nm), ga[i], be[i]);
-        store8(y + rho * C + g * 8, o);
-      }
-    }
-    issue(r + (int64_t)LNF_D * nW, buf);       // refill the slot this lane has just finished reading
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
 __global__ void eltwise_kernel(int src_dtype, const void* __restrict__ src, int64_t ld_src, int B, int Tt, int Tp, int C,
                                nbasr_epilogue e) {
   const int nch = (C + 31) >> 5;
@@ -516,26 +269,9 @@ int nbasr_layernorm_fwd(int dtype, const void* x, void* y, int B, int T, int Tp,
   int64_t rows = (int64_t)B * T;
   int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 8);
   if (blocks < 1) return 0;
-  static const bool ln_v1 = getenv("NBASR_LN_V1") != nullptr;
-  if (dtype == NBASR_BF16 && !ln_v1 && rows * (int64_t)C < (int64_t)1 << 40 && (int64_t)B * Tp < (int64_t)1 << 30)
+  if (dtype == NBASR_BF16 && rows * (int64_t)C < (int64_t)1 << 40 && (int64_t)B * Tp < (int64_t)1 << 30)
     return ln2_fwd(x, y, B, T, Tp, C, gamma, beta, eps, mean, rstd, as_stream(stream));   // packed-fp32x2 kernels (layernorm2.cu)
-  if (dtype == NBASR_BF16 && !getenv("NBASR_LN_FWD_V1")) {
-    const int QN = (C / 8 + 31) / 32;
-    const int grid = (int)std::min<int64_t>((rows + 15) / 16, nbasr_sm_count());
-    const size_t smb = (size_t)C * 8 + (size_t)16 * LNF_D * C * 2;
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaFuncSetAttribute(layernorm_fwd_bf16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(layernorm_fwd_bf16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(layernorm_fwd_bf16_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr2 = true;
-    }
-#define NBASR_LNF(Q) launch_pdl(layernorm_fwd_bf16_kernel<Q>, dim3(grid), dim3(512), smb, as_stream(stream), 1, (const bf16*)x, (bf16*)y, B, T, Tp, C, gamma, beta, eps, mean, rstd)
-    if (QN <= 3) NBASR_LNF(3);
-    else if (QN == 4) NBASR_LNF(4);
-    else NBASR_LNF(5);
-#undef NBASR_LNF
-  } else if (dtype == NBASR_BF16)
+  if (dtype == NBASR_BF16)
     layernorm_fwd_kernel<bf16><<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)x, (bf16*)y, B, T, Tp, C, gamma, beta, eps, mean, rstd);
   else
     layernorm_fwd_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>((const float*)x, (float*)y, B, T, Tp, C, gamma, beta, eps, mean, rstd);
@@ -551,32 +287,15 @@ int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* m
   int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 2);
   if (blocks < 1) return 0;
   size_t sm = (size_t)8 * 2 * 8 * 32 * LN_MAXG * sizeof(float);   // 80 KB
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) {
     cudaFuncSetAttribute(layernorm_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr = true;
   }
-  static const bool ln_v1 = getenv("NBASR_LN_V1") != nullptr;
-  if (dtype == NBASR_BF16 && !ln_v1 && (int64_t)B * Tp < (int64_t)1 << 30 && mask_rows * 8 * ((C + 31) / 32 + 1) < (int64_t)1 << 31)
+  if (dtype == NBASR_BF16 && (int64_t)B * Tp < (int64_t)1 << 30 && mask_rows * 8 * ((C + 31) / 32 + 1) < (int64_t)1 << 31)
     return ln2_bwd(dy, x, mean, rstd, gamma, B, T, Tp, C, dx, dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta, as_stream(stream));
-  if (dtype == NBASR_BF16 && !getenv("NBASR_LN_BWD_V1")) {
-    const int QN = (C / 8 + 31) / 32;
-    const int grid = (int)std::min<int64_t>((rows + 15) / 16, nbasr_sm_count());
-    const size_t smb = (size_t)C * 4 + std::max((size_t)16 * 4 * C * 2, (size_t)16 * 2 * QN * 256 * 4);
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaFuncSetAttribute(layernorm_bwd_bf16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      cudaFuncSetAttribute(layernorm_bwd_bf16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      cudaFuncSetAttribute(layernorm_bwd_bf16_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      attr2 = true;
-    }
-#define NBASR_LNB(Q) launch_pdl(layernorm_bwd_bf16_kernel<Q>, dim3(grid), dim3(512), smb, as_stream(stream), 1, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma, B, T, Tp, C, (bf16*)dx, (bf16*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta)
-    if (QN <= 3) NBASR_LNB(3);
-    else if (QN == 4) NBASR_LNB(4);
-    else NBASR_LNB(5);
-#undef NBASR_LNB
-  } else if (dtype == NBASR_BF16)
+  if (dtype == NBASR_BF16)
     layernorm_bwd_kernel<bf16><<<blocks, 256, sm, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, B, T, Tp, C, (bf16*)dx, (bf16*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta);
   else
     layernorm_bwd_kernel<float><<<blocks, 256, sm, as_stream(stream)>>>((const float*)dy, (const float*)x, mean, rstd, gamma, B, T, Tp, C, (float*)dx, (float*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta);

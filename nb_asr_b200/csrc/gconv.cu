@@ -234,11 +234,11 @@ int nbasr_gconv_fwd(const nbasr_gconv* p, void* stream) {
   dim3 grid((p->C + CS - 1) / CS, (p->T + G_TT - 1) / G_TT, p->B);
   size_t sm = fwd_smem(p->cpg, p->ktaps);
   if (p->dtype == NBASR_BF16) {
-    static bool attr = false;
+    static DevOnce attr;
     if (!attr) { cudaFuncSetAttribute(gconv_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     gconv_fwd_kernel<bf16><<<grid, G_NT, sm, as_stream(stream)>>>(*p);
   } else {
-    static bool attr = false;
+    static DevOnce attr;
     if (!attr) { cudaFuncSetAttribute(gconv_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     gconv_fwd_kernel<float><<<grid, G_NT, sm, as_stream(stream)>>>(*p);
   }
@@ -258,18 +258,18 @@ int nbasr_gconv_wgrad(int dtype, const void* dz, const void* x, int B, int T, in
   NBASR_REQUIRE(cpg == 6 || cpg == 8 || cpg == 10 || cpg == 12, "cpg");
   NBASR_REQUIRE(ktaps <= 7 && (dstep == 1 || dstep == 2), "taps");
   if (B <= 0 || T <= 0) return 0;
-  if (dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT"))
+  if (dtype == NBASR_BF16 && !nbasr_env_flag(NBASR_ENV_FORCE_SIMT))
     return sm100_gconv_wgrad(dz, x, B, T, Tp, C, cpg, ktaps, off0, dstep, dw, dbias, as_stream(stream));
   if (dbias && nbasr_colsum(dtype, dz, B, T, Tp, C, dbias, stream)) return 1;
   int CS = slab_channels(cpg);
   dim3 grid((C + CS - 1) / CS, B);
   size_t sm = wgrad_smem(cpg);
   if (dtype == NBASR_BF16) {
-    static bool attr = false;
+    static DevOnce attr;
     if (!attr) { cudaFuncSetAttribute(gconv_wgrad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     gconv_wgrad_kernel<bf16><<<grid, G_NT, sm, as_stream(stream)>>>((const bf16*)dz, (const bf16*)x, B, T, Tp, C, cpg, ktaps, off0, dstep, dw);
   } else {
-    static bool attr = false;
+    static DevOnce attr;
     if (!attr) { cudaFuncSetAttribute(gconv_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     gconv_wgrad_kernel<float><<<grid, G_NT, sm, as_stream(stream)>>>((const float*)dz, (const float*)x, B, T, Tp, C, cpg, ktaps, off0, dstep, dw);
   }

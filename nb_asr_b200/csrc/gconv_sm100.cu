@@ -8,7 +8,7 @@
 //  * The input tile (128 frames + halo) x 64 channels is TMA-loaded ONCE per (frame tile, slab) in the
 //    128B-swizzled K-major layout; every (dilated) tap is the SAME tile addressed through a UMMA
 //    descriptor whose start address is advanced by whole 128-byte rows (swizzle is a function of the
-//    absolute smem address, verified on B200 with csrc/dbg.cu) -- no im2col, no per-tap reload.
+//    absolute smem address, verified on B200 with tools/experiments/dbg.cu) -- no im2col, no per-tap reload.
 //  * A CTA keeps one slab's block-diagonal weights (<= 7 taps x 6 KB) in smem and walks frame tiles;
 //    2 CTAs / SM, 3-stage TMA ring, 4 TMEM accumulator stages, warp roles as in gemm_sm100.cu.
 //  * Forward and input-gradient share the kernel (different weight pack / tap offsets); the fused
@@ -27,8 +27,6 @@
 #include "sm100_ptx.cuh"
 
 using namespace sm100;
-
-extern int g_gconv_slots;
 
 namespace {
 
@@ -67,18 +65,8 @@ struct GcFwdArgs {
   int nslabs, ntiles, tiles_per_utt, nlanes, nstage, no_prefetch, w_stable;
   nbasr_epilogue epi;
   int64_t Tp;
-  unsigned long long* dbg;   // optional timeline dump (tools/trace_gconv.py): [cta][tile][8] globaltimer ns
 };
 
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define GC_STAMP(slot)                                                                         \
-  do {                                                                                         \
-    if (p.dbg && blockIdx.x < 8 && it < 64) p.dbg[((size_t)blockIdx.x * 64 + it) * 8 + (slot)] = gtime(); \
-  } while (0)
 
 // Epilogue of the forward / input-gradient kernel.  8 warps: warp pair (w, w+4) shares a TMEM lane quadrant and
 // splits the 48 accumulator columns in two halves of 24.  Results are staged in shared memory as a dense
@@ -188,9 +176,7 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int as = it % NACC;
         const uint32_t aphase = (it / NACC) & 1;
         mbar_wait(tempty_bar(as), aphase ^ 1);
-        GC_STAMP(2);
         mbar_wait(full_bar(stage), phase);
-        GC_STAMP(3);
         tcgen05_fence_after();
         const uint32_t sa = asm0 + stage * A_BYTES;
         for (int j = 0; j < p.ktaps; ++j) {
@@ -235,7 +221,6 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           if (g * 8 < nvalid) w2[g] = reinterpret_cast<const uint8_t*>(epi.mask2)[mask_byte_addr(rho2, cbeg + g * 8, epi.mask2_w, epi.mask_rows)];
       }
       mbar_wait(tfull_bar(as), aphase);
-      if (etid == 0) GC_STAMP(4);
       tcgen05_fence_after();
       float v[24];
       const uint32_t ta = tm + ((uint32_t)(q * 32) << 16) + as * 64 + 24 * hh;
@@ -244,7 +229,6 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));           // accumulator is in registers: release the TMEM stage early
-      if (etid == 0) GC_STAMP(6);
       const bool rowok = t < p.T;
       const int64_t rho = (int64_t)b * p.Tp + NBASR_PAD_L + t;
       uint32_t m[3] = {0, 0, 0};
@@ -280,10 +264,8 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int i = 0; i < 24; ++i) v[i] = 0.f;      // rows past the utterance land on zero pad rows / are clipped
       }
       // staging buffers are free once the previous tile's TMA stores have finished READING shared memory
-      if (etid == 0) GC_STAMP(0);
       if (etid == 0) bulk_wait_read0();
       named_bar_sync(1, NEPI);
-      if (etid == 0) GC_STAMP(7);
       uint8_t* orow = ost + row * OUTB + 48 * hh;
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
@@ -300,7 +282,6 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (epi.mask_out) mst[row * 8 + 3 * hh + g] = (g * 8 < nvalid) ? (uint8_t)m[g] : (uint8_t)0;   // 8-byte entry per row
       }
       fence_async_smem();
-      if (etid == 0) GC_STAMP(1);
       named_bar_sync(1, NEPI);
       if (epi.mask_out && etid < GT && t0 + etid < p.T) {
         // 128 consecutive 8-byte entries of this slab's mask plane: one fully coalesced store per warp
@@ -311,7 +292,6 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (epi.out) tma_store_3d(&tmO, osm, c0, NBASR_PAD_L + t0, b);
         if (epi.out2) tma_store_3d(&tmO2, osm + OSTAGE_BYTES, c0, NBASR_PAD_L + t0, b);
         bulk_commit();
-        GC_STAMP(5);
       }
     }
     if (etid == 0) bulk_wait0();
@@ -482,12 +462,9 @@ __global__ void pack_gconv_mma_kernel(const float* __restrict__ w, bf16* __restr
 
 }  // namespace
 
-unsigned long long* g_gconv_dbg = nullptr;
-int g_gconv_slots = 2;   // resident CTAs per SM the grouped-conv kernels size their persistent grids for (experiments: 1)
-extern "C" void nbasr_dbg_gconv_slots(int n) { g_gconv_slots = n < 1 ? 1 : (n > 2 ? 2 : n); }
-extern "C" void nbasr_dbg_gconv_trace(unsigned long long* buf) { g_gconv_dbg = buf; }
+constexpr int GCONV_SLOTS = 2;   // resident CTAs per SM the grouped-conv kernels size their persistent grids for
 
-int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st) {
+int sm100_gconv_fwd(const nbasr_gconv* g, cudaStream_t st) {
   GcFwdArgs a{};
   a.B = g->B; a.T = g->T; a.Tp = g->Tp; a.C = g->C; a.OUT = slab_out(g->cpg);
   a.ktaps = g->ktaps; a.dstep = g->dstep; a.off0 = g->off0;
@@ -499,13 +476,11 @@ int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st) {
   a.tiles_per_utt = (g->T + GT - 1) / GT;
   a.ntiles = a.tiles_per_utt * g->B;
   a.nstage = fwd_nstage(a.ktaps);
-  int slots = g_gconv_slots * nbasr_sm_count();
+  int slots = GCONV_SLOTS * nbasr_sm_count();
   a.nlanes = std::max(1, std::min(a.ntiles, slots / a.nslabs));
   a.epi = g->epi;
-  static const bool no_pf = getenv("NBASR_GCONV_NO_PREFETCH") != nullptr;
-  a.no_prefetch = no_pf ? 1 : 0;
+  a.no_prefetch = nbasr_env_flag(NBASR_ENV_GCONV_NO_PREFETCH) ? 1 : 0;
   a.w_stable = (g->w_packed & 2) ? 1 : 0;
-  a.dbg = g_gconv_dbg;
   CUtensorMap tmX, tmW, tmO, tmO2;
   uint64_t dx[3] = {(uint64_t)g->C, (uint64_t)g->Tp, (uint64_t)g->B};
   int64_t sx[3] = {1, g->C, (int64_t)g->Tp * g->C};
@@ -522,7 +497,7 @@ int sm100_gconv_fwd_v1(const nbasr_gconv* g, cudaStream_t st) {
   if (sm100_get_map(o2, 3, dx, sx, bo, &tmO2, 0)) return 1;
   NBASR_REQUIRE(!g->epi.mask_out || g->epi.mask_w == a.OUT, "grouped-conv mask planes are slab wide");
   size_t smem = (size_t)a.ktaps * WTAP_BYTES + (size_t)a.nstage * A_BYTES + 2 * OSTAGE_BYTES + 1024 + 256 + 1024;
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gconv_mma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BUDGET);
     if (e != cudaSuccess) return nbasr_fail("gconv_mma_fwd smem attr: %s", cudaGetErrorString(e));
@@ -541,7 +516,7 @@ int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C
   a.nslabs = (C + a.OUT - 1) / a.OUT;
   a.nchunks = (T + dstep + GT - 1) / GT;
   a.nunits = a.nchunks * B;
-  int slots = g_gconv_slots * nbasr_sm_count();
+  int slots = GCONV_SLOTS * nbasr_sm_count();
   a.nlanes = std::max(1, std::min(a.nunits, slots / a.nslabs));
   a.dw = dw;
   a.dbias = dbias;
@@ -552,7 +527,7 @@ int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C
   uint32_t bx[3] = {64, AROWS, 1};
   if (sm100_get_map(dz, 3, dd, sd, bz, &tmDZ)) return 1;
   if (sm100_get_map(x, 3, dd, sd, bx, &tmX)) return 1;
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gconv_mma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
     if (e != cudaSuccess) return nbasr_fail("gconv_mma_wgrad smem attr: %s", cudaGetErrorString(e));

@@ -371,7 +371,7 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
   }
 }
 
-// waves x cycles per K block (see gemm_sm100.cu pick_bn), for the paired tile 256 x BN: four MMAs of max(88, BN/2)
+// waves x cycles per K block , for the paired tile 256 x BN: four MMAs of max(88, BN/2)
 // cycles against 16 KB of A + 64 BN bytes of B ingest per CTA
 int pick_bn_pair(int N, int m_tiles, int pairs) {
   int best = 256;
@@ -396,8 +396,7 @@ int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
   a.m_tiles = a.mt_per_utt * g->nb;
   const int sms = nbasr_sm_count();
   a.BN = pick_bn_pair(g->N, a.m_tiles, sms / 2);
-  static const char* env_bn = getenv("NBASR_GEMM_BN");      // tuning override (tools/bench_gemm.py)
-  if (env_bn) a.BN = std::max(64, std::min(256, atoi(env_bn) / 32 * 32));
+  if (nbasr_env_gemm_bn()) a.BN = std::max(64, std::min(256, nbasr_env_gemm_bn() / 32 * 32));   // tuning override (tools/bench_gemm.py)
   a.n_tiles = (g->N + a.BN - 1) / a.BN;
   a.pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
   a.o_r0 = g->o_r0; a.o_bs = g->o_bs; a.o_rs = g->o_rs;
@@ -411,7 +410,7 @@ int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
   int64_t sb[2] = {1, g->ldw};
   uint32_t bb[2] = {BK, (uint32_t)(a.BN / 2)};
   if (sm100_get_map(g->w, 2, db, sb, bb, &tmB)) return 1;
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return nbasr_fail("gemm_tn_pair smem attr: %s", cudaGetErrorString(e));
@@ -435,7 +434,7 @@ int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, gemm_tn_pair_kernel, &cfg) != cudaSuccess || n < 1) n = sms / 2;
     max_pairs = std::min(n, sms / 2);
-    if (getenv("NBASR_DEBUG")) fprintf(stderr, "[nbasr] gemm_tn_pair: %d co-resident CTA pairs on %d SMs\n", max_pairs, sms);
+    if (nbasr_env_flag(NBASR_ENV_DEBUG)) fprintf(stderr, "[nbasr] gemm_tn_pair: %d co-resident CTA pairs on %d SMs\n", max_pairs, sms);
   }
   const int npairs = std::max(1, std::min(a.pair_tiles, max_pairs));
   cudaError_t e = launch_pdl(gemm_tn_pair_kernel, dim3(2 * npairs), dim3(THREADS), (size_t)SMEM_BYTES, st, 2, tmA, tmB, a);
@@ -464,7 +463,7 @@ int sm100_gemm_wgrad_pair(const nbasr_wgrad* g, cudaStream_t st) {
       const int ups = (a.total_units + sp - 1) / sp;
       const int eff = (a.total_units + ups - 1) / ups;
       const int waves = (pairs * eff + slots - 1) / slots;
-      static const double epi_us = getenv("NBASR_WGRAD_EPI_US") ? atof(getenv("NBASR_WGRAD_EPI_US")) : 3.0;
+      const double epi_us = nbasr_env_wgrad_epi_us();
       const double cost = waves * (ups * 0.27 * a.BN / 256.0 + epi_us);
       if (best < 0 || cost < best) { best = cost; splits = eff; }
     }
@@ -480,7 +479,7 @@ int sm100_gemm_wgrad_pair(const nbasr_wgrad* g, cudaStream_t st) {
   uint64_t dx[3] = {(uint64_t)g->N, (uint64_t)g->nr, (uint64_t)g->nb};
   int64_t sx[3] = {1, g->x_rs, g->x_bs};
   if (sm100_get_map(g->x, 3, dx, sx, bx, &tmX)) return 1;
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_BYTES);
     if (e != cudaSuccess) return nbasr_fail("gemm_wgrad_pair smem attr: %s", cudaGetErrorString(e));

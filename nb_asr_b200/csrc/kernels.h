@@ -5,10 +5,26 @@
 
 #include "../../include/nbasr.h"
 
+// Environment switches are read ONCE, when the library is loaded (api.cu), never on the call path.
+enum NbasrEnvFlag { NBASR_ENV_FORCE_SIMT = 0, NBASR_ENV_NO_PDL, NBASR_ENV_GCONV_NO_PREFETCH, NBASR_ENV_LSTM_SS, NBASR_ENV_DEBUG,
+                    NBASR_ENV_COUNT };
+bool nbasr_env_flag(int which);
+int nbasr_env_gemm_bn();          // NBASR_GEMM_BN tuning override (0 = cost model)
+double nbasr_env_wgrad_epi_us();  // NBASR_WGRAD_EPI_US cost-model constant (default 3.0)
+
+// "Do once per device" latch for cudaFuncSetAttribute(MaxDynamicSharedMemorySize): the attribute is per (function, device),
+// so a process that drives several GPUs (Trainer(gpus=[k]) with k != 0) must opt in on each of them.
+// Usage keeps the classic shape:  static DevOnce attr; if (!attr) { ...set...; attr = true; }
+struct DevOnce {
+  unsigned long long mask = 0;
+  static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool operator!() const { return !((mask >> dev()) & 1ull); }
+  DevOnce& operator=(bool v) { if (v) mask |= 1ull << dev(); return *this; }
+};
+
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait() in common.cuh) and an optional cluster
 // width.  NBASR_NO_PDL=1 disables the attribute (plain stream ordering).
 #ifdef __CUDACC__
-#include <cstdlib>
 #include <utility>
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
@@ -17,8 +33,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[2];
   int n = 0;
-  static const bool pdl = getenv("NBASR_NO_PDL") == nullptr;
-  if (pdl) {
+  if (!nbasr_env_flag(NBASR_ENV_NO_PDL)) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -49,13 +64,11 @@ struct SimtGemmArgs {
 };
 int simt_gemm_launch(const SimtGemmArgs& a, cudaStream_t st);
 
-// tcgen05 paths (gemm_sm100.cu)
-int sm100_gemm_tn(const nbasr_gemm* p, cudaStream_t st);
-int sm100_gemm_tn_pair(const nbasr_gemm* p, cudaStream_t st);   // cta_group::2 (gemm2_sm100.cu)
-int sm100_gemm_wgrad(const nbasr_wgrad* p, cudaStream_t st);
-int sm100_gemm_wgrad_pair(const nbasr_wgrad* p, cudaStream_t st);   // cta_group::2 (gemm2_sm100.cu)
+// tcgen05 dense GEMMs on CTA pairs, cta_group::2 (gemm2_sm100.cu)
+int sm100_gemm_tn_pair(const nbasr_gemm* p, cudaStream_t st);
+int sm100_gemm_wgrad_pair(const nbasr_wgrad* p, cudaStream_t st);
 
-// cached bf16 TMA descriptor (rank 2/3, 128B swizzle); strides in elements for dims 1..rank-1
+// cached TMA descriptor of 2-byte elements (rank 2/3, 128B swizzle); strides in elements for dims 1..rank-1 (tma_maps.cu)
 struct CUtensorMap_st;
 int sm100_get_map(const void* base, int rank, const uint64_t* dims, const int64_t* strides_el, const uint32_t* box,
                   CUtensorMap_st* out, int swizzle128 = 1);

@@ -359,7 +359,7 @@ int ln2_fwd_launch(const bf16* x, bf16* y, int B, int T, int Tp, int C, const fl
   const int64_t rows = (int64_t)B * T;
   const int grid = (int)std::min<int64_t>((rows + 15) / 16, nbasr_sm_count());
   const size_t smb = (size_t)C * 8 + (size_t)16 * LN2_D * C * 2;
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(ln2_fwd_kernel<QN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return nbasr_fail("ln2_fwd smem attr: %s", cudaGetErrorString(e));
@@ -381,7 +381,7 @@ int ln2_bwd_launch(const bf16* dy, const bf16* x, const float* mean, const float
   // gamma | row ring (re-used by the final reduction) | dbeta slots
   const size_t ring = (size_t)NWARP * 4 * C * 2;
   const size_t smb = (size_t)C * 4 + std::max(ring, (size_t)NWARP * 2 * QN * 256 * 4) + (DBS ? (size_t)NWARP * QN * 1024 : 0);
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(ln2_bwd_kernel<QN, NWARP, DBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return nbasr_fail("ln2_bwd smem attr: %s", cudaGetErrorString(e));

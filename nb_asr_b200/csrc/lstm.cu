@@ -261,7 +261,7 @@ extern "C" {
 int nbasr_lstm_fwd(const float* gx, const float* w_hh, int T, int B, int H, void* h_seq, int h_dtype, int64_t h_bs,
                    int64_t h_rs, int64_t ld_h, float* gates, float* cstate, const void* hstate, float* work, void* stream) {
   (void)ld_h;
-  if (hstate && h_dtype == NBASR_BF16 && !getenv("NBASR_FORCE_SIMT"))   // bf16 mode: tensor-core cluster kernel
+  if (hstate && h_dtype == NBASR_BF16 && !nbasr_env_flag(NBASR_ENV_FORCE_SIMT))   // bf16 mode: tensor-core cluster kernel
     return sm100_lstm_fwd(gx, hstate, T, B, H, h_seq, h_dtype, h_bs, h_rs, gates, cstate, as_stream(stream));
   NBASR_REQUIRE(H <= L_KP && H % 4 == 0, "hidden size");
   int sms = nbasr_sm_count();
@@ -275,7 +275,7 @@ int nbasr_lstm_fwd(const float* gx, const float* w_hh, int T, int B, int H, void
   cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * ngroups, st);
   LstmFwdArgs a{gx, w_hh, T, B, H, bg, h_seq, h_dtype, h_bs, h_rs, gates, cstate, work, cnt};
   size_t sm = sizeof(float) * ((size_t)bg * L_KP + (size_t)L_KS * L_ROWS * (bg + 1));
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) { cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   void* args[] = {&a};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)lstm_fwd_kernel, dim3(nslices, ngroups), dim3(L_NT), args, sm, st);
@@ -287,7 +287,7 @@ int nbasr_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, int64_t ld
                    const float* gates, const float* cstate, int T, int B, int H, float* dgx, float* work,
                    const void* w_hh_packed, void* dgx_bf16, void* stream) {
   (void)ld_dh;
-  if (w_hh_packed && !getenv("NBASR_FORCE_SIMT"))
+  if (w_hh_packed && !nbasr_env_flag(NBASR_ENV_FORCE_SIMT))
     return sm100_lstm_bwd(dh_seq, dh_bs, dh_rs, w_hh_packed, gates, cstate, T, B, H, dgx, dgx_bf16, as_stream(stream));
   if (dgx_bf16) return nbasr_fail("the fp32 SIMT recurrence does not write a bf16 copy");
   NBASR_REQUIRE(4 * H <= LB_RP && H <= L_KP && H % 4 == 0, "hidden size");
@@ -301,7 +301,7 @@ int nbasr_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, int64_t ld
   cudaMemsetAsync(cnt, 0, sizeof(unsigned int) * ngroups, st);
   LstmBwdArgs a{dh_seq, dh_bs, dh_rs, w_hh, gates, cstate, T, B, H, bg, dgx, cnt};
   size_t sm = sizeof(float) * ((size_t)bg * LB_RP + (size_t)LB_RS * L_U * (bg + 1));
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) { cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   void* args[] = {&a};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)lstm_bwd_kernel, dim3(nslices, ngroups), dim3(L_NT), args, sm, st);

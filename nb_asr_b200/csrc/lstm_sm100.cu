@@ -436,8 +436,8 @@ int sm100_lstm_fwd(const float* gx, const void* w_packed, int T, int B, int H, v
   int64_t sw[2] = {1, LC_KP};
   uint32_t bw[2] = {64, 128};
   if (sm100_get_map(w_packed, 2, dw, sw, bw, &tmW)) return 1;
-  static const bool ts = getenv("NBASR_LSTM_SS") == nullptr;      // default: W slice resident in tensor memory
-  static bool attr = false;
+  const bool ts = !nbasr_env_flag(NBASR_ENV_LSTM_SS);      // default: W slice resident in tensor memory
+  static DevOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(lstm_cluster_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_cluster_fwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -474,7 +474,7 @@ int sm100_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, const void
   int64_t sw[2] = {1, LC_KP};
   uint32_t bw[2] = {64, 128};
   if (sm100_get_map(w_packed, 2, dw, sw, bw, &tmW)) return 1;
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(lstm_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_cluster_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);

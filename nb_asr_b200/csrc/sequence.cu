@@ -819,8 +819,8 @@ int nbasr_head_fwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B
   if (rows == 0) return 0;
   const size_t smt = sizeof(float) * ((size_t)V * K + HT_ROWS * HT_HP);
   const bool aligned = h_dtype != NBASR_BF16 || (((h_bs | h_rs) & 1) == 0 && ((uintptr_t)h & 3) == 0);
-  if (smt <= 200 * 1024 && rows >= 4 * HT_ROWS && aligned && !getenv("NBASR_HEAD_V1")) {
-    static bool attr = false;
+  if (smt <= 200 * 1024 && rows >= 4 * HT_ROWS && aligned) {
+    static DevOnce attr;
     if (!attr) { cudaFuncSetAttribute(head_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     int grid = (int)std::min<int64_t>((rows + HT_ROWS - 1) / HT_ROWS, nbasr_sm_count());
     head_fwd_tiled_kernel<<<grid, 256, smt, as_stream(stream)>>>(h_dtype, h, h_bs, h_rs, B, T, K, V, w, bias, logits, logp);
@@ -841,7 +841,7 @@ int nbasr_head_bwd(int h_dtype, const void* h, int64_t h_bs, int64_t h_rs, int B
   const bool fuse_dw = dw && (size_t)(2 * V * K + HB_R * K + HB_R * 64) * sizeof(float) <= 220 * 1024;
   size_t sm = sizeof(float) * ((size_t)V * K + (fuse_dw ? (size_t)V * K : 0) + HB_R * K + HB_R * 64);
   NBASR_REQUIRE(sm <= 220 * 1024, "head too wide for the fused backward kernel");
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) { cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
   int blocks = (int)std::min<int64_t>((rows + HB_R - 1) / HB_R, nbasr_sm_count());
   head_bwd_kernel<<<blocks, 256, sm, as_stream(stream)>>>(h_dtype, h, h_bs, h_rs, B, T, K, V, w, dlogits, dh, dh_bs, dh_rs,
@@ -868,7 +868,7 @@ int nbasr_head_bwd_dh(int B, int T, int K, int V, const float* w, const float* d
   if (rows == 0) return 0;
   const size_t smt = sizeof(float) * ((size_t)V * K + HD_ROWS * 65);
   NBASR_REQUIRE(smt <= 200 * 1024, "head too wide for head_bwd_dh");
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) { cudaFuncSetAttribute(head_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   int grid = (int)std::min<int64_t>((rows + HD_ROWS - 1) / HD_ROWS, nbasr_sm_count());
   head_bwd_dh_kernel<<<grid, 256, smt, as_stream(stream)>>>(B, T, K, V, w, dlogits, dh, dh_bs, dh_rs, (bf16*)dl16);
@@ -896,7 +896,7 @@ int nbasr_greedy_per(const float* logp, int B, int T, int V, const int64_t* audi
   if (B == 0) return 0;
   size_t sm = sizeof(int) * ((size_t)2 * T + S + 3 * (S + 1));
   NBASR_REQUIRE(sm <= 200 * 1024, "sequence too long for the decode kernel");
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) { cudaFuncSetAttribute(greedy_per_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   greedy_per_kernel<<<B, 256, sm, as_stream(stream)>>>(logp, B, T, V, audio_len, len_div, targets, S, targets_len, lut, hyp,
                                                        hyp_len, dist, per, work, nullptr, nullptr);
@@ -911,7 +911,7 @@ int nbasr_beam_per(const float* logp, int B, int T, int V, const int64_t* audio_
   NBASR_REQUIRE(beam_width >= 1 && beam_width <= BS_MAXW && V <= BS_MAXV && T < 32768, "beam search shape");
   const size_t smb = (size_t)2 * beam_width * T * sizeof(int16_t);
   NBASR_REQUIRE(smb <= 150 * 1024, "sequence too long for the beam-search kernel");
-  static bool attr = false;
+  static DevOnce attr;
   if (!attr) {
     cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);
     cudaFuncSetAttribute(greedy_per_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

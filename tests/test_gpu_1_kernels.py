@@ -81,20 +81,11 @@ def test_simt_wgrad_and_dgrad():
         assert U.relerr(U.from_padded(dx, B, T).cpu(), gx) < 1e-5
 
 
-@pytest.mark.parametrize('dt', [F32, BF16, 'mma', 'frag'])
+@pytest.mark.parametrize('dt', [F32, BF16, 'mma'])
 @pytest.mark.parametrize('op', ['conv5', 'conv5d2', 'conv7', 'conv7d2'])
 @pytest.mark.parametrize('Cc', [600, 800, 1000, 1200])
 def test_gconv_fwd_bwd(dt, op, Cc):
-    """F32 / BF16: SIMT kernels.  'mma': bf16 tcgen05 block-diagonal kernels (the product path in bf16 mode).
-    'frag': the experimental warp-level MMA (mma.sync + ldmatrix) forward / input-gradient kernel on the same packs."""
-    if dt == 'frag':
-        lib = _lib.load()
-        lib.nbasr_dbg_gconv_impl(1)
-        try:
-            _gconv_fwd_bwd('mma', op, Cc)
-        finally:
-            lib.nbasr_dbg_gconv_impl(0)
-        return
+    """F32 / BF16: SIMT kernels.  'mma': bf16 tcgen05 block-diagonal kernels (the product path in bf16 mode)."""
     _gconv_fwd_bwd(dt, op, Cc)
 
 

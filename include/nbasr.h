@@ -12,7 +12,14 @@
  *   - caller allocates all outputs/workspaces; no hidden allocation, no sync, no host<->device
  *     copies; every launch goes to the `stream` argument (a cudaStream_t passed as void*);
  *   - return 0 on success, non-zero on error (nbasr_last_error() gives the message);
- *   - dtype codes: NBASR_F32 = 0, NBASR_BF16 = 1.
+ *   - dtype codes: NBASR_F32 = 0, NBASR_BF16 = 1, NBASR_F16 = 2.
+ *
+ * 16-bit mode ("bf16" precision of the engine): FORWARD activations and the weight operands that multiply them are
+ * IEEE fp16 (10-bit mantissa: bf16 storage of every activation costs 2-4e-2 on the logits of this 80-layer net, fp16
+ * 0.8-1.5e-2), stored multiplied by a power-of-two `act_scale` so that small activations stay out of the
+ * fp16 subnormal range; GRADIENTS and the operands that multiply them are bf16 (range).  One tcgen05.mma needs both
+ * operands in the same format (mixed f16 x bf16 faults, tools/experiments/README.md), so tensors that feed a weight
+ * gradient are additionally written as an unscaled bf16 copy by their producer (training plans only).
  *
  * Activation layout ("frames x channels", channels-last): a tensor of one encoder block is
  * (B, Tp, C) contiguous with Tp = T + NBASR_PAD_L + NBASR_PAD_R; frame t of utterance b is row
@@ -30,14 +37,15 @@ extern "C" {
 
 #define NBASR_F32 0
 #define NBASR_BF16 1
+#define NBASR_F16 2
 #define NBASR_PAD_L 8
 #define NBASR_PAD_R 4
 #define NBASR_MAX_ADD 3
 
 /* Fused output stage shared by the dense GEMM, grouped-conv and element-wise kernels.
  * For an accumulator value v at output row rho, column n:
- *   v += bias[n]                                   (ops.py:26,45 bias of Conv1d / Linear)
- *   m  = (0 < v <= 20); v = min(max(v,0),20)       (ops.py:27-28,46-47 ReLU + clamp_max 20)
+ *   v  = v*acc_scale + bias[n]*bias_scale          (ops.py:26,45 bias of Conv1d / Linear; scales: see below)
+ *   m  = (0 < v <= relu_hi); v = min(max(v,0),relu_hi)   (ops.py:27-28,46-47 ReLU + clamp_max 20)
  *   keep ~ Bernoulli(1-p); m &= keep; v = keep ? v/(1-p) : 0   (ops.py:22,29,40,48 Dropout)
  *   v += add[0][rho,n] + add[1][rho,n] + ...       (model.py:16-22 skip-connection sum)
  *   out[rho,n] = v ; mask_out bit(rho,n) = m
@@ -68,6 +76,14 @@ typedef struct nbasr_epilogue {
   int32_t mask_w;       /* plane width of mask_out: 32, 40 or 48 */
   int32_t mask2_w;      /* plane width of mask2 */
   int32_t accumulate;   /* out += v instead of out = v (fp32 out only, SIMT path) */
+  /* Scaled fp16 activations: a kernel whose A operand holds act_scale*x produces act_scale*(W x) in its accumulator.
+   * Forward edges stay in the scaled domain (acc_scale 1, bias_scale = act_scale, relu_hi = 20*act_scale, skip tensors
+   * and `out` scaled alike; out2 with scale2 = 1/act_scale and mask2 = NULL is the unscaled bf16 copy for the weight
+   * gradient); a consumer that wants true values (LSTM input projection) sets acc_scale = 1/act_scale.
+   * 0 means "unset": acc_scale 1, bias_scale 1, relu_hi 20. */
+  float acc_scale;
+  float bias_scale;
+  float relu_hi;
 } nbasr_epilogue;
 
 /* Dense GEMM  C[(b,r), n] = sum_k A[(b,r), k] * W[n, k]  followed by the epilogue.
@@ -78,7 +94,7 @@ typedef struct nbasr_epilogue {
  * nn.Linear edge (ops.py:45), LSTM input projection (model.py:100), and their input-gradients
  * (W pre-packed by nbasr_pack_weight).  dtype BF16 -> tcgen05/TMEM/TMA kernel; F32 -> SIMT. */
 typedef struct nbasr_gemm {
-  int32_t dtype;          /* of A and W */
+  int32_t dtype;          /* of A and W: F32 (SIMT), BF16 or F16 (tcgen05; both operands share the format) */
   const void* a;
   int64_t a_bs, a_rs;
   int32_t nb, nr, K, N;
@@ -114,7 +130,7 @@ int nbasr_gemm_wgrad(const nbasr_wgrad* p, void* stream);
  * made by nbasr_pack_gconv_dgrad (input gradient, with negated offsets). */
 #define NBASR_W_STABLE 2
 typedef struct nbasr_gconv {
-  int32_t dtype;
+  int32_t dtype;          /* of x and of the packed weights: F32 / BF16 / F16 */
   const void* x;          /* (B, Tp, C) padded activation, pointer to row 0 of the buffer */
   int32_t B, T, Tp, C, cpg, ktaps, off0, dstep;
   const void* w;          /* w_packed = 0: fp32 (C, cpg, ktaps)  -> SIMT kernel (any dtype)
@@ -131,7 +147,7 @@ int nbasr_pack_gconv_dgrad(const float* w, float* wt, int C, int cpg, int ktaps,
 /* bf16 block-diagonal operand for the tcgen05 grouped-conv kernel: [slab][tap][48][64], slabs of 48 (cpg 6/8/12)
  * or 40 (cpg 10) channels; transposed = 1 gives the input-gradient operand (group-transposed, taps flipped).
  * nbasr_gconv_mma_pack_elems returns the number of bf16 elements of the pack. */
-int nbasr_pack_gconv_mma(const float* w, void* out, int C, int cpg, int ktaps, int transposed, void* stream);
+int nbasr_pack_gconv_mma(const float* w, void* out, int out_dtype, int C, int cpg, int ktaps, int transposed, void* stream);
 int64_t nbasr_gconv_mma_pack_elems(int C, int cpg, int ktaps);
 /* dw[c_out][i][j] += sum_{b,t} dz[b,t,c_out] * x[b, t+off0+j*dstep, g*cpg+i];  dbias[c] += sum_{b,t} dz[b,t,c]
  * (dbias may be NULL). BF16 -> tcgen05 kernel, F32 -> SIMT. */
@@ -148,18 +164,23 @@ int nbasr_eltwise(int src_dtype, const void* src, int64_t ld_src, int B, int T, 
 int nbasr_colsum(int dtype, const void* x, int B, int T, int Tp, int C, float* out, void* stream);
 
 /* LayerNorm over channels, eps given (model.py:47,92: nn.LayerNorm(C, eps=1e-3)), biased
- * variance, affine.  Saves mean / rstd per row for the backward pass. */
+ * variance, affine.  Saves mean / rstd per row for the backward pass.
+ * y = (gamma * xhat + beta) * out_scale in `dtype`; optional y2 = (gamma * xhat + beta) as bf16 (the unscaled copy a
+ * weight gradient reads; NULL in eval plans).  With scaled fp16 input (x = s*x_true) the caller passes eps * s^2: xhat
+ * is then exactly that of the unscaled tensor, and the saved mean / rstd are those of the scaled one. */
 int nbasr_layernorm_fwd(int dtype, const void* x, void* y, int B, int T, int Tp, int C,
                         const float* gamma, const float* beta, float eps, float* mean, float* rstd,
-                        void* stream);
-/* dx (+ optional dx2 = dx * bit(mask2) * scale2), dgamma += , dbeta += */
-int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* mean, const float* rstd,
-                        const float* gamma, int B, int T, int Tp, int C, void* dx, void* dx2,
+                        float out_scale, void* y2, void* stream);
+/* dx (+ optional dx2 = dx * bit(mask2) * scale2), dgamma += , dbeta +=.  dy / dx / dx2 have dtype `dtype` (BF16 in
+ * 16-bit mode), x has x_dtype; x_scale = s when x (and the saved mean / rstd) are those of the scaled tensor s*x_true:
+ * the gradient wrt x_true is s times the gradient wrt the stored tensor. */
+int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, int x_dtype, float x_scale, const float* mean,
+                        const float* rstd, const float* gamma, int B, int T, int Tp, int C, void* dx, void* dx2,
                         const uint32_t* mask2, float scale2, int64_t mask_rows, int mask2_w, float* dgamma,
                         float* dbeta, void* stream);
 
-/* (B, F, T) fp32 channel-first input (trainer.py:210) -> padded channels-last (B, Tp, F). */
-int nbasr_transpose_in(const float* audio, void* out, int dtype, int B, int F, int T, int Tp, void* stream);
+/* (B, F, T) fp32 channel-first input (trainer.py:210) -> padded channels-last (B, Tp, F), multiplied by `scale`. */
+int nbasr_transpose_in(const float* audio, void* out, int dtype, int B, int F, int T, int Tp, float scale, void* stream);
 
 /* Weight packing: out[n][q*M + m] = w[m*ws_m + n*ws_n + (t0 + q*tstep)*ws_t],  q < nq.
  * Produces the bf16 / fp32 operand copies (plain, transposed, tap-flipped) used by gemm_tn. */

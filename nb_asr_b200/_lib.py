@@ -4,7 +4,7 @@ import os
 
 from . import _build
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 PAD_L, PAD_R = 8, 4
 MAX_ADD = 3
 
@@ -15,7 +15,8 @@ class Epilogue(C.Structure):
     _fields_ = [('bias', _vp), ('relu20', _i32), ('drop_p', _f32), ('drop_seed', _u64), ('drop_step', _vp),
                 ('n_add', _i32), ('add', _vp * MAX_ADD), ('add_dtype', _i32), ('out', _vp), ('out_dtype', _i32),
                 ('ld_out', _i64), ('mask_out', _vp), ('out2', _vp), ('out2_dtype', _i32), ('mask2', _vp),
-                ('scale2', _f32), ('mask_rows', _i64), ('mask_w', _i32), ('mask2_w', _i32), ('accumulate', _i32)]
+                ('scale2', _f32), ('mask_rows', _i64), ('mask_w', _i32), ('mask2_w', _i32), ('accumulate', _i32),
+                ('acc_scale', _f32), ('bias_scale', _f32), ('relu_hi', _f32)]
 
 
 class Gemm(C.Structure):
@@ -43,15 +44,15 @@ _SIGS = {
     'nbasr_gemm_wgrad': [C.POINTER(Wgrad), _vp],
     'nbasr_gconv_fwd': [C.POINTER(GConv), _vp],
     'nbasr_pack_gconv_dgrad': [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp],
-    'nbasr_pack_gconv_mma': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    'nbasr_pack_gconv_mma': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     'nbasr_gconv_mma_pack_elems': [C.c_int, C.c_int, C.c_int],
     'nbasr_gconv_wgrad': [C.c_int, _vp, _vp] + [C.c_int] * 8 + [_vp, _vp, _vp],
     'nbasr_eltwise': [C.c_int, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), _vp],
     'nbasr_colsum': [C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
-    'nbasr_layernorm_fwd': [C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _vp],
-    'nbasr_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
+    'nbasr_layernorm_fwd': [C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _f32, _vp, _vp, _f32, _vp, _vp],
+    'nbasr_layernorm_bwd': [C.c_int, _vp, _vp, C.c_int, _f32, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
                             _f32, _i64, C.c_int, _vp, _vp, _vp],
-    'nbasr_transpose_in': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    'nbasr_transpose_in': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32, _vp],
     'nbasr_pack_weight': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64, _i64, _i64, _vp],
     'nbasr_convert': [_vp, _vp, C.c_int, _i64, _vp],
     'nbasr_lstm_fwd': [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp],

@@ -55,6 +55,7 @@ int nbasr_sm_count(void) {
 int nbasr_gemm_tn(const nbasr_gemm* p, void* stream) {
   if (p->nb <= 0 || p->nr <= 0 || p->N <= 0) return 0;
   if (p->dtype != NBASR_F32 && !nbasr_env_flag(NBASR_ENV_FORCE_SIMT)) return sm100_gemm_tn_pair(p, as_stream(stream));
+  NBASR_REQUIRE(p->dtype != NBASR_F16, "the SIMT GEMM takes fp32 / bf16 operands");
   SimtGemmArgs a{};
   a.a = p->a; a.a_dtype = p->dtype; a.a_ib = p->a_bs; a.a_ir = p->a_rs; a.a_kb = 0; a.a_kr = 1;
   a.nib = p->nb; a.nir = p->nr;
@@ -67,7 +68,8 @@ int nbasr_gemm_tn(const nbasr_gemm* p, void* stream) {
 
 int nbasr_gemm_wgrad(const nbasr_wgrad* p, void* stream) {
   if (p->nb <= 0 || p->nr <= 0 || p->N <= 0 || p->M <= 0) return 0;
-  if (p->dtype != NBASR_F32 && !nbasr_env_flag(NBASR_ENV_FORCE_SIMT)) return sm100_gemm_wgrad_pair(p, as_stream(stream));
+  NBASR_REQUIRE(p->dtype != NBASR_F16, "weight gradients take bf16 (or fp32) operands: dY is a gradient");
+  if (p->dtype == NBASR_BF16 && !nbasr_env_flag(NBASR_ENV_FORCE_SIMT)) return sm100_gemm_wgrad_pair(p, as_stream(stream));
   SimtGemmArgs a{};
   a.a = p->dy; a.a_dtype = p->dtype; a.a_ib = 0; a.a_ir = 1; a.a_kb = p->dy_bs; a.a_kr = p->dy_rs;
   a.nib = 1; a.nir = p->M;

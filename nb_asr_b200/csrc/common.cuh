@@ -1,6 +1,7 @@
 // Shared device helpers for libnbasr (sm_100a). See include/nbasr.h for the ABI.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -11,6 +12,22 @@
 #include "../../include/nbasr.h"
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
+
+// 16-bit pair conversions (round to nearest; fp16 saturates to +-65504 instead of overflowing to inf)
+__device__ __forceinline__ uint32_t f2_to_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t f2_to_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 f16x2_to_f2(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
 
 extern thread_local char g_nbasr_err[512];
 int nbasr_fail(const char* fmt, ...);
@@ -44,6 +61,22 @@ __device__ __forceinline__ void load8(const bf16* p, float* v) {
     v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
 }
+__device__ __forceinline__ void load8(const f16* p, float* v) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = f16x2_to_f2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(f16* p, const float* v) {
+  uint4 r;
+  uint32_t* h = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = f2_to_f16x2(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
 __device__ __forceinline__ void store8(float* p, const float* v) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -57,33 +90,47 @@ __device__ __forceinline__ void store8(bf16* p, const float* v) {
 }
 __device__ __forceinline__ void load8_dt(const void* base, int dtype, int64_t idx, float* v) {
   if (dtype == NBASR_BF16) load8(reinterpret_cast<const bf16*>(base) + idx, v);
+  else if (dtype == NBASR_F16) load8(reinterpret_cast<const f16*>(base) + idx, v);
   else load8(reinterpret_cast<const float*>(base) + idx, v);
 }
 __device__ __forceinline__ void store8_dt(void* base, int dtype, int64_t idx, const float* v) {
   if (dtype == NBASR_BF16) store8(reinterpret_cast<bf16*>(base) + idx, v);
+  else if (dtype == NBASR_F16) store8(reinterpret_cast<f16*>(base) + idx, v);
   else store8(reinterpret_cast<float*>(base) + idx, v);
+}
+// 8 values -> 16 bytes of a 16-bit tensor (dtype BF16 or F16) at a shared / global address
+__device__ __forceinline__ void store8_h(void* p, int dtype, const float* v) {
+  if (dtype == NBASR_F16) store8(reinterpret_cast<f16*>(p), v);
+  else store8(reinterpret_cast<bf16*>(p), v);
+}
+__device__ __forceinline__ float ld1_dt(const void* base, int dtype, int64_t idx) {
+  return dtype == NBASR_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(base)[idx])
+       : dtype == NBASR_F16  ? __half2float(reinterpret_cast<const f16*>(base)[idx])
+                             : reinterpret_cast<const float*>(base)[idx];
+}
+__device__ __forceinline__ void st1_dt(void* base, int dtype, int64_t idx, float v) {
+  if (dtype == NBASR_BF16) reinterpret_cast<bf16*>(base)[idx] = __float2bfloat16(v);
+  else if (dtype == NBASR_F16) reinterpret_cast<f16*>(base)[idx] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  else reinterpret_cast<float*>(base)[idx] = v;
 }
 // tail-safe variants: nrem = number of valid elements in this group of 8 (may be < 8)
 __device__ __forceinline__ void load8_dt_n(const void* base, int dtype, int64_t idx, float* v, int nrem) {
   if (nrem >= 8) { load8_dt(base, dtype, idx, v); return; }
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    v[i] = (i < nrem) ? (dtype == NBASR_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(base)[idx + i])
-                                             : reinterpret_cast<const float*>(base)[idx + i]) : 0.f;
+  for (int i = 0; i < 8; ++i) v[i] = (i < nrem) ? ld1_dt(base, dtype, idx + i) : 0.f;
 }
 __device__ __forceinline__ void store8_dt_n(void* base, int dtype, int64_t idx, const float* v, int nrem) {
   if (nrem >= 8) { store8_dt(base, dtype, idx, v); return; }
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-    if (i < nrem) {
-      if (dtype == NBASR_BF16) reinterpret_cast<bf16*>(base)[idx + i] = __float2bfloat16(v[i]);
-      else reinterpret_cast<float*>(base)[idx + i] = v[i];
-    }
+    if (i < nrem) st1_dt(base, dtype, idx + i, v[i]);
 }
-__device__ __forceinline__ float ld_dt(const void* base, int dtype, int64_t idx) {
-  return dtype == NBASR_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(base)[idx])
-                             : reinterpret_cast<const float*>(base)[idx];
-}
+__device__ __forceinline__ float ld_dt(const void* base, int dtype, int64_t idx) { return ld1_dt(base, dtype, idx); }
+
+// epilogue scale fields: 0 means "unset" (see nbasr.h)
+__device__ __forceinline__ float epi_acc_scale(const nbasr_epilogue& e) { return e.acc_scale != 0.f ? e.acc_scale : 1.f; }
+__device__ __forceinline__ float epi_bias_scale(const nbasr_epilogue& e) { return e.bias_scale != 0.f ? e.bias_scale : 1.f; }
+__device__ __forceinline__ float epi_relu_hi(const nbasr_epilogue& e) { return e.relu_hi != 0.f ? e.relu_hi : 20.f; }
 
 // plane-major gate-bit masks (see nbasr.h): byte address of (row, column group starting at col, col % 8 == 0)
 __device__ __forceinline__ int64_t mask_byte_addr(int64_t rho, int col, int w, int64_t rows) {
@@ -113,20 +160,29 @@ __device__ __forceinline__ void epilogue_compute(const nbasr_epilogue& e, int64_
   const int nvalid = FULL ? NV : nvalid_;   // FULL: every column valid -> all guards fold at compile time
 #pragma unroll
   for (int g = 0; g < NG; ++g) m[g] = 0xffu;
-  if (!NOBIAS && e.bias) {
+  if (!NOBIAS) {      // (NOBIAS: the caller has already applied acc_scale and the bias)
+    const float as = epi_acc_scale(e);
+    if (as != 1.f) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (i < nvalid) v[i] += __ldg(e.bias + c0 + i);
+      for (int i = 0; i < NV; ++i) v[i] *= as;
+    }
+    if (e.bias) {
+      const float bs = epi_bias_scale(e);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (i < nvalid) v[i] = fmaf(__ldg(e.bias + c0 + i), bs, v[i]);
+    }
   }
   if (e.relu20) {
+    const float hi = epi_relu_hi(e);
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       uint32_t mm = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float z = v[g * 8 + i];
-        if (z > 0.f && z <= 20.f) mm |= (1u << i);
-        v[g * 8 + i] = fminf(fmaxf(z, 0.f), 20.f);
+        if (z > 0.f && z <= hi) mm |= (1u << i);
+        v[g * 8 + i] = fminf(fmaxf(z, 0.f), hi);
       }
       m[g] = mm;
     }

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
 }
 
 template <typename T>
-__global__ void transpose_in_kernel(const float* __restrict__ a, T* __restrict__ out, int B, int F, int Tt, int Tp) {
+__global__ void transpose_in_kernel(const float* __restrict__ a, T* __restrict__ out, int B, int F, int Tt, int Tp, float scale) {
   __shared__ float tile[32][33];
   int b = blockIdx.z;
   int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
@@ -232,7 +232,7 @@ __global__ void transpose_in_kernel(const float* __restrict__ a, T* __restrict__
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int t = t0 + i, f = f0 + threadIdx.x;
-    if (t < Tt && f < F) out[((int64_t)b * Tp + NBASR_PAD_L + t) * F + f] = static_cast<T>(tile[threadIdx.x][i]);
+    if (t < Tt && f < F) out[((int64_t)b * Tp + NBASR_PAD_L + t) * F + f] = static_cast<T>(tile[threadIdx.x][i] * scale);
   }
 }
 
@@ -264,13 +264,16 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, int64_t n) {
 extern "C" {
 
 int nbasr_layernorm_fwd(int dtype, const void* x, void* y, int B, int T, int Tp, int C, const float* gamma,
-                        const float* beta, float eps, float* mean, float* rstd, void* stream) {
+                        const float* beta, float eps, float* mean, float* rstd, float out_scale, void* y2, void* stream) {
   NBASR_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_MAXG, "C");
   int64_t rows = (int64_t)B * T;
   int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 8);
   if (blocks < 1) return 0;
-  if (dtype == NBASR_BF16 && rows * (int64_t)C < (int64_t)1 << 40 && (int64_t)B * Tp < (int64_t)1 << 30)
-    return ln2_fwd(x, y, B, T, Tp, C, gamma, beta, eps, mean, rstd, as_stream(stream));   // packed-fp32x2 kernels (layernorm2.cu)
+  if (out_scale == 0.f) out_scale = 1.f;
+  const bool small = rows * (int64_t)C < (int64_t)1 << 40 && (int64_t)B * Tp < (int64_t)1 << 30;
+  if (dtype != NBASR_F32 && small)      // packed-fp32x2 kernels (layernorm2.cu)
+    return ln2_fwd(x, y, dtype == NBASR_F16, B, T, Tp, C, gamma, beta, eps, mean, rstd, out_scale, y2, as_stream(stream));
+  NBASR_REQUIRE(dtype != NBASR_F16 && out_scale == 1.f && !y2, "generic LayerNorm kernel: fp32 / bf16, unscaled, single output");
   if (dtype == NBASR_BF16)
     layernorm_fwd_kernel<bf16><<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)x, (bf16*)y, B, T, Tp, C, gamma, beta, eps, mean, rstd);
   else
@@ -279,13 +282,14 @@ int nbasr_layernorm_fwd(int dtype, const void* x, void* y, int B, int T, int Tp,
   return 0;
 }
 
-int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* mean, const float* rstd,
+int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, int x_dtype, float x_scale, const float* mean, const float* rstd,
                         const float* gamma, int B, int T, int Tp, int C, void* dx, void* dx2, const uint32_t* mask2,
                         float scale2, int64_t mask_rows, int mask2_w, float* dgamma, float* dbeta, void* stream) {
   NBASR_REQUIRE(C % 8 == 0 && C <= 8 * 32 * LN_MAXG, "C");
   int64_t rows = (int64_t)B * T;
   int blocks = (int)std::min<int64_t>((rows + 7) / 8, 148 * 2);
   if (blocks < 1) return 0;
+  if (x_scale == 0.f) x_scale = 1.f;
   size_t sm = (size_t)8 * 2 * 8 * 32 * LN_MAXG * sizeof(float);   // 80 KB
   static DevOnce attr;
   if (!attr) {
@@ -293,8 +297,11 @@ int nbasr_layernorm_bwd(int dtype, const void* dy, const void* x, const float* m
     cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr = true;
   }
-  if (dtype == NBASR_BF16 && (int64_t)B * Tp < (int64_t)1 << 30 && mask_rows * 8 * ((C + 31) / 32 + 1) < (int64_t)1 << 31)
-    return ln2_bwd(dy, x, mean, rstd, gamma, B, T, Tp, C, dx, dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta, as_stream(stream));
+  const bool small = (int64_t)B * Tp < (int64_t)1 << 30 && mask_rows * 8 * ((C + 31) / 32 + 1) < (int64_t)1 << 31;
+  if (dtype == NBASR_BF16 && x_dtype != NBASR_F32 && small)
+    return ln2_bwd(dy, x, x_dtype == NBASR_F16, x_scale, mean, rstd, gamma, B, T, Tp, C, dx, dx2, mask2, scale2, mask_rows, mask2_w, dgamma,
+                   dbeta, as_stream(stream));
+  NBASR_REQUIRE(x_dtype == dtype && x_scale == 1.f && dtype != NBASR_F16, "generic LayerNorm backward: one unscaled dtype (fp32 / bf16)");
   if (dtype == NBASR_BF16)
     layernorm_bwd_kernel<bf16><<<blocks, 256, sm, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, B, T, Tp, C, (bf16*)dx, (bf16*)dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta);
   else
@@ -324,10 +331,12 @@ int nbasr_colsum(int dtype, const void* x, int B, int T, int Tp, int C, float* o
   return 0;
 }
 
-int nbasr_transpose_in(const float* audio, void* out, int dtype, int B, int F, int T, int Tp, void* stream) {
+int nbasr_transpose_in(const float* audio, void* out, int dtype, int B, int F, int T, int Tp, float scale, void* stream) {
   dim3 grid((T + 31) / 32, (F + 31) / 32, B), block(32, 8);
-  if (dtype == NBASR_BF16) transpose_in_kernel<bf16><<<grid, block, 0, as_stream(stream)>>>(audio, (bf16*)out, B, F, T, Tp);
-  else transpose_in_kernel<float><<<grid, block, 0, as_stream(stream)>>>(audio, (float*)out, B, F, T, Tp);
+  if (scale == 0.f) scale = 1.f;
+  if (dtype == NBASR_BF16) transpose_in_kernel<bf16><<<grid, block, 0, as_stream(stream)>>>(audio, (bf16*)out, B, F, T, Tp, scale);
+  else if (dtype == NBASR_F16) transpose_in_kernel<f16><<<grid, block, 0, as_stream(stream)>>>(audio, (f16*)out, B, F, T, Tp, scale);
+  else transpose_in_kernel<float><<<grid, block, 0, as_stream(stream)>>>(audio, (float*)out, B, F, T, Tp, scale);
   NBASR_CHECK_LAUNCH();
   return 0;
 }
@@ -338,6 +347,8 @@ int nbasr_pack_weight(const float* w, void* out, int out_dtype, int M, int N, in
   unsigned blocks = (unsigned)((total + 255) / 256);
   if (out_dtype == NBASR_BF16)
     pack_weight_kernel<bf16><<<blocks, 256, 0, as_stream(stream)>>>(w, (bf16*)out, M, N, nq, t0, tstep, ws_m, ws_n, ws_t);
+  else if (out_dtype == NBASR_F16)
+    pack_weight_kernel<f16><<<blocks, 256, 0, as_stream(stream)>>>(w, (f16*)out, M, N, nq, t0, tstep, ws_m, ws_n, ws_t);
   else
     pack_weight_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(w, (float*)out, M, N, nq, t0, tstep, ws_m, ws_n, ws_t);
   NBASR_CHECK_LAUNCH();
@@ -347,6 +358,7 @@ int nbasr_pack_weight(const float* w, void* out, int out_dtype, int M, int N, in
 int nbasr_convert(const float* src, void* dst, int dst_dtype, int64_t n, void* stream) {
   unsigned blocks = (unsigned)((n + 255) / 256);
   if (dst_dtype == NBASR_BF16) convert_kernel<bf16><<<blocks, 256, 0, as_stream(stream)>>>(src, (bf16*)dst, n);
+  else if (dst_dtype == NBASR_F16) convert_kernel<f16><<<blocks, 256, 0, as_stream(stream)>>>(src, (f16*)dst, n);
   else convert_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(src, (float*)dst, n);
   NBASR_CHECK_LAUNCH();
   return 0;

@@ -225,7 +225,7 @@ int nbasr_gconv_fwd(const nbasr_gconv* p, void* stream) {
   NBASR_REQUIRE(p->C % p->cpg == 0 && p->C % 8 == 0, "channels");
   if (p->B <= 0 || p->T <= 0) return 0;
   if (p->w_packed & 1) {
-    NBASR_REQUIRE(p->dtype == NBASR_BF16, "packed grouped-conv weights need bf16 activations");
+    NBASR_REQUIRE(p->dtype != NBASR_F32, "packed grouped-conv weights need 16-bit activations");
     return sm100_gconv_fwd(p, as_stream(stream));
   }
   NBASR_REQUIRE(p->ktaps <= 7 && (p->dstep == 1 || p->dstep == 2), "taps");

@@ -62,7 +62,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 struct GcFwdArgs {
   int B, T, C, OUT, ktaps, dstep, off0;
-  int nslabs, ntiles, tiles_per_utt, nlanes, nstage, no_prefetch, w_stable;
+  int nslabs, ntiles, tiles_per_utt, nlanes, nstage, no_prefetch, w_stable, f16;
   nbasr_epilogue epi;
   int64_t Tp;
 };
@@ -126,7 +126,7 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // is ready, so their latency sits on the epilogue's critical path (1 skip operand: 55 -> 92 us per launch).  The whole
     // producer warp therefore L2-prefetches them for each tile at the moment that tile's input load is issued, i.e. NS tiles
     // ahead of their use (the register prefetch tried earlier spilled).
-    const int esz = p.epi.add_dtype == NBASR_BF16 ? 2 : 4;
+    const int esz = p.epi.add_dtype == NBASR_F32 ? 4 : 2;
     const bool pf_mask = p.epi.out2 && p.epi.mask2;
     const int pl2 = pf_mask ? c0 / p.epi.mask2_w : 0;
     const int eb2 = p.epi.mask2_w == 32 ? 4 : 8;
@@ -168,7 +168,7 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, NW, 0, 0);
+      const uint32_t idesc = make_idesc(128, NW, 0, 0, p.f16);
       mbar_wait(wbar, 0);
       int stage = 0, it = 0;
       uint32_t phase = 0;
@@ -201,10 +201,13 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int cbeg = c0 + 24 * hh;
     const int nvalid = max(0, min(24, min(p.C, c0 + p.OUT) - cbeg));     // multiple of 8
     const int OUTB = p.OUT * 2;              // staged row pitch in bytes
+    const nbasr_epilogue& epi = p.epi;       // stays in the kernel-parameter bank (a local copy would live on the stack)
+    // scaled fp16 activations (nbasr.h): v = acc * acc_scale + bias * bias_scale, clamp at relu_hi
+    const float acc_s = epi_acc_scale(epi), bias_s = epi_bias_scale(epi), relu_hi = epi_relu_hi(epi);
+    const uint32_t hi_bits = __float_as_uint(relu_hi);
     float bias_r[24];
 #pragma unroll
-    for (int i = 0; i < 24; ++i) bias_r[i] = (p.epi.bias && i < nvalid) ? __ldg(p.epi.bias + cbeg + i) : 0.f;
-    const nbasr_epilogue& epi = p.epi;       // stays in the kernel-parameter bank (a local copy would live on the stack)
+    for (int i = 0; i < 24; ++i) bias_r[i] = (epi.bias && i < nvalid) ? __ldg(epi.bias + cbeg + i) * bias_s : 0.f;
     int it = 0;
     for (int tile = lane_id; tile < p.ntiles; tile += p.nlanes, ++it) {
       const int as = it % NACC;
@@ -242,20 +245,20 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
               mm = 0;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float z = v[g * 8 + i] + bias_r[g * 8 + i];
-                // 0 < z <= 20  <=>  bits(z) - 1 < bits(20.0f) as unsigned (negative z and +0 wrap to huge values)
-                mm |= ((__float_as_uint(z) - 1u) < 0x41A00000u) ? (1u << i) : 0u;
-                v[g * 8 + i] = fminf(fmaxf(z, 0.f), 20.f);
+                const float z = fmaf(v[g * 8 + i], acc_s, bias_r[g * 8 + i]);
+                // 0 < z <= hi  <=>  bits(z) - 1 < bits(hi) as unsigned (negative z and +0 wrap to huge values)
+                mm |= ((__float_as_uint(z) - 1u) < hi_bits) ? (1u << i) : 0u;
+                v[g * 8 + i] = fminf(fmaxf(z, 0.f), relu_hi);
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[g * 8 + i] += bias_r[g * 8 + i];
+              for (int i = 0; i < 8; ++i) v[g * 8 + i] = fmaf(v[g * 8 + i], acc_s, bias_r[g * 8 + i]);
             }
             m[g] = mm;
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 24; ++i) v[i] += bias_r[i];
+          for (int i = 0; i < 24; ++i) v[i] = fmaf(v[i], acc_s, bias_r[i]);
           if (nvalid == 24) epilogue_compute<24, true, true>(epi, rho, cbeg, 24, v, m);
           else epilogue_compute<24, false, true>(epi, rho, cbeg, nvalid, v, m);
         }
@@ -270,13 +273,13 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
         if (g * 8 < nvalid) {
-          if (epi.out) store8(reinterpret_cast<bf16*>(orow + g * 16), v + g * 8);
+          if (epi.out) store8_h(orow + g * 16, epi.out_dtype, v + g * 8);
           if (epi.out2) {
             const uint32_t w = w2[g];
             float t2[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) t2[i] = ((w >> i) & 1u) ? v[g * 8 + i] * epi.scale2 : 0.f;
-            store8(reinterpret_cast<bf16*>(orow + OSTAGE_BYTES + g * 16), t2);
+            store8_h(orow + OSTAGE_BYTES + g * 16, epi.out2_dtype, t2);
           }
         }
         if (epi.mask_out) mst[row * 8 + 3 * hh + g] = (g * 8 < nvalid) ? (uint8_t)m[g] : (uint8_t)0;   // 8-byte entry per row
@@ -441,7 +444,8 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
 // ---------------------------------------------------------------- weight packs (fp32 master -> bf16 block diagonal)
 // out[slab][tap][n (48 rows)][kk (64 cols)], transposed=0: forward  (n = c_out, kk = c_in, tap j)
 //                                            transposed=1: dgrad    (n = c_in, kk = c_out, tap k-1-j)
-__global__ void pack_gconv_mma_kernel(const float* __restrict__ w, bf16* __restrict__ out, int C, int cpg, int ktaps, int OUT,
+template <typename T>
+__global__ void pack_gconv_mma_kernel(const float* __restrict__ w, T* __restrict__ out, int C, int cpg, int ktaps, int OUT,
                                       int nslabs, int transposed) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)nslabs * ktaps * NW * 64;
@@ -457,7 +461,7 @@ __global__ void pack_gconv_mma_kernel(const float* __restrict__ w, bf16* __restr
     if (!transposed) v = w[((int64_t)cn * cpg + (ck % cpg)) * ktaps + j];
     else v = w[((int64_t)ck * cpg + (cn % cpg)) * ktaps + (ktaps - 1 - j)];
   }
-  out[idx] = __float2bfloat16(v);
+  out[idx] = static_cast<T>(v);
 }
 
 }  // namespace
@@ -470,8 +474,10 @@ int sm100_gconv_fwd(const nbasr_gconv* g, cudaStream_t st) {
   a.ktaps = g->ktaps; a.dstep = g->dstep; a.off0 = g->off0;
   NBASR_REQUIRE(a.off0 >= -NBASR_PAD_L && (a.ktaps - 1) * a.dstep <= AROWS - GT, "tap reach");
   NBASR_REQUIRE(g->epi.ld_out == g->C, "grouped conv writes dense (B,Tp,C) tensors");
-  NBASR_REQUIRE((!g->epi.out || g->epi.out_dtype == NBASR_BF16) && (!g->epi.out2 || g->epi.out2_dtype == NBASR_BF16) &&
-                    !g->epi.accumulate, "tcgen05 grouped conv stores bf16");
+  NBASR_REQUIRE((!g->epi.out || g->epi.out_dtype != NBASR_F32) && (!g->epi.out2 || g->epi.out2_dtype != NBASR_F32) &&
+                    !g->epi.accumulate, "tcgen05 grouped conv stores 16-bit tensors");
+  NBASR_REQUIRE(g->epi.n_add == 0 || g->epi.add_dtype != NBASR_F32, "tcgen05 grouped conv adds 16-bit skip tensors");
+  a.f16 = g->dtype == NBASR_F16 ? 1 : 0;
   a.nslabs = (g->C + a.OUT - 1) / a.OUT;
   a.tiles_per_utt = (g->T + GT - 1) / GT;
   a.ntiles = a.tiles_per_utt * g->B;
@@ -538,12 +544,14 @@ int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C
   return 0;
 }
 
-extern "C" int nbasr_pack_gconv_mma(const float* w, void* out, int C, int cpg, int ktaps, int transposed, void* stream) {
+extern "C" int nbasr_pack_gconv_mma(const float* w, void* out, int out_dtype, int C, int cpg, int ktaps, int transposed, void* stream) {
   int OUT = slab_out(cpg);
   int nslabs = (C + OUT - 1) / OUT;
   int64_t total = (int64_t)nslabs * ktaps * NW * 64;
-  pack_gconv_mma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(w, (bf16*)out, C, cpg, ktaps, OUT, nslabs,
-                                                                                        transposed);
+  NBASR_REQUIRE(out_dtype == NBASR_BF16 || out_dtype == NBASR_F16, "16-bit pack");
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (out_dtype == NBASR_F16) pack_gconv_mma_kernel<f16><<<grid, 256, 0, as_stream(stream)>>>(w, (f16*)out, C, cpg, ktaps, OUT, nslabs, transposed);
+  else pack_gconv_mma_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(w, (bf16*)out, C, cpg, ktaps, OUT, nslabs, transposed);
   NBASR_CHECK_LAUNCH();
   return 0;
 }

@@ -36,7 +36,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barrier
 constexpr int THREADS = 320;
 
 struct Args {
-  int nb, nr, K, N, BN;
+  int nb, nr, K, N, BN, f16;
   int mt_per_utt, m_tiles, n_tiles, pair_tiles;
   int64_t o_r0, o_bs, o_rs;
   nbasr_epilogue epi;
@@ -167,7 +167,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = make_idesc(2 * BM, p.BN, 0, 0);
+      const uint32_t idesc = make_idesc(2 * BM, p.BN, 0, 0, p.f16);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -392,6 +392,7 @@ int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
   NBASR_REQUIRE(g->K % 8 == 0, "K must keep 16-byte row alignment");
   Args a{};
   a.nb = g->nb; a.nr = g->nr; a.K = g->K; a.N = g->N;
+  a.f16 = g->dtype == NBASR_F16 ? 1 : 0;
   a.mt_per_utt = (g->nr + BM - 1) / BM;
   a.m_tiles = a.mt_per_utt * g->nb;
   const int sms = nbasr_sm_count();

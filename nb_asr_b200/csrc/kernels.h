@@ -84,8 +84,9 @@ int sm100_lstm_fwd(const float* gx, const void* w_packed, int T, int B, int H, v
 int sm100_lstm_bwd(const float* dh_seq, int64_t dh_bs, int64_t dh_rs, const void* w_packed, const float* gates, const float* cstate,
                    int T, int B, int H, float* dgx, void* dgx_bf16, cudaStream_t st);
 
-// packed-fp32x2 bf16 LayerNorm (layernorm2.cu)
-int ln2_fwd(const void* x, void* y, int B, int T, int Tp, int C, const float* gamma, const float* beta, float eps, float* mean,
-            float* rstd, cudaStream_t st);
-int ln2_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, int B, int T, int Tp, int C, void* dx,
-            void* dx2, const uint32_t* mask2, float scale2, int64_t mask_rows, int mask2_w, float* dgamma, float* dbeta, cudaStream_t st);
+// packed-fp32x2 16-bit LayerNorm (layernorm2.cu); f16 / x_f16: the forward activations are scaled fp16 (see nbasr.h)
+int ln2_fwd(const void* x, void* y, int f16, int B, int T, int Tp, int C, const float* gamma, const float* beta, float eps, float* mean,
+            float* rstd, float out_scale, void* y2, cudaStream_t st);
+int ln2_bwd(const void* dy, const void* x, int x_f16, float x_scale, const float* mean, const float* rstd, const float* gamma, int B, int T,
+            int Tp, int C, void* dx, void* dx2, const uint32_t* mask2, float scale2, int64_t mask_rows, int mask2_w, float* dgamma,
+            float* dbeta, cudaStream_t st);

@@ -47,9 +47,22 @@ __device__ __forceinline__ u64 bf2_to_f2(uint32_t w) { return pk2(__uint_as_floa
 __device__ __forceinline__ uint32_t f2_to_bf2(u64 v) {
   float lo, hi;
   upk2(v, lo, hi);
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
+  return f2_to_bf16x2(lo, hi);
+}
+// 16-bit pair of either format (F16 = the scaled fp16 forward activations of the 16-bit mode) <-> fp32 pair
+template <bool F16>
+__device__ __forceinline__ u64 h2_to_f2(uint32_t w) {
+  if (F16) {
+    const float2 f = f16x2_to_f2(w);
+    return pk2(f.x, f.y);
+  }
+  return bf2_to_f2(w);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t f2_to_h2(u64 v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return F16 ? f2_to_f16x2(lo, hi) : f2_to_bf16x2(lo, hi);
 }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 r;
@@ -75,10 +88,12 @@ struct RowCur {
 
 constexpr int LN2_D = 4;   // forward: rows in flight per warp
 
-template <int QN>
+// F16: x and y are fp16 (y multiplied by out_scale, folded into gamma / beta); y2 (optional) = the unscaled result as bf16.
+template <int QN, bool F16>
 __global__ void __launch_bounds__(512, 1)
 ln2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int Tt, int Tp, int C, const float* __restrict__ gamma,
-               const float* __restrict__ beta, float eps, float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+               const float* __restrict__ beta, float eps, float* __restrict__ mean_o, float* __restrict__ rstd_o, float out_scale,
+               bf16* __restrict__ y2) {
   extern __shared__ __align__(16) uint8_t lnsm[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gw = blockIdx.x * 16 + wib, nW = gridDim.x * 16;
@@ -91,8 +106,10 @@ ln2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int Tt, 
   const bool tail_ok = lane + 32 * (QN - 1) < ngroups;  // only the last slice of a row can be partial
   pdl_launch_dependents();
   pdl_wait();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { gs[i] = gamma[i]; gs[C + i] = beta[i]; }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { gs[i] = gamma[i] * out_scale; gs[C + i] = beta[i] * out_scale; }
   __syncthreads();
+  const float inv_os = 1.f / out_scale;            // out_scale is a power of two: y2 = y / out_scale is exact
+  const u64 inv_os2 = pk2(inv_os, inv_os);
   const int dq = nW / Tt, dr = nW - dq * Tt;
   auto adv = [&](RowCur& c) {
     c.r += nW; c.b += dq; c.t += dr;
@@ -124,7 +141,7 @@ ln2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int Tt, 
     for (int q = 0; q < QN; ++q) {
       if (q < QN - 1 || tail_ok) {
         const uint4 w = lds128(xb + q * 512);
-        v[q][0] = bf2_to_f2(w.x); v[q][1] = bf2_to_f2(w.y); v[q][2] = bf2_to_f2(w.z); v[q][3] = bf2_to_f2(w.w);
+        v[q][0] = h2_to_f2<F16>(w.x); v[q][1] = h2_to_f2<F16>(w.y); v[q][2] = h2_to_f2<F16>(w.z); v[q][3] = h2_to_f2<F16>(w.w);
         sa = add2(sa, add2(v[q][0], v[q][1]));
         sb = add2(sb, add2(v[q][2], v[q][3]));
       } else {
@@ -156,10 +173,13 @@ ln2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int Tt, 
         u64 ga[4], be[4];
         lds8p(gsa + (lane * 8 + q * 256) * 4, ga);
         lds8p(gsa + (C + lane * 8 + q * 256) * 4, be);
-        uint32_t o[4];
+        u64 r[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = f2_to_bf2(fma2(fma2(v[q][i], rstd2, nm2), ga[i], be[i]));
-        stg128(dst + q * 256, o[0], o[1], o[2], o[3]);
+        for (int i = 0; i < 4; ++i) r[i] = fma2(fma2(v[q][i], rstd2, nm2), ga[i], be[i]);
+        stg128(dst + q * 256, f2_to_h2<F16>(r[0]), f2_to_h2<F16>(r[1]), f2_to_h2<F16>(r[2]), f2_to_h2<F16>(r[3]));
+        if (y2)
+          stg128(y2 + (size_t)rho * C + lane * 8 + q * 256, f2_to_bf2(mul2(r[0], inv_os2)), f2_to_bf2(mul2(r[1], inv_os2)),
+                 f2_to_bf2(mul2(r[2], inv_os2)), f2_to_bf2(mul2(r[3], inv_os2)));
       }
     }
     issue(ci, buf);       // refill the slot this lane has just finished reading
@@ -174,12 +194,14 @@ ln2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int Tt, 
 // The dgamma / dbeta partial sums are 16 QN registers per lane.  For QN >= 4 that spills (measured: slower than the first
 // generation), so there the dbeta sums live in a private, conflict-free shared-memory slot per lane (DBS) and QN = 5 runs 12
 // warps per CTA instead of 16.
-template <int QN, int NWARP, bool DBS>
+// XF16: x is the scaled fp16 activation x_scale * x_true (mean / rstd are those of the stored tensor, so xhat is exact);
+// the gradient wrt x_true is x_scale times the gradient wrt the stored tensor.  dy / dx / dx2 are bf16.
+template <int QN, int NWARP, bool DBS, bool XF16>
 __global__ void __launch_bounds__(NWARP * 32, 1)
 ln2_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_i, const float* __restrict__ rstd_i,
                const float* __restrict__ gamma, int B, int Tt, int Tp, int C, bf16* __restrict__ dx, bf16* __restrict__ dx2,
                const uint32_t* __restrict__ mask2, float scale2, int64_t mask_rows, int mask2_w, float* __restrict__ dgamma,
-               float* __restrict__ dbeta) {
+               float* __restrict__ dbeta, float x_scale) {
   extern __shared__ __align__(16) uint8_t lnsm[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gw = blockIdx.x * NWARP + wib, nW = gridDim.x * NWARP;
@@ -278,7 +300,7 @@ ln2_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const fl
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const u64 dv = bf2_to_f2(ds[i]);
-          const u64 xh = fma2(bf2_to_f2(xs[i]), rstd2, nm2);
+          const u64 xh = fma2(h2_to_f2<XF16>(xs[i]), rstd2, nm2);
           const u64 gy = mul2(dv, ga[i]);
           s1 = add2(s1, gy);
           s2 = fma2(gy, xh, s2);
@@ -294,9 +316,10 @@ ln2_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const fl
     }
     const float m1 = warp_sum(hsum2(s1)) * invC;
     const float m2 = warp_sum(hsum2(s2)) * invC;
-    // dx = rstd (gy - m1 - xh m2) = gy rstd + x k1 + k0   (xh = x rstd + nm)
-    const float k1 = -rstd * rstd * m2, k0 = -rstd * (m1 + nm * m2);
-    const u64 k1p = pk2(k1, k1), k0p = pk2(k0, k0);
+    // dx = rstd_t (gy - m1 - xh m2) = gy rstd_t + x k1 + k0   (xh = x rstd + nm; rstd_t = x_scale rstd: true-domain rstd)
+    const float rstd_t = rstd * x_scale;
+    const float k1 = -rstd_t * rstd * m2, k0 = -rstd_t * (m1 + nm * m2);
+    const u64 k1p = pk2(k1, k1), k0p = pk2(k0, k0), rstd_t2 = pk2(rstd_t, rstd_t);
     const size_t eo = (size_t)rho * C + lane * 8;
 #pragma unroll
     for (int q = 0; q < QN; ++q) {
@@ -307,7 +330,7 @@ ln2_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const fl
         const uint32_t xs[4] = {xw.x, xw.y, xw.z, xw.w}, ds[4] = {dw.x, dw.y, dw.z, dw.w};
         u64 o[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = fma2(bf2_to_f2(xs[i]), k1p, fma2(mul2(bf2_to_f2(ds[i]), ga[i]), rstd2, k0p));
+        for (int i = 0; i < 4; ++i) o[i] = fma2(h2_to_f2<XF16>(xs[i]), k1p, fma2(mul2(bf2_to_f2(ds[i]), ga[i]), rstd_t2, k0p));
         if (dx) stg128(dx + eo + q * 256, f2_to_bf2(o[0]), f2_to_bf2(o[1]), f2_to_bf2(o[2]), f2_to_bf2(o[3]));
         if (dx2) {
           const uint32_t w = mw[q];
@@ -353,27 +376,28 @@ ln2_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const fl
   }
 }
 
-template <int QN>
+template <int QN, bool F16>
 int ln2_fwd_launch(const bf16* x, bf16* y, int B, int T, int Tp, int C, const float* gamma, const float* beta, float eps, float* mean,
-                   float* rstd, cudaStream_t st) {
+                   float* rstd, float out_scale, bf16* y2, cudaStream_t st) {
   const int64_t rows = (int64_t)B * T;
   const int grid = (int)std::min<int64_t>((rows + 15) / 16, nbasr_sm_count());
   const size_t smb = (size_t)C * 8 + (size_t)16 * LN2_D * C * 2;
   static DevOnce attr;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(ln2_fwd_kernel<QN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ln2_fwd_kernel<QN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return nbasr_fail("ln2_fwd smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  cudaError_t le = launch_pdl(ln2_fwd_kernel<QN>, dim3(grid), dim3(512), smb, st, 1, x, y, B, T, Tp, C, gamma, beta, eps, mean, rstd);
+  cudaError_t le = launch_pdl(ln2_fwd_kernel<QN, F16>, dim3(grid), dim3(512), smb, st, 1, x, y, B, T, Tp, C, gamma, beta, eps, mean, rstd,
+                              out_scale, y2);
   if (le != cudaSuccess) return nbasr_fail("ln2_fwd launch: %s", cudaGetErrorString(le));
   return 0;
 }
 
-template <int QN>
+template <int QN, bool XF16>
 int ln2_bwd_launch(const bf16* dy, const bf16* x, const float* mean, const float* rstd, const float* gamma, int B, int T, int Tp, int C,
                    bf16* dx, bf16* dx2, const uint32_t* mask2, float scale2, int64_t mask_rows, int mask2_w, float* dgamma, float* dbeta,
-                   cudaStream_t st) {
+                   float x_scale, cudaStream_t st) {
   constexpr int NWARP = QN <= 4 ? 16 : 12;
   constexpr bool DBS = QN >= 4;
   const int64_t rows = (int64_t)B * T;
@@ -383,12 +407,12 @@ int ln2_bwd_launch(const bf16* dy, const bf16* x, const float* mean, const float
   const size_t smb = (size_t)C * 4 + std::max(ring, (size_t)NWARP * 2 * QN * 256 * 4) + (DBS ? (size_t)NWARP * QN * 1024 : 0);
   static DevOnce attr;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(ln2_bwd_kernel<QN, NWARP, DBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ln2_bwd_kernel<QN, NWARP, DBS, XF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return nbasr_fail("ln2_bwd smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  cudaError_t le = launch_pdl(ln2_bwd_kernel<QN, NWARP, DBS>, dim3(grid), dim3(NWARP * 32), smb, st, 1, dy, x, mean, rstd, gamma, B, T, Tp, C, dx,
-                              dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta);
+  cudaError_t le = launch_pdl(ln2_bwd_kernel<QN, NWARP, DBS, XF16>, dim3(grid), dim3(NWARP * 32), smb, st, 1, dy, x, mean, rstd, gamma, B, T, Tp, C,
+                              dx, dx2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta, x_scale);
   if (le != cudaSuccess) return nbasr_fail("ln2_bwd launch: %s", cudaGetErrorString(le));
   return 0;
 }
@@ -396,30 +420,35 @@ int ln2_bwd_launch(const bf16* dy, const bf16* x, const float* mean, const float
 }  // namespace
 
 // rows = B*T must fit 32 bits and (B*Tp + pad) * C must fit size_t arithmetic from 32-bit row indices: checked by the callers
-int ln2_fwd(const void* x, void* y, int B, int T, int Tp, int C, const float* gamma, const float* beta, float eps, float* mean,
-            float* rstd, cudaStream_t st) {
+int ln2_fwd(const void* x, void* y, int f16, int B, int T, int Tp, int C, const float* gamma, const float* beta, float eps, float* mean,
+            float* rstd, float out_scale, void* y2, cudaStream_t st) {
   const bf16* xx = (const bf16*)x;
-  bf16* yy = (bf16*)y;
+  bf16 *yy = (bf16*)y, *y2b = (bf16*)y2;
+#define NBASR_LN2F(Q)                                                                                                       \
+  case Q:                                                                                                                   \
+    return f16 ? ln2_fwd_launch<Q, true>(xx, yy, B, T, Tp, C, gamma, beta, eps, mean, rstd, out_scale, y2b, st)             \
+               : ln2_fwd_launch<Q, false>(xx, yy, B, T, Tp, C, gamma, beta, eps, mean, rstd, out_scale, y2b, st);
   switch ((C / 8 + 31) / 32) {
-    case 1: return ln2_fwd_launch<1>(xx, yy, B, T, Tp, C, gamma, beta, eps, mean, rstd, st);
-    case 2: return ln2_fwd_launch<2>(xx, yy, B, T, Tp, C, gamma, beta, eps, mean, rstd, st);
-    case 3: return ln2_fwd_launch<3>(xx, yy, B, T, Tp, C, gamma, beta, eps, mean, rstd, st);
-    case 4: return ln2_fwd_launch<4>(xx, yy, B, T, Tp, C, gamma, beta, eps, mean, rstd, st);
-    case 5: return ln2_fwd_launch<5>(xx, yy, B, T, Tp, C, gamma, beta, eps, mean, rstd, st);
+    NBASR_LN2F(1) NBASR_LN2F(2) NBASR_LN2F(3) NBASR_LN2F(4) NBASR_LN2F(5)
   }
+#undef NBASR_LN2F
   return nbasr_fail("ln2_fwd: C = %d out of range", C);
 }
 
-int ln2_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, int B, int T, int Tp, int C, void* dx,
-            void* dx2, const uint32_t* mask2, float scale2, int64_t mask_rows, int mask2_w, float* dgamma, float* dbeta, cudaStream_t st) {
+int ln2_bwd(const void* dy, const void* x, int x_f16, float x_scale, const float* mean, const float* rstd, const float* gamma, int B, int T,
+            int Tp, int C, void* dx, void* dx2, const uint32_t* mask2, float scale2, int64_t mask_rows, int mask2_w, float* dgamma,
+            float* dbeta, cudaStream_t st) {
   const bf16 *a = (const bf16*)dy, *b = (const bf16*)x;
   bf16 *o = (bf16*)dx, *o2 = (bf16*)dx2;
+#define NBASR_LN2B(Q)                                                                                                                   \
+  case Q:                                                                                                                               \
+    return x_f16 ? ln2_bwd_launch<Q, true>(a, b, mean, rstd, gamma, B, T, Tp, C, o, o2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta, \
+                                           x_scale, st)                                                                                 \
+                 : ln2_bwd_launch<Q, false>(a, b, mean, rstd, gamma, B, T, Tp, C, o, o2, mask2, scale2, mask_rows, mask2_w, dgamma,       \
+                                            dbeta, x_scale, st);
   switch ((C / 8 + 31) / 32) {
-    case 1: return ln2_bwd_launch<1>(a, b, mean, rstd, gamma, B, T, Tp, C, o, o2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta, st);
-    case 2: return ln2_bwd_launch<2>(a, b, mean, rstd, gamma, B, T, Tp, C, o, o2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta, st);
-    case 3: return ln2_bwd_launch<3>(a, b, mean, rstd, gamma, B, T, Tp, C, o, o2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta, st);
-    case 4: return ln2_bwd_launch<4>(a, b, mean, rstd, gamma, B, T, Tp, C, o, o2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta, st);
-    case 5: return ln2_bwd_launch<5>(a, b, mean, rstd, gamma, B, T, Tp, C, o, o2, mask2, scale2, mask_rows, mask2_w, dgamma, dbeta, st);
+    NBASR_LN2B(1) NBASR_LN2B(2) NBASR_LN2B(3) NBASR_LN2B(4) NBASR_LN2B(5)
   }
+#undef NBASR_LN2B
   return nbasr_fail("ln2_bwd: C = %d out of range", C);
 }

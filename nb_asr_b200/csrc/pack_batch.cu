@@ -7,8 +7,8 @@ namespace {
 
 constexpr int PB_CHUNK = 4096;
 
-template <typename T>
-__device__ __forceinline__ void put(void* dst, int64_t i, float v) { reinterpret_cast<T*>(dst)[i] = static_cast<T>(v); }
+// store one value as out_dtype (F32 / BF16 / F16)
+__device__ __forceinline__ void put_dt(void* dst, int dtype, int64_t i, float v) { st1_dt(dst, dtype, i, v); }
 
 __global__ void __launch_bounds__(256) pack_batch_kernel(const nbasr_pack_job* __restrict__ jobs, int n,
                                                          const int2* __restrict__ blockmap) {
@@ -34,8 +34,7 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const nbasr_pack_job* _
     for (int r = r4; r < 64; r += 4) {          // r = n within the tile, c = m within the tile
       if (n0 + r < N && m0 + c < M) {
         const int64_t o = (int64_t)(n0 + r) * nq * M + (int64_t)q * M + m0 + c;
-        if (J.out_dtype == NBASR_BF16) put<bf16>(J.dst, o, tile[c][r]);
-        else put<float>(J.dst, o, tile[c][r]);
+        put_dt(J.dst, J.out_dtype, o, tile[c][r]);
       }
     }
     return;
@@ -47,7 +46,6 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const nbasr_pack_job* _
     const int OUT = cpg == 10 ? 40 : 48;
     const int64_t nsrc = (int64_t)Cc * cpg * ktaps;
     const int64_t s0 = blk * PB_CHUNK, s1 = min(nsrc, s0 + PB_CHUNK);
-    bf16* dst = reinterpret_cast<bf16*>(J.dst);
     for (int64_t idx = s0 + threadIdx.x; idx < s1; idx += blockDim.x) {
       const int jt = (int)(idx % ktaps);
       const int i = (int)((idx / ktaps) % cpg);
@@ -55,20 +53,19 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const nbasr_pack_job* _
       const int ci = (co / cpg) * cpg + i;
       const int sl = co / OUT;
       const int row = (tr ? ci : co) - sl * OUT, col = (tr ? co : ci) - sl * OUT, tap = tr ? ktaps - 1 - jt : jt;
-      dst[(((int64_t)sl * ktaps + tap) * 48 + row) * 64 + col] = __float2bfloat16(J.src[idx]);
+      put_dt(J.dst, J.out_dtype, (((int64_t)sl * ktaps + tap) * 48 + row) * 64 + col, J.src[idx]);
     }
     return;
   }
-  if (J.kind == 0 && J.out_dtype == NBASR_BF16 && (J.n_out & 3) == 0) {      // fp32 -> bf16 copy, 4 elements per thread
+  if (J.kind == 0 && J.out_dtype != NBASR_F32 && (J.n_out & 3) == 0) {      // fp32 -> 16-bit copy, 4 elements per thread
     const int64_t s0 = blk * (PB_CHUNK / 4), s1 = min(J.n_out >> 2, s0 + PB_CHUNK / 4);
     const float4* src = reinterpret_cast<const float4*>(J.src);
     uint2* dst = reinterpret_cast<uint2*>(J.dst);
     for (int64_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
       const float4 f = src[i];
-      __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
       uint2 o;
-      o.x = *reinterpret_cast<uint32_t*>(&lo);
-      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      if (J.out_dtype == NBASR_F16) { o.x = f2_to_f16x2(f.x, f.y); o.y = f2_to_f16x2(f.z, f.w); }
+      else { o.x = f2_to_bf16x2(f.x, f.y); o.y = f2_to_bf16x2(f.z, f.w); }
       dst[i] = o;
     }
     return;
@@ -92,8 +89,7 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const nbasr_pack_job* _
       int g = ci / cpg, i = ci % cpg;
       v = J.src[((int64_t)(g * cpg + o) * cpg + i) * ktaps + (ktaps - 1 - jt)];
     }
-    if (J.out_dtype == NBASR_BF16) put<bf16>(J.dst, idx, v);
-    else put<float>(J.dst, idx, v);
+    put_dt(J.dst, J.out_dtype, idx, v);
   }
 }
 

@@ -127,10 +127,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, bf16 inputs, fp32 accumulate
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, fp32 accumulate.  Operand format field (bits 7-9
+// for A, 10-12 for B): 1 = bf16, 0 = f16; both operands must share it (a mixed pair raises an illegal-instruction fault
+// on B200, tools/experiments/README.md), hence ONE flag.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int f16 = 0) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 

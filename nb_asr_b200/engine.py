@@ -13,16 +13,23 @@ Forward semantics follow ASRModel.forward (model.py:116-131), SearchCell/Node (m
 PadConvRelu/Linear (ops.py:7-50); backward is the hand-derived adjoint (there is no autograd
 inside the engine).
 """
+import collections
 import ctypes as C
+import functools
 import math
+import os
 
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, PAD_L, PAD_R, Epilogue, GConv, Gemm, Wgrad
+from ._lib import BF16, F16, F32, PAD_L, PAD_R, Epilogue, GConv, Gemm, Wgrad
 from .model import CELLS_PER_BLOCK, CONV_EDGES, FEATURES, FILTERS, HIDDEN, TR_STRIDES, PadConvRelu, pad_rule
 
 HP = 512  # padded LSTM hidden width of the h_seq buffer (TMA-friendly row pitch)
+# 16-bit mode: forward activations are fp16 holding ACT_SCALE * x (a power of two keeps the rescaling exact and small
+# activations out of the fp16 subnormal range; the largest representable true value is 65504 / 32 = 2047, far above
+# anything a ReLU20 / LayerNorm / skip-sum net produces).  Gradients stay bf16.  See include/nbasr.h and DESIGN.md 4.
+ACT_SCALE = 32.0
 
 
 def _ptr(t, off_elems=0):
@@ -44,13 +51,55 @@ class _Plan:
     pass
 
 
+class _Arena:
+    """Zero-initialised device memory for one plan, carved from a few large blocks (64 MiB, doubling up to 2 GiB): one
+    fill launch per block instead of one per buffer, and everything a plan owns is freed together when it is evicted."""
+
+    def __init__(self, dev):
+        self.dev, self.blocks, self.off, self.next = dev, [], 0, 64 << 20
+        self.bytes = 0
+
+    def raw(self, nbytes):
+        nbytes = max(256, (nbytes + 255) & ~255)
+        if not self.blocks or self.off + nbytes > self.blocks[-1].numel():
+            size = max(self.next, nbytes)
+            self.next = min(self.next * 2, 2 << 30)
+            self.blocks.append(torch.zeros(size, dtype=torch.uint8, device=self.dev))
+            self.off = 0
+            self.bytes += size
+        t = self.blocks[-1][self.off:self.off + nbytes]
+        self.off += nbytes
+        return t
+
+    def zeros(self, shape, dtype):
+        shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        n = 1
+        for x in shape:
+            n *= x
+        nb = n * dtype.itemsize
+        return self.raw(nb)[:nb].view(dtype).view(shape)
+
+
 class _Mask:
     """Plane-major gate-bit mask of a (rows, C) tensor: planes of w columns, one 4/8-byte entry per row and plane."""
 
-    def __init__(self, rows, C, w, dev):
+    def __init__(self, rows, C, w, arena):
         self.w = w
         eb = 4 if w == 32 else 8
-        self.t = torch.zeros(((C + w - 1) // w) * rows * eb, dtype=torch.uint8, device=dev)
+        self.t = arena.zeros(((C + w - 1) // w) * rows * eb, torch.uint8)
+
+
+def _on_device(fn):
+    """Run a method with the engine's GPU as the current device: libnbasr launches on torch's CURRENT stream, so a model on
+    cuda:k must not run in another device's context (Trainer(gpus=[k]) / get_model(gpu=k) without torch.cuda.set_device)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        dev = getattr(self, 'device', None) or self.params[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('nb_asr_b200 needs the model on a CUDA device (no CPU fallback)')
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 class Engine:
@@ -58,12 +107,18 @@ class Engine:
         assert precision in ('bf16', 'fp32')
         self.model = model
         self.precision = precision
+        # dt / tdt: gradients and the operands that multiply them; adt / tadt: forward activations and their weight operands
         self.dt = BF16 if precision == 'bf16' else F32
         self.tdt = torch.bfloat16 if precision == 'bf16' else torch.float32
+        self.adt = F16 if precision == 'bf16' else F32
+        self.tadt = torch.float16 if precision == 'bf16' else torch.float32
+        self.S = ACT_SCALE if precision == 'bf16' else 1.0
         self.lib = _lib.load()
         self.params = list(model.parameters())
         self.names = [n for n, _ in model.named_parameters()]
-        self.plans = {}
+        self.plans = collections.OrderedDict()      # (B, T, training) -> plan, least recently used first
+        self.max_plans = int(os.environ.get('NBASR_MAX_PLANS', '6'))
+        self.device = None
         self.flat_p = None
         self._pack_version = None
         self._bound_ptr = None
@@ -81,6 +136,12 @@ class Engine:
         dev = p0.device
         if dev.type != 'cuda':
             raise RuntimeError('nb_asr_b200 needs the model on a CUDA device (no CPU fallback)')
+        with torch.cuda.device(dev):
+            self._bind(dev)
+
+    def _bind(self, dev):
+        # a re-bind (model.to(other device), load_state_dict(assign=True), ...) keeps the optimiser state
+        old = (self.adam_m, self.adam_v, self.opt_state) if self.flat_p is not None else None
         self.device = dev
         offs, total = [], 0
         for p in self.params:
@@ -107,16 +168,22 @@ class Engine:
         self.n_flat = total
         self.adam_m = torch.zeros_like(flat_p)
         self.adam_v = torch.zeros_like(flat_p)
+        if old is not None and old[0].numel() == total:
+            self.adam_m.copy_(old[0])
+            self.adam_v.copy_(old[1])
         reg = [self.slices[n] for n in self.names if n.endswith('.conv.weight')]
         self.seg_off = torch.tensor([o for o, _ in reg], dtype=torch.int64, device=dev)
         self.seg_len = torch.tensor([l for _, l in reg], dtype=torch.int64, device=dev)
         self.opt_state = torch.zeros(8 + len(reg), dtype=torch.float32, device=dev)
+        if old is not None and old[2].numel() == self.opt_state.numel():
+            self.opt_state.copy_(old[2])
+        self._lr_host = None          # the device copy of lr is rewritten by the next set_lr()
         self.drop_step = torch.zeros(1, dtype=torch.int64, device=dev)
         self._bound_ptr = (self.params[0].data_ptr(), dev)
         self.seg_chunks = int(sum((l + 16383) // 16384 for _, l in reg))
         self._build_packs()
         self._compile_pack_jobs()
-        self.plans = {}
+        self.plans = collections.OrderedDict()
         self._pack_version = None
 
     def P(self, name):
@@ -131,7 +198,10 @@ class Engine:
     def _build_packs(self):
         """Describe every derived weight buffer; (re)filled by refresh_packs()."""
         m = self.model
-        dev, tdt = self.device, self.tdt
+        dev, tdt, tadt, adt = self.device, self.tdt, self.tadt, self.adt
+        # wf: FORWARD operands (multiply activations: activation format, fp16 in 16-bit mode);
+        # wd / wt: INPUT-GRADIENT operands (multiply gradients: bf16 in 16-bit mode)
+        parena = self.pack_arena = _Arena(dev)      # every derived operand lives in one zero-filled arena
         self.pack_ops = []     # (cfunc, args) without stream
         self.wf, self.wd, self.wt = {}, {}, {}
         lib = self.lib
@@ -144,8 +214,8 @@ class Engine:
             self.block_conv.append(name)
             n = cout * 8 * cin
             if self.dt == BF16:
-                buf = torch.empty(n, dtype=tdt, device=dev)
-                self.pack_ops.append((lib.nbasr_convert, (self.P(name + '.weight'), buf.data_ptr(), BF16, n)))
+                buf = parena.zeros(n, tadt)
+                self.pack_ops.append((lib.nbasr_convert, (self.P(name + '.weight'), buf.data_ptr(), adt, n)))
                 self.wf[name] = buf
             else:
                 self.wf[name] = None   # flat fp32 master is already (C_out, 8*C_in)
@@ -156,7 +226,7 @@ class Engine:
                     specs = [(4, 7, -2), (4, 6, -2)]
                 bufs = []
                 for nq, t0, ts in specs:
-                    b = torch.empty(cin * nq * cout, dtype=tdt, device=dev)
+                    b = parena.zeros(cin * nq * cout, tdt)
                     # out[n=ci][q*Cout + co] = w[co][t0+q*ts][ci]
                     self.pack_ops.append((lib.nbasr_pack_weight, (self.P(name + '.weight'), b.data_ptr(), self.dt, cout, cin,
                                                                    nq, t0, ts, 8 * cin, 1, cin)))
@@ -174,12 +244,12 @@ class Engine:
                     if op == 'linear':
                         n = cout * cout
                         if self.dt == BF16:
-                            b = torch.empty(n, dtype=tdt, device=dev)
-                            self.pack_ops.append((lib.nbasr_convert, (self.P(pn + '.linear.weight'), b.data_ptr(), BF16, n)))
+                            b = parena.zeros(n, tadt)
+                            self.pack_ops.append((lib.nbasr_convert, (self.P(pn + '.linear.weight'), b.data_ptr(), adt, n)))
                             self.wf[pn] = b
                         else:
                             self.wf[pn] = None
-                        bt = torch.empty(n, dtype=tdt, device=dev)
+                        bt = parena.zeros(n, tdt)
                         self.pack_ops.append((lib.nbasr_pack_weight, (self.P(pn + '.linear.weight'), bt.data_ptr(), self.dt,
                                                                        cout, cout, 1, 0, 0, cout, 1, 0)))
                         self.wt[pn] = bt
@@ -190,12 +260,12 @@ class Engine:
                             # block-diagonal bf16 operands of the tcgen05 grouped-conv kernel (forward / input-gradient)
                             ne = int(lib.nbasr_gconv_mma_pack_elems(cout, cpg, k))
                             # zeros: the batched refresh only rewrites the diagonal blocks (pack_batch.cu kind 2)
-                            bf_, bt = (torch.zeros(ne, dtype=tdt, device=dev) for _ in range(2))
-                            for buf, tr_ in ((bf_, 0), (bt, 1)):
-                                self.pack_ops.append((lib.nbasr_pack_gconv_mma, (self.P(pn + '.conv.weight'), buf.data_ptr(), cout, cpg, k, tr_)))
+                            bf_, bt = parena.zeros(ne, tadt), parena.zeros(ne, tdt)
+                            for buf, odt, tr_ in ((bf_, adt, 0), (bt, BF16, 1)):
+                                self.pack_ops.append((lib.nbasr_pack_gconv_mma, (self.P(pn + '.conv.weight'), buf.data_ptr(), odt, cout, cpg, k, tr_)))
                             self.wf[pn] = bf_
                         else:
-                            bt = torch.empty(cout * cpg * k, dtype=torch.float32, device=dev)
+                            bt = parena.zeros(cout * cpg * k, torch.float32)
                             self.pack_ops.append((lib.nbasr_pack_gconv_dgrad, (self.P(pn + '.conv.weight'), bt.data_ptr(), cout, cpg, k)))
                         self.wt[pn] = bt
                 idx += 1
@@ -206,20 +276,20 @@ class Engine:
             ln = self.lstm_name
             n = 4 * HIDDEN * FILTERS[-1]
             if self.dt == BF16:
-                b = torch.empty(n, dtype=tdt, device=dev)
-                self.pack_ops.append((lib.nbasr_convert, (self.P(ln + '.weight_ih_l0'), b.data_ptr(), BF16, n)))
+                b = parena.zeros(n, tadt)
+                self.pack_ops.append((lib.nbasr_convert, (self.P(ln + '.weight_ih_l0'), b.data_ptr(), adt, n)))
                 self.wf[ln] = b
             else:
                 self.wf[ln] = None
-            bt = torch.empty(n, dtype=tdt, device=dev)
+            bt = parena.zeros(n, tdt)
             self.pack_ops.append((lib.nbasr_pack_weight, (self.P(ln + '.weight_ih_l0'), bt.data_ptr(), self.dt, 4 * HIDDEN,
                                                            FILTERS[-1], 1, 0, 0, FILTERS[-1], 1, 0)))
             self.wt[ln] = bt
-            self.lstm_bias = torch.zeros(4 * HIDDEN, dtype=torch.float32, device=dev)
+            self.lstm_bias = parena.zeros(4 * HIDDEN, torch.float32)
             self.whh_packed = None
             if self.dt == BF16:
                 # W_hh operand of the tcgen05 cluster recurrence: [16 CTAs][gate*32 + unit][512] bf16
-                self.whh_packed = torch.zeros(16 * 128 * 512, dtype=tdt, device=dev)
+                self.whh_packed = parena.zeros(16 * 128 * 512, tdt)
                 self.pack_ops.append(('lstm_whh', (self.P(ln + '.weight_hh_l0'), self.whh_packed.data_ptr(), HIDDEN)))
             idx += 1
         self.head_name = f'model.{idx}'
@@ -247,8 +317,8 @@ class Engine:
                 j.a[0], j.a[1], j.a[2], j.a[3], j.a[4] = M, N, nq, t0, ts
                 j.s[0], j.s[1], j.s[2] = wm, wn, wt
             elif j.kind == 2:
-                src, dst, Cc, cpg, k, tr_ = a
-                j.src, j.dst, j.out_dtype = src, dst, BF16
+                src, dst, odt, Cc, cpg, k, tr_ = a
+                j.src, j.dst, j.out_dtype = src, dst, odt
                 j.n_out = int(lib.nbasr_gconv_mma_pack_elems(Cc, cpg, k))
                 j.a[0], j.a[1], j.a[2], j.a[3] = Cc, cpg, k, tr_
             else:
@@ -278,6 +348,7 @@ class Engine:
     def _param_version(self):
         return sum(p._version for p in self.params)
 
+    @_on_device
     def refresh_packs(self, force=False):
         v = self._param_version()
         if not force and v == self._pack_version:
@@ -294,9 +365,21 @@ class Engine:
 
     # ------------------------------------------------------------------ plan construction
     def _epi(self, ld, bias=0, relu=0, drop_p=0.0, salt=0, adds=(), out=0, out_dtype=None, mask_out=None, out2=0,
-             mask2=None, scale2=1.0, mask_rows=0, accumulate=0):
-        """mask_out / mask2 are _Mask objects (tensor + plane width) or None."""
+             mask2=None, scale2=1.0, mask_rows=0, accumulate=0, fwd=False, copy=0, acc_scale=1.0):
+        """mask_out / mask2 are _Mask objects (tensor + plane width) or None.
+        fwd=True: a FORWARD epilogue in the scaled activation domain (16-bit mode: fp16 tensors holding S*x): bias and the
+        ReLU20 bound are scaled by S, skip tensors and `out` are activation-format; copy = optional unscaled bf16 copy of
+        `out` for the weight gradient that will read this tensor (out2 slot, scale 1/S)."""
         e = Epilogue()
+        if fwd:
+            e.acc_scale, e.bias_scale, e.relu_hi = acc_scale, self.S, 20.0 * self.S
+            act = self.adt
+            if copy:
+                assert not out2
+                out2, scale2, mask2 = copy, 1.0 / self.S, None
+        else:
+            e.acc_scale, e.bias_scale, e.relu_hi = acc_scale, 1.0, 20.0
+            act = self.dt
         e.bias = bias or None
         e.relu20 = relu
         e.drop_p = drop_p
@@ -305,9 +388,9 @@ class Engine:
         e.n_add = len(adds)
         for i, a in enumerate(adds):
             e.add[i] = a
-        e.add_dtype = self.dt
+        e.add_dtype = act
         e.out = out or None
-        e.out_dtype = self.dt if out_dtype is None else out_dtype
+        e.out_dtype = act if out_dtype is None else out_dtype
         e.ld_out = ld
         e.mask_out = mask_out.t.data_ptr() if mask_out is not None else None
         e.mask_w = mask_out.w if mask_out is not None else 32
@@ -321,11 +404,23 @@ class Engine:
         return e
 
     def plan(self, B, T, training):
+        """Plans are cached per (B, T, training), least recently used first.  A plan owns every activation / mask /
+        gradient buffer of its shape (about 3.7 GB at 64 x 500) plus the CUDA graphs and CTC workspaces captured on it, so
+        loaders whose padded length changes from batch to batch would otherwise grow without bound: beyond `max_plans`
+        (NBASR_MAX_PLANS, default 6) the oldest plan is dropped and its memory returns to the allocator."""
         key = (B, T, bool(training))
-        if key not in self.plans:
-            self.plans[key] = self._build_plan(B, T, bool(training))
-        return self.plans[key]
+        pl = self.plans.get(key)
+        if pl is None:
+            while len(self.plans) >= max(1, self.max_plans):
+                _, old = self.plans.popitem(last=False)
+                old.graphs.clear()
+                old.ws.clear()
+            pl = self.plans[key] = self._build_plan(B, T, bool(training))
+        else:
+            self.plans.move_to_end(key)
+        return pl
 
+    @_on_device
     def _build_plan(self, B, T, training):
         self.bind()
         m, lib, dev, dt, tdt = self.model, self.lib, self.device, self.dt, self.tdt
@@ -333,6 +428,8 @@ class Engine:
         pl = _Plan()
         pl.B, pl.T, pl.training = B, T, training
         pl.keep = []       # keeps ctypes structs / tensors alive
+        pl.graphs, pl.ws = {}, {}     # CUDA graphs / CTC workspaces captured on this plan (trainer.py); die with the plan
+        arena = pl.arena = _Arena(dev)
         fwd, bwd_rev = [], []   # bwd_rev: groups appended in forward order, executed reversed
         drop_p = self.training_drop if training else 0.0
         dscale = 1.0 / (1.0 - drop_p) if drop_p > 0 else 1.0
@@ -342,10 +439,26 @@ class Engine:
             salt[0] += 1
             return salt[0] * 0x9E3779B1
 
+        adt, tadt, S = self.adt, self.tadt, self.S
+        bcopy = {}          # id(forward activation) -> its unscaled bf16 copy (training plans of the 16-bit mode)
+
         def zbuf(rows, cols, dtype=None):
-            t = torch.zeros((rows, cols), dtype=tdt if dtype is None else dtype, device=dev)
-            pl.keep.append(t)
+            return arena.zeros((rows, cols), tdt if dtype is None else dtype)
+
+        def zact(rows, cols, copy=False):
+            """forward activation buffer (activation format) and, if asked for in a 16-bit training plan, its bf16 twin"""
+            t = arena.zeros((rows, cols), tadt)
+            if copy and training and adt != dt:
+                bcopy[id(t)] = arena.zeros((rows, cols), tdt)
             return t
+
+        def Bc(t):
+            """the tensor a weight gradient reads for forward activation t"""
+            return bcopy.get(id(t), t)
+
+        def cptr(t):
+            c = bcopy.get(id(t))
+            return c.data_ptr() if c is not None else 0
 
         def call(lst, fn, *args):
             pl.keep.append(args)
@@ -369,10 +482,12 @@ class Engine:
             pl.keep.append(w)
 
         # ---- input
-        pl.audio = torch.zeros((B, FEATURES, T), dtype=torch.float32, device=dev)
+        pl.audio = arena.zeros((B, FEATURES, T), torch.float32)
         g_in = _Geo(B, T, FEATURES)
-        x_in = zbuf(g_in.rows, FEATURES)
-        call(fwd, lib.nbasr_transpose_in, pl.audio.data_ptr(), x_in.data_ptr(), dt, B, FEATURES, T, g_in.Tp)
+        x_in = zact(g_in.rows, FEATURES, copy=True)
+        call(fwd, lib.nbasr_transpose_in, pl.audio.data_ptr(), x_in.data_ptr(), adt, B, FEATURES, T, g_in.Tp, S)
+        if cptr(x_in):
+            call(fwd, lib.nbasr_transpose_in, pl.audio.data_ptr(), cptr(x_in), dt, B, FEATURES, T, g_in.Tp, 1.0)
 
         prev, pg = x_in, g_in
         Tcur = T
@@ -390,21 +505,24 @@ class Engine:
             cname = self.block_conv[i]
             lpad, _ = pad_rule(8, 1, s)
             K = 8 * pg.C
-            z = zbuf(geo.rows, Cc)
-            zmask = _Mask(geo.rows, Cc, 32, dev)
+            z = zact(geo.rows, Cc)
+            zmask = _Mask(geo.rows, Cc, 32, arena) if training else None     # gate bits are only read by the backward pass
             pl.keep.append(zmask)
             wf_ptr = self.wf[cname].data_ptr() if self.wf[cname] is not None else self.P(cname + '.weight')
             a_ptr = _ptr(prev, (PAD_L - lpad) * pg.C)
-            epi = self._epi(Cc, bias=self.P(cname + '.bias'), relu=1, out=z.data_ptr(), mask_out=zmask, mask_rows=geo.rows)
-            gemm(fwd, a_ptr, pg.Tp * pg.C, s * pg.C, B, Ti, K, Cc, wf_ptr, K, PAD_L, Tp, 1, epi)
-            y = zbuf(geo.rows, Cc)
+            a_ptr_b = _ptr(Bc(prev), (PAD_L - lpad) * pg.C)      # the same rows of the bf16 copy (weight gradient)
+            epi = self._epi(Cc, bias=self.P(cname + '.bias'), relu=1, out=z.data_ptr(), mask_out=zmask, mask_rows=geo.rows, fwd=True)
+            gemm(fwd, a_ptr, pg.Tp * pg.C, s * pg.C, B, Ti, K, Cc, wf_ptr, K, PAD_L, Tp, 1, epi, dtype=adt)
+            n_ops = [nd[0] != 'zero' for nd in arch]        # which nodes hold a parametrised op (and read a bf16 copy)
+            y = zact(geo.rows, Cc, copy=True)
             mean0 = zbuf(geo.rows, 1, torch.float32)
             rstd0 = zbuf(geo.rows, 1, torch.float32)
             lname = self.block_ln[i]
-            call(fwd, lib.nbasr_layernorm_fwd, dt, z.data_ptr(), y.data_ptr(), B, Ti, Tp, Cc, self.P(lname + '.weight'),
-                 self.P(lname + '.bias'), 1e-3, mean0.data_ptr(), rstd0.data_ptr())
+            # scaled fp16 input S*x: eps*S^2 gives the exact xhat of the unscaled tensor; output again scaled by S
+            call(fwd, lib.nbasr_layernorm_fwd, adt, z.data_ptr(), y.data_ptr(), B, Ti, Tp, Cc, self.P(lname + '.weight'),
+                 self.P(lname + '.bias'), 1e-3 * S * S, mean0.data_ptr(), rstd0.data_ptr(), S, cptr(y) or None)
             rec = dict(i=i, geo=geo, prev=prev, pg=pg, z=z, zmask=zmask, y=y, mean=mean0, rstd=rstd0, cells=[],
-                       a_ptr=a_ptr, K=K, s=s, lpad=lpad)
+                       a_ptr=a_ptr_b, K=K, s=s, lpad=lpad)
             cur = y
             for cellname in self.block_cells[i]:
                 outs = [cur]
@@ -413,50 +531,52 @@ class Engine:
                     op, branches = node[0], node[1:]
                     src = outs[-1]
                     skips = [outs[k] for k, bit in enumerate(branches) if bit]
-                    o = zbuf(geo.rows, Cc)
+                    # node n's output feeds node n+1's op (bf16 copy for its weight gradient); the last node's output feeds
+                    # the cell LayerNorm, or -- without norm -- the next cell / block / LSTM directly
+                    o = zact(geo.rows, Cc, copy=(n_ops[n + 1] if n + 1 < len(arch) else not m.use_norm))
                     pn = f'{cellname}.nodes.{n}.op'
                     nrec = dict(op=op, branches=list(branches), pn=pn, mask=None, salt=0)
                     adds = [t.data_ptr() for t in skips]
                     if op == 'zero':
-                        epi = self._epi(Cc, adds=adds, out=o.data_ptr())
-                        call(fwd, lib.nbasr_eltwise, dt, None, Cc, B, Ti, Tp, Cc, C.byref(epi))
+                        epi = self._epi(Cc, adds=adds, out=o.data_ptr(), fwd=True, copy=cptr(o))
+                        call(fwd, lib.nbasr_eltwise, adt, None, Cc, B, Ti, Tp, Cc, C.byref(epi))
                         pl.keep.append(epi)
                     else:
                         # plane width = the producing kernel's slab: 32 (GEMM / SIMT) or 48/40 (tcgen05 grouped conv)
                         mwid = (40 if Cc // 100 == 10 else 48) if (op in CONV_EDGES and dt == BF16) else 32
-                        mask = _Mask(geo.rows, Cc, mwid, dev)
+                        mask = _Mask(geo.rows, Cc, mwid, arena) if training else None
                         pl.keep.append(mask)
                         nrec['mask'] = mask
                         sl = next_salt()
                         if op == 'linear':
                             epi = self._epi(Cc, bias=self.P(pn + '.linear.bias'), relu=1, drop_p=drop_p, salt=sl, adds=adds,
-                                            out=o.data_ptr(), mask_out=mask, mask_rows=geo.rows)
+                                            out=o.data_ptr(), mask_out=mask, mask_rows=geo.rows, fwd=True, copy=cptr(o))
                             w_ptr = self.wf[pn].data_ptr() if self.wf[pn] is not None else self.P(pn + '.linear.weight')
-                            gemm(fwd, _ptr(src, PAD_L * Cc), Tp * Cc, Cc, B, Ti, Cc, Cc, w_ptr, Cc, PAD_L, Tp, 1, epi)
+                            gemm(fwd, _ptr(src, PAD_L * Cc), Tp * Cc, Cc, B, Ti, Cc, Cc, w_ptr, Cc, PAD_L, Tp, 1, epi, dtype=adt)
                         else:
                             k, d = CONV_EDGES[op]
                             lp, _ = pad_rule(k, d, 1)
                             gc = GConv()
-                            gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = dt, src.data_ptr(), B, Ti, Tp, Cc, Cc // 100
+                            gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = adt, src.data_ptr(), B, Ti, Tp, Cc, Cc // 100
                             gc.ktaps, gc.off0, gc.dstep = k, -lp, d
                             if dt == BF16:
                                 gc.w, gc.w_packed = self.wf[pn].data_ptr(), 3     # packed | stable (re-packed by the optimiser tail)
                             else:
                                 gc.w, gc.w_packed = self.P(pn + '.conv.weight'), 0
                             gc.epi = self._epi(Cc, bias=self.P(pn + '.conv.bias'), relu=1, drop_p=drop_p, salt=sl, adds=adds,
-                                               out=o.data_ptr(), mask_out=mask, mask_rows=geo.rows)
+                                               out=o.data_ptr(), mask_out=mask, mask_rows=geo.rows, fwd=True, copy=cptr(o))
                             call(fwd, lib.nbasr_gconv_fwd, C.byref(gc))
                             pl.keep.append(gc)
                             nrec.update(k=k, d=d, lp=lp)
                     crec['nodes'].append(nrec)
                     outs.append(o)
                 if m.use_norm:
-                    co = zbuf(geo.rows, Cc)
+                    co = zact(geo.rows, Cc, copy=True)
                     mean = zbuf(geo.rows, 1, torch.float32)
                     rstd = zbuf(geo.rows, 1, torch.float32)
-                    call(fwd, lib.nbasr_layernorm_fwd, dt, outs[-1].data_ptr(), co.data_ptr(), B, Ti, Tp, Cc,
-                         self.P(cellname + '.norm_layer.weight'), self.P(cellname + '.norm_layer.bias'), 1e-3,
-                         mean.data_ptr(), rstd.data_ptr())
+                    call(fwd, lib.nbasr_layernorm_fwd, adt, outs[-1].data_ptr(), co.data_ptr(), B, Ti, Tp, Cc,
+                         self.P(cellname + '.norm_layer.weight'), self.P(cellname + '.norm_layer.bias'), 1e-3 * S * S,
+                         mean.data_ptr(), rstd.data_ptr(), S, cptr(co) or None)
                     crec.update(mean=mean, rstd=rstd, out=co)
                     cur = co
                 else:
@@ -472,26 +592,28 @@ class Engine:
         pl.Tq = Tq
         V = m.num_classes + 1
         pl.V = V
-        pl.logits = torch.zeros((B, Tq, V), dtype=torch.float32, device=dev)
-        pl.logp = torch.zeros((B, Tq, V), dtype=torch.float32, device=dev)
+        pl.logits = arena.zeros((B, Tq, V), torch.float32)
+        pl.logp = arena.zeros((B, Tq, V), torch.float32)
         hn = self.head_name
         head = dict()
         if m.use_rnn:
             ln = self.lstm_name
             if drop_p > 0:
-                lin = zbuf(geo3.rows, C3)
-                dmask = _Mask(geo3.rows, C3, 32, dev)
+                lin = zact(geo3.rows, C3, copy=True)
+                dmask = _Mask(geo3.rows, C3, 32, arena)
                 pl.keep.append(dmask)
-                epi = self._epi(C3, drop_p=drop_p, salt=next_salt(), out=lin.data_ptr(), mask_out=dmask, mask_rows=geo3.rows)
-                call(fwd, lib.nbasr_eltwise, dt, prev.data_ptr(), C3, B, Tq, Tp3, C3, C.byref(epi))
+                epi = self._epi(C3, drop_p=drop_p, salt=next_salt(), out=lin.data_ptr(), mask_out=dmask, mask_rows=geo3.rows,
+                                fwd=True, copy=cptr(lin))
+                call(fwd, lib.nbasr_eltwise, adt, prev.data_ptr(), C3, B, Tq, Tp3, C3, C.byref(epi))
                 pl.keep.append(epi)
             else:
                 lin, dmask = prev, None
             H4 = 4 * HIDDEN
             gx = zbuf(B * Tq, H4, torch.float32)
             wih = self.wf[ln].data_ptr() if self.wf[ln] is not None else self.P(ln + '.weight_ih_l0')
-            epi = self._epi(H4, bias=self.lstm_bias.data_ptr(), out=gx.data_ptr(), out_dtype=F32)
-            gemm(fwd, _ptr(lin, PAD_L * C3), Tp3 * C3, C3, B, Tq, C3, H4, wih, C3, 0, Tq, 1, epi)
+            # the LSTM wants true values: un-scale the accumulator of the scaled fp16 operand
+            epi = self._epi(H4, bias=self.lstm_bias.data_ptr(), out=gx.data_ptr(), out_dtype=F32, acc_scale=1.0 / S)
+            gemm(fwd, _ptr(lin, PAD_L * C3), Tp3 * C3, C3, B, Tq, C3, H4, wih, C3, 0, Tq, 1, epi, dtype=adt)
             gh = _Geo(B, Tq, HP)
             hseq = zbuf(gh.rows, HP)
             gates = zbuf(B * Tq, H4, torch.float32)
@@ -504,14 +626,22 @@ class Engine:
                  self.P(hn + '.bias'), pl.logits.data_ptr(), pl.logp.data_ptr())
             head.update(lin=lin, dmask=dmask, gx=gx, hseq=hseq, gh=gh, gates=gates, cst=cst, work=work)
         else:
-            call(fwd, lib.nbasr_head_fwd, dt, _ptr(prev, PAD_L * C3), Tp3 * C3, C3, B, Tq, C3, V, self.P(hn + '.weight'),
+            hsrc = prev
+            if adt != dt:
+                # the classifier kernels read bf16 / fp32: un-scale the fp16 encoder output once
+                hsrc = zbuf(geo3.rows, C3)
+                epi = self._epi(C3, out=hsrc.data_ptr(), acc_scale=1.0 / S)
+                call(fwd, lib.nbasr_eltwise, adt, prev.data_ptr(), C3, B, Tq, Tp3, C3, C.byref(epi))
+                pl.keep.append(epi)
+            head.update(hsrc=hsrc)
+            call(fwd, lib.nbasr_head_fwd, dt, _ptr(hsrc, PAD_L * C3), Tp3 * C3, C3, B, Tq, C3, V, self.P(hn + '.weight'),
                  self.P(hn + '.bias'), pl.logits.data_ptr(), pl.logp.data_ptr())
         pl.fwd = fwd
         pl.final = prev
 
         # =========================================================== backward plan
         bwd = []
-        pl.dlogits = torch.zeros((B, Tq, V), dtype=torch.float32, device=dev)
+        pl.dlogits = arena.zeros((B, Tq, V), torch.float32)
         # gradient wrt the last cell output of block 3 (act dtype, padded geometry)
         pools = []
         for geo in pl.block_geo:
@@ -547,7 +677,7 @@ class Engine:
                 for bn in ('.bias_ih_l0', '.bias_hh_l0'):
                     call(bwd, lib.nbasr_colsum, F32, dgx.data_ptr() - PAD_L * H4 * 4, 1, B * Tq, B * Tq, H4, self.G(ln + bn))
             # dW_ih += dgx^T X ; dW_hh += dgx^T H_{t-1} (h_seq shifted one row up; row -1 is a zero pad row)
-            wgrad(bwd, dgx_a.data_ptr(), Tq * H4, H4, _ptr(head['lin'], PAD_L * C3), Tp3 * C3, C3, B, Tq, H4, C3,
+            wgrad(bwd, dgx_a.data_ptr(), Tq * H4, H4, _ptr(Bc(head['lin']), PAD_L * C3), Tp3 * C3, C3, B, Tq, H4, C3,
                   self.G(ln + '.weight_ih_l0'), C3, dbias=self.G(ln + '.bias_ih_l0') if fuse_b else None)
             wgrad(bwd, dgx_a.data_ptr(), Tq * H4, H4, _ptr(head['hseq'], (PAD_L - 1) * HP), head['gh'].Tp * HP, HP, B, Tq, H4,
                   HIDDEN, self.G(ln + '.weight_hh_l0'), HIDDEN, dbias=self.G(ln + '.bias_hh_l0') if fuse_b else None)
@@ -559,7 +689,7 @@ class Engine:
             gemm(bwd, dgx_a.data_ptr(), Tq * H4, H4, B, Tq, H4, C3, self.wt[ln].data_ptr(), H4, PAD_L, Tp3, 1, epi)
         else:
             dhp = zbuf(geo3.rows, C3, torch.float32)
-            call(bwd, lib.nbasr_head_bwd, dt, _ptr(prev, PAD_L * C3), Tp3 * C3, C3, B, Tq, C3, V, self.P(hn + '.weight'),
+            call(bwd, lib.nbasr_head_bwd, dt, _ptr(head['hsrc'], PAD_L * C3), Tp3 * C3, C3, B, Tq, C3, V, self.P(hn + '.weight'),
                  pl.dlogits.data_ptr(), _ptr(dhp, PAD_L * C3), Tp3 * C3, C3, self.G(hn + '.weight'), self.G(hn + '.bias'))
             epi = self._epi(C3, out=gout.data_ptr())
             call(bwd, lib.nbasr_eltwise, F32, dhp.data_ptr(), C3, B, Tq, Tp3, C3, C.byref(epi))
@@ -591,7 +721,7 @@ class Engine:
                     if last['op'] != 'zero':
                         dz_t = dz[(nn_ - 1) & 1]
                         dzb[nn_ - 1] = dz_t
-                    call(bwd, lib.nbasr_layernorm_bwd, dt, gout.data_ptr(), outs[nn_].data_ptr(), crec['mean'].data_ptr(),
+                    call(bwd, lib.nbasr_layernorm_bwd, dt, gout.data_ptr(), outs[nn_].data_ptr(), adt, S, crec['mean'].data_ptr(),
                          crec['rstd'].data_ptr(), self.P(crec['name'] + '.norm_layer.weight'), B, Ti, Tp, Cc,
                          g[nn_].data_ptr(), dz_t.data_ptr() if dz_t is not None else None,
                          last['mask'].t.data_ptr() if dz_t is not None else None, dscale, geo.rows,
@@ -625,7 +755,7 @@ class Engine:
                     elif op == 'linear':
                         d = dzb[j]
                         fuse = dt == BF16       # bias gradient rides on the tensor-core wgrad (ones operand)
-                        wgrad(bwd, _ptr(d, PAD_L * Cc), Tp * Cc, Cc, _ptr(src, PAD_L * Cc), Tp * Cc, Cc, B, Ti, Cc, Cc,
+                        wgrad(bwd, _ptr(d, PAD_L * Cc), Tp * Cc, Cc, _ptr(Bc(src), PAD_L * Cc), Tp * Cc, Cc, B, Ti, Cc, Cc,
                               self.G(pn + '.linear.weight'), Cc, dbias=self.G(pn + '.linear.bias') if fuse else None)
                         if not fuse:
                             call(bwd, lib.nbasr_colsum, dt, d.data_ptr(), B, Ti, Tp, Cc, self.G(pn + '.linear.bias'))
@@ -633,7 +763,7 @@ class Engine:
                     else:
                         d = dzb[j]
                         k, dd, lp = nrec['k'], nrec['d'], nrec['lp']
-                        call(bwd, lib.nbasr_gconv_wgrad, dt, d.data_ptr(), src.data_ptr(), B, Ti, Tp, Cc, Cc // 100, k, -lp, dd,
+                        call(bwd, lib.nbasr_gconv_wgrad, dt, d.data_ptr(), Bc(src).data_ptr(), B, Ti, Tp, Cc, Cc // 100, k, -lp, dd,
                              self.G(pn + '.conv.weight'), self.G(pn + '.conv.bias'))
                         gc = GConv()
                         gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = dt, d.data_ptr(), B, Ti, Tp, Cc, Cc // 100
@@ -648,7 +778,7 @@ class Engine:
             # ---- top of the block: LayerNorm bwd -> dZ of the time-reduction conv
             dzc = dz[0]
             lname, cname = self.block_ln[i], self.block_conv[i]
-            call(bwd, lib.nbasr_layernorm_bwd, dt, gout.data_ptr(), rec['z'].data_ptr(), rec['mean'].data_ptr(),
+            call(bwd, lib.nbasr_layernorm_bwd, dt, gout.data_ptr(), rec['z'].data_ptr(), adt, S, rec['mean'].data_ptr(),
                  rec['rstd'].data_ptr(), self.P(lname + '.weight'), B, Ti, Tp, Cc, None, dzc.data_ptr(), rec['zmask'].t.data_ptr(),
                  1.0, geo.rows, 32, self.G(lname + '.weight'), self.G(lname + '.bias'))
             pool.append(gout)
@@ -686,6 +816,7 @@ class Engine:
             n += 1
         self.launches += n     # kernels launched (every C-ABI call launches >= 1 kernel of libnbasr)
 
+    @_on_device
     def forward(self, audio, training=None):
         """audio (B, 80, T) fp32 cuda -> plan (holds logits / logp buffers)."""
         self.bind()
@@ -700,6 +831,7 @@ class Engine:
         self._run(pl.fwd)
         return pl
 
+    @_on_device
     def backward(self, pl, dlogits=None, zero_grad=True):
         if dlogits is not None:
             pl.dlogits.copy_(dlogits)
@@ -719,11 +851,13 @@ class Engine:
                 else:
                     p.grad = gv.view(p.shape)
 
+    @_on_device
     def set_lr(self, lr):
         if getattr(self, '_lr_host', None) != lr:   # device write only when the schedule changes lr
             self.opt_state[1:2].fill_(lr)
             self._lr_host = lr
 
+    @_on_device
     def optimizer_step(self, lr, reg_coef=0.01, max_norm=5.0, betas=(0.9, 0.999), eps=1e-7):
         self.set_lr(lr)
         self._optimizer_launch(reg_coef, max_norm, betas, eps)
@@ -731,6 +865,7 @@ class Engine:
     def snapshot_state(self):
         return (self.flat_p.clone(), self.adam_m.clone(), self.adam_v.clone(), self.opt_state.clone(), self.drop_step.clone())
 
+    @_on_device
     def restore_state(self, st):
         self.flat_p.copy_(st[0]); self.adam_m.copy_(st[1]); self.adam_v.copy_(st[2]); self.opt_state.copy_(st[3])
         self.drop_step.copy_(st[4])
@@ -759,12 +894,34 @@ class ModelFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         eng, pl = ctx.eng, ctx.pl
-        # accumulate like autograd: grads of this call are added to whatever .grad holds
-        had = any(p.grad is not None for p in eng.params)
-        saved = eng.flat_g.clone() if had else None
+        # Accumulate like autograd: the gradients of this call are added to whatever .grad holds.  A .grad can be (a) a
+        # view of the flat gradient buffer (ours, from an earlier call) or (b) a fresh tensor another autograd node made
+        # after optimizer.zero_grad(set_to_none=True) -- e.g. the conv-weight regulariser of the reference step
+        # (trainer.py:221), whose norm nodes run before this one.  (b) is folded into the flat buffer, then re-pointed.
+        views, foreign = False, []
+        for name, p in zip(eng.names, eng.params):
+            if p.grad is None:
+                continue
+            off, _ = eng.slices[name]
+            if p.grad.data_ptr() == eng.flat_g.data_ptr() + 4 * off:
+                views = True
+            else:
+                foreign.append((name, p, p.grad))
+        saved = eng.flat_g.clone() if views else None
         eng.backward(pl, dlogits.contiguous(), zero_grad=True)
-        if had:
+        if views:
+            for name, p, _ in foreign:          # stale flat content under a foreign .grad is not a gradient of p
+                off, n = eng.slices[name]
+                saved[off:off + n].zero_()
             eng.flat_g.add_(saved)
+        for name, p, g in foreign:
+            off, n = eng.slices[name]
+            dst = eng.flat_g[off:off + n]
+            if eng._is_dense_conv_w(name):
+                co, ci, k = p.shape
+                dst.view(co, k, ci).add_(g.detach().to(dst.device, torch.float32).permute(0, 2, 1))
+            else:
+                dst.view(p.shape).add_(g.detach().to(dst.device, torch.float32))
         eng.attach_grads()
         # gradients were written in place into p.grad (views of the flat buffer)
         return (None, None) + tuple(None for _ in eng.params)

@@ -25,7 +25,9 @@ def op_work(fn_name, args, es):
         rows = g.nb * g.nr
         flops = 2.0 * rows * g.K * g.N
         a_cols = min(g.K, g.a_rs) if g.a_rs > 0 else g.K      # overlapping rows are read once
-        n_o = g.epi.n_add + (1 if g.epi.out else 0) + (1 if g.epi.out2 else 0)
+        # (an out2 without a gate mask is the bf16 twin of `out` for the weight gradient: an implementation cost of the
+        # fp16-forward / bf16-backward split, not algorithmic traffic)
+        n_o = g.epi.n_add + (1 if g.epi.out else 0) + (1 if (g.epi.out2 and g.epi.mask2) else 0)
         byts = rows * a_cols * es + g.N * g.K * es + rows * g.N * es * n_o
         return f'gemm_tn K={g.K} N={g.N}', flops, byts
     if fn_name == 'nbasr_gemm_wgrad':
@@ -38,7 +40,7 @@ def op_work(fn_name, args, es):
     if fn_name == 'nbasr_gconv_fwd':
         g = _struct_of(args[0], GConv)
         el = g.B * g.T * g.C
-        n_t = 1 + g.epi.n_add + (1 if g.epi.out else 0) + (1 if g.epi.out2 else 0)     # tensors read/written once
+        n_t = 1 + g.epi.n_add + (1 if g.epi.out else 0) + (1 if (g.epi.out2 and g.epi.mask2) else 0)     # tensors read/written once
         n_m = (1 if g.epi.mask_out else 0) + (1 if g.epi.mask2 else 0)                 # 1 bit / element each
         return f'gconv C={g.C} k={g.ktaps} d={g.dstep}', 2.0 * el * g.cpg * g.ktaps, el * es * n_t + el * n_m / 8.0
     if fn_name == 'nbasr_gconv_wgrad':
@@ -49,8 +51,8 @@ def op_work(fn_name, args, es):
         if fn_name.endswith('fwd'):
             B, T, Tp, Cc = args[3:7]
             return f'ln_fwd C={Cc}', 0.0, B * T * Cc * es * 2
-        B, T, Tp, Cc = args[6:10]
-        n_out = (1 if args[10] else 0) + (1 if args[11] else 0)
+        B, T, Tp, Cc = args[8:12]
+        n_out = (1 if args[12] else 0) + (1 if args[13] else 0)
         return f'ln_bwd C={Cc}', 0.0, B * T * Cc * es * (2 + n_out)
     if fn_name == 'nbasr_eltwise':
         B, T, Tp, Cc = args[3:7]
@@ -75,7 +77,7 @@ def gconv_issue_floor_cycles(fn_name, args):
 def profile_ops(engine, ops, iters=3):
     """Time every entry of a plan op list. Returns {tag: dict(n, ms, flops, bytes)} averaged over iters."""
     st = torch.cuda.current_stream()
-    es = 2 if engine.dt == BF16 else 4
+    es = 2 if engine.dt == BF16 else 4          # 16-bit mode: fp16 activations and bf16 gradients are both 2 bytes
     n = len(ops)
     acc = collections.OrderedDict()
     for it in range(iters + 1):

@@ -10,8 +10,9 @@ backward plan -> [NCCL all-reduce] -> regulariser+clip+Adam kernel) with no auto
 no host synchronisation; data-parallel training is one process per GPU (torch.distributed)
 instead of single-process nn.DataParallel (:91-92).
 """
-import pathlib
+import collections
 import collections.abc as cabc
+import pathlib
 
 import numpy as np
 import os
@@ -46,27 +47,38 @@ class _Ws:
 
 
 class _CtcWorkspace:
-    """Per-shape scratch buffers; never freed, so pointers captured in CUDA graphs stay valid."""
+    """Per-shape scratch buffers for loss() / decode() called on free-standing tensors (bounded LRU).  The step itself
+    keeps its workspaces on the engine plan (`plan.ws`), so pointers captured in CUDA graphs live exactly as long as
+    the plan and the graphs do."""
+    MAX = 16
 
     def __init__(self):
-        self.cache = {}
+        self.cache = collections.OrderedDict()
+
+    @staticmethod
+    def make(dev, B, T, V, S):
+        L = 2 * S + 1
+        w = _Ws()
+        w.work = torch.empty(2 * B * T * L + 16, dtype=torch.float32, device=dev)
+        w.nll = torch.zeros(B, dtype=torch.float32, device=dev)
+        w.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        w.dlogits = torch.zeros((B, T, V), dtype=torch.float32, device=dev)
+        w.hyp = torch.zeros((B, T), dtype=torch.int32, device=dev)
+        w.hyp_len = torch.zeros(B, dtype=torch.int32, device=dev)
+        w.dist = torch.zeros(B, dtype=torch.int32, device=dev)
+        w.per = torch.zeros(2, dtype=torch.float64, device=dev)
+        w.iwork = torch.zeros(B * (S + 2) + 16, dtype=torch.int32, device=dev)
+        return w
 
     def get(self, dev, B, T, V, S):
         key = (str(dev), B, T, V, S)
         w = self.cache.get(key)
         if w is None:
-            L = 2 * S + 1
-            w = _Ws()
-            w.work = torch.empty(2 * B * T * L + 16, dtype=torch.float32, device=dev)
-            w.nll = torch.zeros(B, dtype=torch.float32, device=dev)
-            w.loss = torch.zeros(1, dtype=torch.float32, device=dev)
-            w.dlogits = torch.zeros((B, T, V), dtype=torch.float32, device=dev)
-            w.hyp = torch.zeros((B, T), dtype=torch.int32, device=dev)
-            w.hyp_len = torch.zeros(B, dtype=torch.int32, device=dev)
-            w.dist = torch.zeros(B, dtype=torch.int32, device=dev)
-            w.per = torch.zeros(2, dtype=torch.float64, device=dev)
-            w.iwork = torch.zeros(B * (S + 2) + 16, dtype=torch.int32, device=dev)
-            self.cache[key] = w
+            while len(self.cache) >= self.MAX:
+                self.cache.popitem(last=False)
+            w = self.cache[key] = self.make(dev, B, T, V, S)
+        else:
+            self.cache.move_to_end(key)
         return w
 
 
@@ -78,11 +90,12 @@ def ctc_loss_cuda(logp, output_len_src, len_div, targets, targets_len, dlogits=N
     lib = _lib.load()
     B, T, V = logp.shape
     S = targets.shape[1]
-    ws = _ws.get(logp.device, B, T, V, S)
-    st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.nbasr_ctc(logp.data_ptr(), B, T, V, targets.data_ptr(), S, output_len_src.data_ptr(), len_div,
-                             targets_len.data_ptr(), ws.nll.data_ptr(), ws.loss.data_ptr(),
-                             dlogits.data_ptr() if dlogits is not None else None, ws.work.data_ptr(), st), 'ctc')
+    with torch.cuda.device(logp.device):
+        ws = _ws.get(logp.device, B, T, V, S)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.nbasr_ctc(logp.data_ptr(), B, T, V, targets.data_ptr(), S, output_len_src.data_ptr(), len_div,
+                                 targets_len.data_ptr(), ws.nll.data_ptr(), ws.loss.data_ptr(),
+                                 dlogits.data_ptr() if dlogits is not None else None, ws.work.data_ptr(), st), 'ctc')
     return ws.loss, ws.nll
 
 
@@ -231,21 +244,30 @@ class Trainer:
         (loss w/o regulariser, log-probs (B,T',49), output_len), all detached (trainer.py:208-227)."""
         (audio, audio_len), (targets, targets_len) = inputs
         dev = self.device
-        audio = audio.to(device=dev, dtype=torch.float32, non_blocking=True)
-        audio_len = audio_len.to(device=dev, dtype=torch.int64, non_blocking=True)
-        targets = targets.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
-        targets_len = targets_len.to(device=dev, dtype=torch.int64, non_blocking=True)
-        if getattr(self, 'use_graph', False):
-            try:
-                return self._step_graph(audio, audio_len, targets, targets_len, training)
-            except _GraphCaptureError as e:       # eager launches of the same kernels; still GPU-only
-                import sys
-                sys.stderr.write(f'[nb_asr_b200] CUDA graph capture unavailable ({e}); running eagerly\n')
-                self.use_graph = False
-        return self._step_eager(audio, audio_len, targets, targets_len, training)
+        with torch.cuda.device(dev):      # libnbasr launches on the CURRENT stream: make gpus[0] the current device
+            audio = audio.to(device=dev, dtype=torch.float32, non_blocking=True)
+            audio_len = audio_len.to(device=dev, dtype=torch.int64, non_blocking=True)
+            targets = targets.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+            targets_len = targets_len.to(device=dev, dtype=torch.int64, non_blocking=True)
+            if getattr(self, 'use_graph', False):
+                try:
+                    return self._step_graph(audio, audio_len, targets, targets_len, training)
+                except _GraphCaptureError as e:       # eager launches of the same kernels; still GPU-only
+                    import sys
+                    sys.stderr.write(f'[nb_asr_b200] CUDA graph capture unavailable ({e}); running eagerly\n')
+                    self.use_graph = False
+            return self._step_eager(audio, audio_len, targets, targets_len, training)
 
     def _lr(self):
         return self.optimizer.param_groups[0]['lr'] if self.optimizer is not None else (self.lr or 1e-4)
+
+    @staticmethod
+    def _plan_ws(pl, dev, B, S):
+        """CTC / decode workspace of this (plan, S): owned by the plan, so it lives as long as graphs captured on it."""
+        ws = pl.ws.get(S)
+        if ws is None:
+            ws = pl.ws[S] = _CtcWorkspace.make(dev, B, pl.Tq, pl.V, S)
+        return ws
 
     def _ctc(self, eng, pl, targets, audio_len, targets_len, training, ws):
         B, S = targets.shape
@@ -260,7 +282,7 @@ class Trainer:
         eng = model.engine
         pl = eng.forward(audio, training=model.training)
         B, S = targets.shape
-        ws = _ws.get(self.device, B, pl.Tq, pl.V, S)
+        ws = self._plan_ws(pl, self.device, B, S)
         self._ctc(eng, pl, targets, audio_len, targets_len, training, ws)
         if training:
             eng.backward(pl)
@@ -269,7 +291,9 @@ class Trainer:
         return ws.loss[0].clone(), pl.logp.clone(), audio_len // 4
 
     def _step_graph(self, audio, audio_len, targets, targets_len, training):
-        """Same launches as _step_eager, replayed from CUDA graphs (static buffers, no per-launch host cost)."""
+        """Same launches as _step_eager, replayed from CUDA graphs (static buffers, no per-launch host cost).  The graphs
+        are stored ON the engine plan they were captured on (plan.graphs), so they can never outlive its buffers or be
+        replayed against another engine."""
         import torch.distributed as dist
         model = self._model
         eng = model.engine
@@ -277,12 +301,10 @@ class Trainer:
         B, _, T = audio.shape
         S = targets.shape[1]
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        key = (id(eng), B, T, S, bool(training), bool(model.training), multi)
-        if not hasattr(self, '_graphs'):
-            self._graphs = {}
-        ent = self._graphs.get(key)
         pl = eng.plan(B, T, model.training)
-        ws = _ws.get(self.device, B, pl.Tq, pl.V, S)
+        key = (S, bool(training), multi)
+        ent = pl.graphs.get(key)
+        ws = self._plan_ws(pl, self.device, B, S)
         eng.refresh_packs()
         if training:
             eng.set_lr(self._lr())
@@ -302,8 +324,9 @@ class Trainer:
                     if not multi:
                         eng._optimizer_launch()
 
-            # eager warm-up run on a side stream (sets function attributes, fills the tensor-map cache)
-            state = eng.snapshot_state() if training else None
+            # eager warm-up run on a side stream (sets function attributes, fills the tensor-map cache); its effect on
+            # the parameters, the optimiser state and the dropout counter is rolled back afterwards
+            state = eng.snapshot_state() if (training or model.training) else None
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -348,7 +371,7 @@ class Trainer:
             except Exception as e:  # noqa: BLE001
                 torch.cuda.synchronize()
                 raise _GraphCaptureError(str(e)) from e
-            self._graphs[key] = ent
+            pl.graphs[key] = ent
         ent['alen'].copy_(audio_len, non_blocking=True)
         ent['tg'].copy_(targets, non_blocking=True)
         ent['tl'].copy_(targets_len, non_blocking=True)
@@ -383,11 +406,15 @@ class Trainer:
 
         Default (north_star): greedy decode.  ``beam_width=12`` (or ``trainer.beam_width = 12``) runs the prefix beam
         search the reference's CTCBeamDecoder performs (trainer.py:71,236) -- see nbasr_beam_per."""
+        with torch.cuda.device(self.device):
+            return self._decode(output, output_len, val_inputs, beam_width)
+
+    def _decode(self, output, output_len, val_inputs, beam_width):
         _, (targets, targets_len) = val_inputs
         dev = self.device
         targets = targets.to(device=dev, dtype=torch.int32).contiguous()
         targets_len = targets_len.to(device=dev, dtype=torch.int64)
-        output = output.contiguous().float()
+        output = output.to(device=dev).contiguous().float()
         output_len = output_len.to(device=dev, dtype=torch.int64)
         B, T, V = output.shape
         S = targets.shape[1]

@@ -25,21 +25,8 @@ GOLD = os.path.join(ROOT, 'tests', 'golden')
 
 
 def import_reference():
-    import torchaudio
-    torchaudio.set_audio_backend = lambda *a, **k: None
-    ed = types.ModuleType('torch_edit_distance')
-    sys.modules['torch_edit_distance'] = ed
-    cd = types.ModuleType('ctcdecode')
-
-    class CTCBeamDecoder:
-        def __init__(self, *a, **k):
-            pass
-    cd.CTCBeamDecoder = CTCBeamDecoder
-    sys.modules['ctcdecode'] = cd
-    torch.clamp_max_ = lambda x, m: torch.clamp_max(x, m)
-    sys.path.insert(0, REF)
-    import nasbench_asr
-    nasbench_asr.set_default_backend('torch')
+    from oracle.reference_shims import import_reference as _imp
+    nasbench_asr = _imp(REF)
     from nasbench_asr.training.torch.encoder import PhonemeEncoder
     return nasbench_asr, PhonemeEncoder
 

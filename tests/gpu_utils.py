@@ -4,13 +4,13 @@ import ctypes as C
 import torch
 
 from nb_asr_b200 import _lib
-from nb_asr_b200._lib import BF16, F32, PAD_L, PAD_R, Epilogue, GConv, Gemm, Wgrad
+from nb_asr_b200._lib import BF16, F16, F32, PAD_L, PAD_R, Epilogue, GConv, Gemm, Wgrad
 
 DEV = 'cuda:0'
 
 
 def tdt(dt):
-    return torch.bfloat16 if dt == BF16 else torch.float32
+    return {BF16: torch.bfloat16, F16: torch.float16}.get(dt, torch.float32)
 
 
 def geo(T):
@@ -51,7 +51,8 @@ def new_mask(rows, Cc, w=32):
 
 
 def epilogue(dt, ld, bias=None, relu=0, drop_p=0.0, salt=0, adds=(), out=None, out_dtype=None, mask_out=None, out2=None,
-             mask2=None, scale2=1.0, mask_w=32, mask2_w=32, accumulate=0):
+             mask2=None, scale2=1.0, mask_w=32, mask2_w=32, accumulate=0, out2_dtype=None, acc_scale=0.0, bias_scale=0.0,
+             relu_hi=0.0):
     e = Epilogue()
     e.bias = bias.data_ptr() if bias is not None else None
     e.relu20, e.drop_p, e.drop_seed, e.drop_step = relu, drop_p, salt, None
@@ -64,7 +65,8 @@ def epilogue(dt, ld, bias=None, relu=0, drop_p=0.0, salt=0, adds=(), out=None, o
     e.ld_out = ld
     e.mask_out = mask_out.data_ptr() if mask_out is not None else None
     e.out2 = out2.data_ptr() if out2 is not None else None
-    e.out2_dtype = dt
+    e.out2_dtype = dt if out2_dtype is None else out2_dtype
+    e.acc_scale, e.bias_scale, e.relu_hi = acc_scale, bias_scale, relu_hi
     e.mask2 = mask2.data_ptr() if mask2 is not None else None
     e.scale2, e.accumulate = scale2, accumulate
     e.mask_w, e.mask2_w = mask_w, mask2_w

@@ -119,8 +119,8 @@ def _gconv_fwd_bwd(dt, op, Cc):
         ne = int(lib.nbasr_gconv_mma_pack_elems(Cc, cpg, k))
         wpk = torch.zeros(ne, dtype=torch.bfloat16, device=U.DEV)
         wpk_t = torch.zeros(ne, dtype=torch.bfloat16, device=U.DEV)
-        _lib.check(lib.nbasr_pack_gconv_mma(wg.data_ptr(), wpk.data_ptr(), Cc, cpg, k, 0, U.stream()))
-        _lib.check(lib.nbasr_pack_gconv_mma(wg.data_ptr(), wpk_t.data_ptr(), Cc, cpg, k, 1, U.stream()))
+        _lib.check(lib.nbasr_pack_gconv_mma(wg.data_ptr(), wpk.data_ptr(), BF16, Cc, cpg, k, 0, U.stream()))
+        _lib.check(lib.nbasr_pack_gconv_mma(wg.data_ptr(), wpk_t.data_ptr(), BF16, Cc, cpg, k, 1, U.stream()))
         gc.w, gc.w_packed = wpk.data_ptr(), 1
     gc.epi = U.epilogue(dt, Cc, bias=bg, relu=1, adds=[sk], out=out, mask_out=mask, mask_w=mwid)
     _lib.check(lib.nbasr_gconv_fwd(C.byref(gc), U.stream()), 'gconv')
@@ -178,12 +178,12 @@ def test_layernorm_fwd_bwd(dt, Cc):
     rstd = torch.zeros(xb.shape[0], device=U.DEV)
     gd, bd = g.detach().to(U.DEV), b.detach().to(U.DEV)
     _lib.check(lib.nbasr_layernorm_fwd(dt, xb.data_ptr(), yb.data_ptr(), B, T, U.geo(T), Cc, gd.data_ptr(), bd.data_ptr(), 1e-3,
-                                       mean.data_ptr(), rstd.data_ptr(), U.stream()))
+                                       mean.data_ptr(), rstd.data_ptr(), 1.0, None, U.stream()))
     tol = 2e-6 if dt == F32 else 4e-3
     assert U.relerr(U.from_padded(yb, B, T).cpu(), y.detach()) < tol
     dyb, dxb = U.to_padded(dy, dt), U.empty_padded(B, T, Cc, dt)
     dg, db = torch.zeros(Cc, device=U.DEV), torch.zeros(Cc, device=U.DEV)
-    _lib.check(lib.nbasr_layernorm_bwd(dt, dyb.data_ptr(), xb.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gd.data_ptr(), B, T,
+    _lib.check(lib.nbasr_layernorm_bwd(dt, dyb.data_ptr(), xb.data_ptr(), dt, 1.0, mean.data_ptr(), rstd.data_ptr(), gd.data_ptr(), B, T,
                                        U.geo(T), Cc, dxb.data_ptr(), None, None, 1.0, 0, 32, dg.data_ptr(), db.data_ptr(), U.stream()))
     torch.cuda.synchronize()
     assert U.relerr(U.from_padded(dxb, B, T).cpu(), gx) < (1e-4 if dt == F32 else 8e-3)
@@ -198,8 +198,83 @@ def test_layernorm_degenerate_rows():
     g = torch.ones(Cc, device=U.DEV)
     b = torch.full((Cc,), 0.25, device=U.DEV)
     _lib.check(lib.nbasr_layernorm_fwd(F32, xb.data_ptr(), yb.data_ptr(), B, T, U.geo(T), Cc, g.data_ptr(), b.data_ptr(), 1e-3,
-                                       None, None, U.stream()))
+                                       None, None, 1.0, None, U.stream()))
     assert torch.allclose(U.from_padded(yb, B, T), torch.full((B, T, Cc), 0.25, device=U.DEV))
+
+
+@pytest.mark.parametrize('Cc', [600, 800, 1000, 1200])
+def test_layernorm_scaled_fp16_activations(Cc):
+    """16-bit mode: x is fp16 holding S*x_true.  With eps*S^2 the normalised value is that of the unscaled tensor; the output is
+    written scaled (fp16) plus an unscaled bf16 twin; the backward pass (bf16 gradients) returns d/dx_true."""
+    from nb_asr_b200._lib import F16
+    S = 32.0
+    torch.manual_seed(7)
+    B, T = 3, 70
+    x = ((torch.randn(B, T, Cc) * 2 + 0.5) * S).half().float() / S             # exactly representable as scaled fp16
+    x.requires_grad_(True)
+    g = (torch.randn(Cc) * 0.2 + 1).requires_grad_(True)
+    b = (torch.randn(Cc) * 0.1).requires_grad_(True)
+    y = F.layer_norm(x, (Cc,), g, b, 1e-3)
+    dy = torch.randn_like(y).bfloat16().float()
+    gx, gg, gb = torch.autograd.grad(y, (x, g, b), dy)
+    lib = _lib.load()
+    xb = U.to_padded(x.detach() * S, F16)
+    yb, y2 = U.empty_padded(B, T, Cc, F16), U.empty_padded(B, T, Cc, BF16)
+    mean, rstd = torch.zeros(xb.shape[0], device=U.DEV), torch.zeros(xb.shape[0], device=U.DEV)
+    gd, bd = g.detach().to(U.DEV), b.detach().to(U.DEV)
+    _lib.check(lib.nbasr_layernorm_fwd(F16, xb.data_ptr(), yb.data_ptr(), B, T, U.geo(T), Cc, gd.data_ptr(), bd.data_ptr(), 1e-3 * S * S,
+                                       mean.data_ptr(), rstd.data_ptr(), S, y2.data_ptr(), U.stream()))
+    assert U.relerr(U.from_padded(yb, B, T).cpu() / S, y.detach()) < 6e-4         # fp16 output rounding (2^-11)
+    assert U.relerr(U.from_padded(y2, B, T).cpu(), y.detach()) < 4e-3            # bf16 twin
+    dyb, dxb = U.to_padded(dy, BF16), U.empty_padded(B, T, Cc, BF16)
+    dg, db = torch.zeros(Cc, device=U.DEV), torch.zeros(Cc, device=U.DEV)
+    _lib.check(lib.nbasr_layernorm_bwd(BF16, dyb.data_ptr(), xb.data_ptr(), F16, S, mean.data_ptr(), rstd.data_ptr(), gd.data_ptr(), B, T,
+                                       U.geo(T), Cc, dxb.data_ptr(), None, None, 1.0, 0, 32, dg.data_ptr(), db.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    assert U.relerr(U.from_padded(dxb, B, T).cpu(), gx) < 8e-3
+    assert U.relerr(dg.cpu(), gg) < 1e-4 and U.relerr(db.cpu(), gb) < 1e-4
+
+
+@pytest.mark.parametrize('op', ['conv5', 'conv7d2'])
+@pytest.mark.parametrize('Cc', [600, 1000])
+def test_gconv_scaled_fp16_forward(op, Cc):
+    """16-bit mode forward edge: fp16 activations holding S*x, fp16 block-diagonal weights, epilogue in the scaled domain
+    (bias * S, ReLU bound 20 * S, scaled skip tensor), scaled fp16 output plus the unscaled bf16 twin (out2)."""
+    from nb_asr_b200._lib import F16
+    S = 32.0
+    torch.manual_seed(2)
+    k, d = M.CONV_EDGE[op]
+    B, T, cpg = 3, 300, Cc // 100
+    h = lambda t: t.half().float()
+    x = h(torch.randn(B, T, Cc) * S) / S
+    w = h(torch.randn(Cc, cpg, k) * 0.3)
+    bias = torch.randn(Cc) * 0.1
+    skip = h(torch.randn(B, T, Cc) * S) / S
+    lp, rp = pad_rule(k, d, 1)
+    z = F.conv1d(F.pad(x.permute(0, 2, 1), (lp, rp)), w, bias, dilation=d, groups=100).permute(0, 2, 1)
+    ref = M.relu20(z) + skip
+    lib = _lib.load()
+    xb, sk = U.to_padded(x * S, F16), U.to_padded(skip * S, F16)
+    out, out2 = U.empty_padded(B, T, Cc, F16), U.empty_padded(B, T, Cc, BF16)
+    mwid = 40 if cpg == 10 else 48
+    mask = U.new_mask(out.shape[0], Cc, mwid)
+    wg, bg = w.to(U.DEV), bias.to(U.DEV)
+    ne = int(lib.nbasr_gconv_mma_pack_elems(Cc, cpg, k))
+    wpk = torch.zeros(ne, dtype=torch.float16, device=U.DEV)
+    _lib.check(lib.nbasr_pack_gconv_mma(wg.data_ptr(), wpk.data_ptr(), F16, Cc, cpg, k, 0, U.stream()))
+    for with_skip in (True, False):           # general epilogue path / lean path
+        gc = GConv()
+        gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg, gc.ktaps, gc.off0, gc.dstep = F16, xb.data_ptr(), B, T, U.geo(T), Cc, cpg, k, -lp, d
+        gc.w, gc.w_packed = wpk.data_ptr(), 1
+        gc.epi = U.epilogue(F16, Cc, bias=bg, relu=1, adds=[sk] if with_skip else [], out=out, mask_out=mask, mask_w=mwid, out2=out2,
+                            out2_dtype=BF16, scale2=1.0 / S, bias_scale=S, relu_hi=20.0 * S)
+        _lib.check(lib.nbasr_gconv_fwd(C.byref(gc), U.stream()), 'gconv f16')
+        torch.cuda.synchronize()
+        r = ref if with_skip else M.relu20(z)
+        assert U.relerr(U.from_padded(out, B, T).cpu() / S, r) < 6e-4
+        assert U.relerr(U.from_padded(out2, B, T).cpu(), r) < 4e-3
+        assert (U.unpack_mask(mask, B, T, Cc, mwid).cpu() != ((z > 0) & (z <= 20))).float().mean() < 1e-3
+        assert float(out[:PAD_L].abs().sum()) == 0.0
 
 
 @pytest.mark.parametrize('B,T', [(3, 9), (20, 6), (64, 4)])

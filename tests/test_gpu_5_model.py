@@ -28,7 +28,7 @@ def rel64(a, b):
 # the elements whose pre-activation is ~0; each flip switches a gradient term on/off, so a weight-gradient
 # (a random-sign sum) moves by ~sqrt(f) ~ 1e-3..1e-2 relative.  Direction and global norm are pinned tightly.
 GRAD_TOL = 2e-2
-BF16_LOGIT_TOL = 4e-2
+BF16_LOGIT_TOL = 2e-2          # north_star: logits within 2e-2 relative in the 16-bit mode
 
 
 def check_grads(model, raw, total):
@@ -135,10 +135,9 @@ def test_bf16_forward_within_tolerance(name, golden_meta):
     with torch.no_grad():
         logits = model(audio.to(DEV))
     ref = torch.from_numpy(g['logits'])
-    # north_star asks 2e-2 relative in bf16.  The CTC loss meets it with two orders of margin; for the logits
-    # the bound that bf16 storage of every activation can meet on this 80-layer net is BF16_LOGIT_TOL: rounding
-    # the reference's OWN activations/operands to bf16 on the CPU gives 2.1e-2 (conv archs) .. 3.7e-2 (all-linear)
-    # (DESIGN.md "Precision"), and we sit on those figures to 2 digits.
+    # north_star asks 2e-2 relative in the 16-bit mode.  bf16 storage of every activation cannot meet it on this 80-layer
+    # net (rounding the reference's OWN activations / operands to bf16 on the CPU gives 2.1e-2 .. 3.7e-2), so
+    # forward activations and their weight operands are fp16 (scaled by 32), gradients bf16: 0.4e-2 .. 1.0e-2 simulated.
     assert rel64(logits, ref) < BF16_LOGIT_TOL, rel64(logits, ref)
     tr = trainer(model)
     loss, logp, out_len = tr.step(((audio, alen), (tg, tl)), training=False)
@@ -252,8 +251,7 @@ def test_gradient_buckets_partition_the_backward_pass(arch):
     (audio, alen), (tg, tl) = nb.data.make_batch(4, 200, seed=3, min_len=120)
     tr = trainer(model)
     pl = eng.forward(audio.to(DEV), training=True)
-    from nb_asr_b200.trainer import _ws
-    ws = _ws.get(torch.device(DEV), 4, pl.Tq, pl.V, tg.shape[1])
+    ws = tr._plan_ws(pl, torch.device(DEV), 4, tg.shape[1])
     tr._ctc(eng, pl, tg.to(DEV).int().contiguous(), alen.to(DEV), tl.to(DEV), True, ws)
     marks = [m for m, _, _ in pl.buckets]
     assert marks == sorted(marks) and marks[-1] == len(pl.bwd) and len(marks) == 5

@@ -5,7 +5,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-from nb_asr_b200._lib import BF16, F32, PAD_L  # noqa: E402
+from nb_asr_b200._lib import BF16, F16, F32, PAD_L  # noqa: E402
 from nb_asr_b200.model import pad_rule  # noqa: E402
 from oracle import model_ref as M  # noqa: E402
 import gpu_utils as U  # noqa: E402
@@ -56,6 +56,43 @@ def test_gemm_tn_conv_epilogue(stride):
     m = U.unpack_mask(mask, B, To, Cout).cpu()
     exp = (z > 0) & (z <= 20)
     assert (m != exp).float().mean() < 1e-4                    # accumulation-order ties at z ~ 0 only
+
+
+@pytest.mark.parametrize('stride', [1, 2])
+def test_gemm_tn_scaled_fp16_forward(stride):
+    """16-bit mode forward GEMM: fp16 operands (activations hold S*x), scaled-domain epilogue, fp16 output + bf16 twin; and the
+    un-scaling epilogue (acc_scale = 1/S, fp32 output) the LSTM input projection uses."""
+    torch.manual_seed(11)
+    S = 32.0
+    h = lambda t: t.half().float()
+    B, T, Cin, Cout = 3, 300, 80, 600
+    x = h(torch.randn(B, T, Cin) * S) / S
+    w = h(torch.randn(Cout, Cin, 8) * 0.05)
+    bias = torch.randn(Cout) * 0.5
+    To = (T + stride - 1) // stride
+    skip = h(torch.randn(B, To, Cout) * S) / S
+    z = F.conv1d(F.pad(x.permute(0, 2, 1), pad_rule(8, 1, stride)), w, bias, stride=stride).permute(0, 2, 1)
+    ref = M.relu20(z) + skip
+    xb = U.to_padded(x * S, F16)
+    wp = w.permute(0, 2, 1).contiguous().view(Cout, 8 * Cin).half().to(U.DEV)
+    out, out2 = U.empty_padded(B, To, Cout, F16), U.empty_padded(B, To, Cout, BF16)
+    sk = U.to_padded(skip * S, F16)
+    mask = U.new_mask(out.shape[0], Cout)
+    lpad, _ = pad_rule(8, 1, stride)
+    epi = U.epilogue(F16, Cout, bias=bias.to(U.DEV), relu=1, adds=[sk], out=out, mask_out=mask, out2=out2, out2_dtype=BF16,
+                     scale2=1.0 / S, bias_scale=S, relu_hi=20.0 * S)
+    U.run_gemm(F16, U.ptr(xb, (PAD_L - lpad) * Cin), U.geo(T) * Cin, stride * Cin, B, To, 8 * Cin, Cout, wp, 8 * Cin, PAD_L,
+               U.geo(To), 1, epi)
+    assert U.relerr(U.from_padded(out, B, To).cpu() / S, ref) < 6e-4          # fp16 output rounding only
+    assert U.relerr(U.from_padded(out2, B, To).cpu(), ref) < 4e-3             # bf16 twin
+    m = U.unpack_mask(mask, B, To, Cout).cpu()
+    assert (m != ((z > 0) & (z <= 20))).float().mean() < 1e-4
+    # un-scaling epilogue: fp32 output of true values
+    o32 = U.empty_padded(B, To, Cout, F32)
+    epi = U.epilogue(F16, Cout, bias=bias.to(U.DEV), out=o32, out_dtype=F32, acc_scale=1.0 / S)
+    U.run_gemm(F16, U.ptr(xb, (PAD_L - lpad) * Cin), U.geo(T) * Cin, stride * Cin, B, To, 8 * Cin, Cout, wp, 8 * Cin, PAD_L,
+               U.geo(To), 1, epi)
+    assert U.relerr(U.from_padded(o32, B, To).cpu(), z) < 1e-5
 
 
 @pytest.mark.parametrize('nb,nr,M_,N,ldx', [(1, 64, 128, 256, 256), (2, 100, 64, 64, 64), (4, 500, 600, 640, 640),

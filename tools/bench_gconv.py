@@ -20,7 +20,7 @@ for Cc, k, d in ((1000, 5, 1), (600, 5, 1), (1200, 7, 2)):
     bias = torch.randn(Cc, device=U.DEV)
     ne = int(lib.nbasr_gconv_mma_pack_elems(Cc, cpg, k))
     wp = torch.zeros(ne, dtype=torch.bfloat16, device=U.DEV)
-    _lib.check(lib.nbasr_pack_gconv_mma(w.data_ptr(), wp.data_ptr(), Cc, cpg, k, 0, U.stream()))
+    _lib.check(lib.nbasr_pack_gconv_mma(w.data_ptr(), wp.data_ptr(), BF16, Cc, cpg, k, 0, U.stream()))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=U.DEV)
     variants = {
         'fwd: bias+relu+out+mask': dict(bias=bias, relu=1, out=out, mask_out=mask, mask_w=mwid),

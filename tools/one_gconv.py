@@ -17,7 +17,7 @@ w = torch.randn(Cc, cpg, k, device=U.DEV) * 0.3
 bias = torch.randn(Cc, device=U.DEV)
 ne = int(lib.nbasr_gconv_mma_pack_elems(Cc, cpg, k))
 wp = torch.zeros(ne, dtype=torch.bfloat16, device=U.DEV)
-_lib.check(lib.nbasr_pack_gconv_mma(w.data_ptr(), wp.data_ptr(), Cc, cpg, k, 0, U.stream()))
+_lib.check(lib.nbasr_pack_gconv_mma(w.data_ptr(), wp.data_ptr(), BF16, Cc, cpg, k, 0, U.stream()))
 gc = GConv()
 gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg, gc.ktaps, gc.off0, gc.dstep = BF16, x.data_ptr(), B, T, U.geo(T), Cc, cpg, k, 0 if d == 1 else -8, d
 gc.w, gc.w_packed = wp.data_ptr(), 1

@@ -20,9 +20,9 @@ for Cc in ((800,) if once else (600, 800, 1000, 1200)):
     mwid = 40 if Cc == 1000 else 48
     mask = U.new_mask(x.shape[0], Cc, mwid)
     mask.random_(0, 255)
-    fwd = lambda: lib.nbasr_layernorm_fwd(BF16, x.data_ptr(), y.data_ptr(), B, T, U.geo(T), Cc, g.data_ptr(), b.data_ptr(), 1e-3, mean.data_ptr(), rstd.data_ptr(), U.stream())
-    bwd1 = lambda: lib.nbasr_layernorm_bwd(BF16, dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g.data_ptr(), B, T, U.geo(T), Cc, dx.data_ptr(), None, None, 1.0, 0, 32, dg.data_ptr(), db.data_ptr(), U.stream())
-    bwd2 = lambda: lib.nbasr_layernorm_bwd(BF16, dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g.data_ptr(), B, T, U.geo(T), Cc, dx.data_ptr(), dx2.data_ptr(), mask.data_ptr(), 1.0, mask.shape[1], mwid, dg.data_ptr(), db.data_ptr(), U.stream())
+    fwd = lambda: lib.nbasr_layernorm_fwd(BF16, x.data_ptr(), y.data_ptr(), B, T, U.geo(T), Cc, g.data_ptr(), b.data_ptr(), 1e-3, mean.data_ptr(), rstd.data_ptr(), 1.0, None, U.stream())
+    bwd1 = lambda: lib.nbasr_layernorm_bwd(BF16, dy.data_ptr(), x.data_ptr(), BF16, 1.0, mean.data_ptr(), rstd.data_ptr(), g.data_ptr(), B, T, U.geo(T), Cc, dx.data_ptr(), None, None, 1.0, 0, 32, dg.data_ptr(), db.data_ptr(), U.stream())
+    bwd2 = lambda: lib.nbasr_layernorm_bwd(BF16, dy.data_ptr(), x.data_ptr(), BF16, 1.0, mean.data_ptr(), rstd.data_ptr(), g.data_ptr(), B, T, U.geo(T), Cc, dx.data_ptr(), dx2.data_ptr(), mask.data_ptr(), 1.0, mask.shape[1], mwid, dg.data_ptr(), db.data_ptr(), U.stream())
     el = B * T * Cc * 2
     for name, fn, passes in (('fwd', fwd, 2), ('bwd dx', bwd1, 3), ('bwd dx+dx2', bwd2, 4)):
         ts = []

@@ -252,8 +252,10 @@ int nbasr_beam_per(const float* logp, int B, int T, int V, const int64_t* audio_
  * PadConvRelu weights (segments), clip_grad_norm_(5), Adam(eps=1e-7).  Flat fp32 buffers of n
  * elements.  seg_off/seg_len (nseg, int64, device) delimit the regularised tensors.
  * seg_chunks = sum_s ceil(seg_len[s]/16384) (grid size of the per-segment kernels).
- * state: [0]=step count (as float), [1]=lr, [2]=sum of squares scratch, [3]=clip coef,
- *        [4..4+nseg) per-segment sum of squares.  All on device, so the step is graph-replayable. */
+ * state: [0]=step count (as float), [1]=lr, [2]=||grad||^2, [3]=clip coef, [4..4+nseg) per-segment ||W||^2, then
+ *        scratch from [8+nseg): 592 + seg_chunks per-block partial sums -> 8 + nseg + 592 + seg_chunks floats in all.
+ *        All on device, so the step is graph-replayable.  Reductions are deterministic (partials summed in a fixed
+ *        order): replicas fed the same all-reduced gradient stay bit-identical. */
 int nbasr_optim_step(float* param, float* grad, float* m, float* v, int64_t n, const int64_t* seg_off,
                      const int64_t* seg_len, int nseg, int64_t seg_chunks, float reg_coef, float max_norm,
                      float beta1, float beta2, float eps, float* state, void* stream);

@@ -98,6 +98,11 @@ __device__ __forceinline__ void store8_dt(void* base, int dtype, int64_t idx, co
   else if (dtype == NBASR_F16) store8(reinterpret_cast<f16*>(base) + idx, v);
   else store8(reinterpret_cast<float*>(base) + idx, v);
 }
+// 16 bytes of a 16-bit tensor (dtype BF16 or F16) -> 8 values
+__device__ __forceinline__ void load8_h(const void* p, int dtype, float* v) {
+  if (dtype == NBASR_F16) load8(reinterpret_cast<const f16*>(p), v);
+  else load8(reinterpret_cast<const bf16*>(p), v);
+}
 // 8 values -> 16 bytes of a 16-bit tensor (dtype BF16 or F16) at a shared / global address
 __device__ __forceinline__ void store8_h(void* p, int dtype, const float* v) {
   if (dtype == NBASR_F16) store8(reinterpret_cast<f16*>(p), v);
@@ -154,7 +159,8 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
 // are plane-major bit arrays (mask_byte_addr): any 8-aligned column range is whole bytes of one entry.
 // ---------------------------------------------------------------------------------------------
 // compute half: bias, ReLU20 (+ gate bits), dropout, skip-sum.  m[g] = gate bits of column group g.
-template <int NV, bool FULL = false, bool NOBIAS = false>
+// NOADD: the caller sums the skip tensors itself (the GEMM kernel stages them through shared memory with TMA).
+template <int NV, bool FULL = false, bool NOBIAS = false, bool NOADD = false>
 __device__ __forceinline__ void epilogue_compute(const nbasr_epilogue& e, int64_t rho, int c0, int nvalid_, float* v, uint32_t* m) {
   constexpr int NG = NV / 8;
   const int nvalid = FULL ? NV : nvalid_;   // FULL: every column valid -> all guards fold at compile time
@@ -199,7 +205,7 @@ __device__ __forceinline__ void epilogue_compute(const nbasr_epilogue& e, int64_
       v[i] = keep ? v[i] * scale : 0.f;
     }
   }
-  for (int a = 0; a < e.n_add; ++a) {
+  for (int a = 0; a < (NOADD ? 0 : e.n_add); ++a) {
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       if (g * 8 < nvalid) {

@@ -34,9 +34,17 @@ constexpr int B_STAGE_BYTES = 128 * BK * 2;         // up to BN/2 = 128 rows: 16
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int THREADS = 320;
+// Staged epilogue (16-bit outputs): every epilogue warp owns 8 KB of shared memory -- out box | out2 box | two skip-operand
+// boxes, each 32 rows x 32 columns x 2 B in the 64-byte-swizzled TMA layout.  Skip tensors arrive by TMA load, results leave by
+// TMA store: full 64-byte row segments instead of 16 bytes per thread and row (the per-thread path moves half-used 32-byte
+// sectors, which made `linear` edges with skips and the bf16 twin memory-bound at ~0.3 of the tensor peak).
+constexpr int ST_STAGES = 5;                        // 5 x 32 KB ring + 64 KB staging
+constexpr int ST_WARP_BYTES = 8192;
+constexpr int ST_BOX_BYTES = 2048;
+constexpr int ST_SMEM_BYTES = ST_STAGES * STAGE_BYTES + 8 * ST_WARP_BYTES + 1024 + 256;
 
 struct Args {
-  int nb, nr, K, N, BN, f16;
+  int nb, nr, K, N, BN, f16, n_add_staged;
   int mt_per_utt, m_tiles, n_tiles, pair_tiles;
   int64_t o_r0, o_bs, o_rs;
   nbasr_epilogue epi;
@@ -103,17 +111,26 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {
                : "memory");
 }
 
+struct StMaps {      // tensor maps of the staged epilogue: out, out2, up to three skip tensors (all the same geometry)
+  CUtensorMap o, o2, a0, a1, a2;
+};
+
+template <bool STAGED>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args p) {
+gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ StMaps sm,
+                    const Args p) {
+  constexpr int STAGES = STAGED ? ST_STAGES : ::STAGES;
+  constexpr int STG_BYTES = STAGED ? 8 * ST_WARP_BYTES : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES + STG_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  auto add_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4 + w); };      // one per epilogue warp (staged)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + STAGES * STAGE_BYTES + STG_BYTES + 8 * (2 * STAGES + 4 + 8));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,6 +149,10 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 16);    // 8 epilogue warps x 2 CTAs (used in the leader only)
+    }
+    if (STAGED) {
+      prefetch_tmap(&sm.o);
+      for (int w = 0; w < 8; ++w) mbar_init(add_bar(w), 1);
     }
     fence_barrier_init();
   }
@@ -197,10 +218,19 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     const int q = warp & 3;           // TMEM lane quadrant this warp may access
     const int hh = (warp - 2) >> 2;   // the two warps of a quadrant take alternate 32-column chunks
+    // staged epilogue state (see ST_* above): this warp's four 2 KB boxes and its skip-operand barrier
+    const int ew = warp - 2;
+    uint8_t* stg = smem_al + STAGES * STAGE_BYTES + ew * ST_WARP_BYTES;
+    const uint32_t stg_u = smem_base + STAGES * STAGE_BYTES + ew * ST_WARP_BYTES;
+    const uint32_t abar = add_bar(ew);
+    uint32_t aphase = 0;
+    const int na = p.n_add_staged;
+    // byte offset of 16-byte chunk j of this lane's row inside a 64-byte-swizzled 32 x 32 box (bits 4-5 ^= bits 7-8)
+    const int sw_row = lane * 64, sw_x = (lane >> 1) & 3;
     int it = 0;
     for (int pt = pair_id; pt < p.pair_tiles; pt += npairs, ++it) {
       const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const uint32_t aphase_t = (it >> 1) & 1;
       const int n_idx = pt % p.n_tiles;
       const int m_raw = 2 * (pt / p.n_tiles) + (int)rank;
       const int m_idx = min(m_raw, p.m_tiles - 1);
@@ -208,19 +238,122 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int r = r0 + q * 32 + lane;
       const int n0 = n_idx * p.BN;
       const int ncol = min(p.N, n0 + p.BN);
-      mbar_wait(tfull_bar(as), aphase);
-      tcgen05_fence_after();
       const int64_t rho = p.o_r0 + (int64_t)b * p.o_bs + (int64_t)r * p.o_rs;
-      for (int c = 32 * hh; c < p.BN; c += 64) {
-        if (n0 + c >= ncol) break;   // warp-uniform
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + c, v);
-        if (r < p.nr && m_raw < p.m_tiles) epilogue_chunk(p.epi, rho, n0 + c, ncol, v);
+      if (!STAGED) {
+        mbar_wait(tfull_bar(as), aphase_t);
+        tcgen05_fence_after();
+        for (int c = 32 * hh; c < p.BN; c += 64) {
+          if (n0 + c >= ncol) break;   // warp-uniform
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + c, v);
+          if (r < p.nr && m_raw < p.m_tiles) epilogue_chunk(p.epi, rho, n0 + c, ncol, v);
+        }
+      } else {
+        const nbasr_epilogue& e = p.epi;
+        const int rbox = r0 + q * 32;                                   // first row of this warp's 32-row box
+        const bool box_ok = m_raw < p.m_tiles && rbox < p.nr;           // warp-uniform
+        auto load_adds = [&](int c) {                                    // skip operands of chunk c -> shared memory
+          if (box_ok && na > 0 && lane == 0 && c < p.BN && n0 + c < ncol) {   // (only chunks that will be processed)
+            mbar_expect_tx(abar, ST_BOX_BYTES * min(na, 2));
+            tma_load_3d(stg_u + 2 * ST_BOX_BYTES, &sm.a0, abar, n0 + c, rbox, b);
+            if (na > 1) tma_load_3d(stg_u + 3 * ST_BOX_BYTES, &sm.a1, abar, n0 + c, rbox, b);
+          }
+        };
+        load_adds(32 * hh);                   // before the accumulator wait: the load overlaps the tile's last MMAs
+        mbar_wait(tfull_bar(as), aphase_t);
+        tcgen05_fence_after();
+        for (int c = 32 * hh; c < p.BN; c += 64) {
+          if (n0 + c >= ncol) break;   // warp-uniform
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + c, v);
+          if (box_ok) {
+            const int nvalid = min(32, ncol - (n0 + c));
+            uint32_t m[4];
+            if (nvalid == 32) epilogue_compute<32, true, false, true>(e, rho, n0 + c, 32, v, m);
+            else epilogue_compute<32, false, false, true>(e, rho, n0 + c, nvalid, v, m);
+            if (na > 0) {
+              mbar_wait(abar, aphase);
+              aphase ^= 1;
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                if (a < na) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float t[8];
+                    load8_h(stg + (2 + a) * ST_BOX_BYTES + sw_row + ((j ^ sw_x) << 4), e.add_dtype, t);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[j * 8 + i] += t[i];
+                  }
+                }
+              }
+              if (na > 2) {                     // third skip tensor: through the first box once everyone has read it
+                __syncwarp();
+                if (lane == 0) {
+                  mbar_expect_tx(abar, ST_BOX_BYTES);
+                  tma_load_3d(stg_u + 2 * ST_BOX_BYTES, &sm.a2, abar, n0 + c, rbox, b);
+                }
+                mbar_wait(abar, aphase);
+                aphase ^= 1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float t[8];
+                  load8_h(stg + 2 * ST_BOX_BYTES + sw_row + ((j ^ sw_x) << 4), e.add_dtype, t);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[j * 8 + i] += t[i];
+                }
+              }
+              __syncwarp();
+              load_adds(c + 64);      // next chunk's skip operands
+            }
+            // gate bits of the second output (backward: dZ of the previous node), one byte per 8 columns
+            uint32_t w2[4] = {0xffu, 0xffu, 0xffu, 0xffu};
+            if (e.out2 && e.mask2 && r < p.nr) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if (g * 8 < nvalid) w2[g] = reinterpret_cast<const uint8_t*>(e.mask2)[mask_byte_addr(rho, n0 + c + g * 8, e.mask2_w, e.mask_rows)];
+            }
+            // the previous chunk's TMA stores must have finished READING the boxes before they are overwritten
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int off = sw_row + ((j ^ sw_x) << 4);
+              if (e.out) store8_h(stg + off, e.out_dtype, v + j * 8);
+              if (e.out2) {
+                float t2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t2[i] = ((w2[j] >> i) & 1u) ? v[j * 8 + i] * e.scale2 : 0.f;
+                store8_h(stg + ST_BOX_BYTES + off, e.out2_dtype, t2);
+              }
+            }
+            if (e.mask_out && r < p.nr) {
+              uint8_t* mo = reinterpret_cast<uint8_t*>(e.mask_out);
+              if (e.mask_w == 32 && ((n0 + c) & 31) == 0) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) word |= (g * 8 < nvalid ? m[g] : 0u) << (8 * g);
+                *reinterpret_cast<uint32_t*>(mo + mask_byte_addr(rho, n0 + c, 32, e.mask_rows)) = word;
+              } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  if (g * 8 < nvalid) mo[mask_byte_addr(rho, n0 + c + g * 8, e.mask_w, e.mask_rows)] = static_cast<uint8_t>(m[g]);
+              }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {                   // rows >= nr and columns >= N are clipped by the tensor map
+              if (e.out) tma_store_3d(&sm.o, stg_u, n0 + c, rbox, b);
+              if (e.out2) tma_store_3d(&sm.o2, stg_u + ST_BOX_BYTES, n0 + c, rbox, b);
+              bulk_commit();
+            }
+          }
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
     }
+    if (STAGED && lane == 0) bulk_wait0();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -388,6 +521,36 @@ int pick_bn_pair(int N, int m_tiles, int pairs) {
 
 }  // namespace
 
+// persistent pairs: never launch more clusters than can be co-resident (a second wave would double the time)
+template <bool STAGED>
+static int max_resident_pairs(int smem_bytes, cudaStream_t st) {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!cached[dev]) {
+    const int sms = nbasr_sm_count();
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3(sms);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tn_pair_kernel<STAGED>, &cfg) != cudaSuccess || n < 1) n = sms / 2;
+    cached[dev] = std::min(n, sms / 2);
+    if (nbasr_env_flag(NBASR_ENV_DEBUG))
+      fprintf(stderr, "[nbasr] gemm_tn_pair<%d>: %d co-resident CTA pairs on %d SMs\n", (int)STAGED, cached[dev], sms);
+  }
+  return cached[dev];
+}
+
 int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
   NBASR_REQUIRE(g->K % 8 == 0, "K must keep 16-byte row alignment");
   Args a{};
@@ -411,35 +574,52 @@ int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
   int64_t sb[2] = {1, g->ldw};
   uint32_t bb[2] = {BK, (uint32_t)(a.BN / 2)};
   if (sm100_get_map(g->w, 2, db, sb, bb, &tmB)) return 1;
-  static DevOnce attr;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return nbasr_fail("gemm_tn_pair smem attr: %s", cudaGetErrorString(e));
-    attr = true;
+
+  // Staged (TMA) epilogue: every tensor the epilogue touches row-wise is 16-bit with a 16-byte-aligned pitch.
+  const nbasr_epilogue& e = g->epi;
+  const int64_t ld = e.ld_out;
+  auto h16 = [](int dt) { return dt == NBASR_BF16 || dt == NBASR_F16; };
+  auto al16p = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  bool staged = !nbasr_env_flag(NBASR_ENV_GEMM_DIRECT_EPI) && (e.out || e.out2) && !e.accumulate && ld % 8 == 0 &&
+                (!e.out || (h16(e.out_dtype) && al16p(e.out))) && (!e.out2 || (h16(e.out2_dtype) && al16p(e.out2))) &&
+                (e.n_add == 0 || h16(e.add_dtype)) && g->o_rs >= 1 && g->o_bs >= 0;
+  for (int i = 0; i < e.n_add; ++i) staged = staged && al16p(e.add[i]);
+  StMaps sm{};
+  if (staged) {
+    uint64_t dd[3] = {(uint64_t)g->N, (uint64_t)g->nr, (uint64_t)g->nb};
+    int64_t sd[3] = {1, g->o_rs * ld, std::max<int64_t>(g->o_bs, 1) * ld};
+    uint32_t bx[3] = {32, 32, 1};
+    const int64_t off = g->o_r0 * ld * 2;      // bytes: all staged tensors are 16-bit
+    auto at = [&](const void* p) { return reinterpret_cast<const char*>(p) + off; };
+    const void* any = e.out ? e.out : e.out2;
+    if (sm100_get_map(at(e.out ? e.out : any), 3, dd, sd, bx, &sm.o, 2)) return 1;
+    if (sm100_get_map(at(e.out2 ? e.out2 : any), 3, dd, sd, bx, &sm.o2, 2)) return 1;
+    if (sm100_get_map(at(e.n_add > 0 ? e.add[0] : any), 3, dd, sd, bx, &sm.a0, 2)) return 1;
+    if (sm100_get_map(at(e.n_add > 1 ? e.add[1] : any), 3, dd, sd, bx, &sm.a1, 2)) return 1;
+    if (sm100_get_map(at(e.n_add > 2 ? e.add[2] : any), 3, dd, sd, bx, &sm.a2, 2)) return 1;
+    a.n_add_staged = e.n_add;
   }
-  // persistent pairs: never launch more clusters than can be co-resident (a second wave would double the time)
-  static int max_pairs = 0;
-  if (!max_pairs) {
-    cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cfg.gridDim = dim3(sms);
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_tn_pair_kernel, &cfg) != cudaSuccess || n < 1) n = sms / 2;
-    max_pairs = std::min(n, sms / 2);
-    if (nbasr_env_flag(NBASR_ENV_DEBUG)) fprintf(stderr, "[nbasr] gemm_tn_pair: %d co-resident CTA pairs on %d SMs\n", max_pairs, sms);
+  cudaError_t err;
+  if (staged) {
+    static DevOnce attr;
+    if (!attr) {
+      cudaError_t e2 = cudaFuncSetAttribute(gemm_tn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES);
+      if (e2 != cudaSuccess) return nbasr_fail("gemm_tn_pair<staged> smem attr: %s", cudaGetErrorString(e2));
+      attr = true;
+    }
+    const int npairs = std::max(1, std::min(a.pair_tiles, max_resident_pairs<true>(ST_SMEM_BYTES, st)));
+    err = launch_pdl(gemm_tn_pair_kernel<true>, dim3(2 * npairs), dim3(THREADS), (size_t)ST_SMEM_BYTES, st, 2, tmA, tmB, sm, a);
+  } else {
+    static DevOnce attr;
+    if (!attr) {
+      cudaError_t e2 = cudaFuncSetAttribute(gemm_tn_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (e2 != cudaSuccess) return nbasr_fail("gemm_tn_pair smem attr: %s", cudaGetErrorString(e2));
+      attr = true;
+    }
+    const int npairs = std::max(1, std::min(a.pair_tiles, max_resident_pairs<false>(SMEM_BYTES, st)));
+    err = launch_pdl(gemm_tn_pair_kernel<false>, dim3(2 * npairs), dim3(THREADS), (size_t)SMEM_BYTES, st, 2, tmA, tmB, sm, a);
   }
-  const int npairs = std::max(1, std::min(a.pair_tiles, max_pairs));
-  cudaError_t e = launch_pdl(gemm_tn_pair_kernel, dim3(2 * npairs), dim3(THREADS), (size_t)SMEM_BYTES, st, 2, tmA, tmB, a);
-  if (e != cudaSuccess) return nbasr_fail("gemm_tn_pair launch: %s", cudaGetErrorString(e));
+  if (err != cudaSuccess) return nbasr_fail("gemm_tn_pair launch: %s", cudaGetErrorString(err));
   return 0;
 }
 

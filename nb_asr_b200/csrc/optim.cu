@@ -3,7 +3,9 @@
 //   coef = min(1, max_norm / (||grad||_2 + 1e-6))   (torch.nn.utils.clip_grad_norm_),
 //   Adam(betas, eps) with bias correction (torch.optim.Adam, amsgrad=False, weight_decay=0).
 // Step count, lr and every reduction result live in a small device `state` array, so the whole
-// step replays inside a CUDA graph.
+// step replays inside a CUDA graph.  Every reduction is DETERMINISTIC (per-block partials summed in a fixed order, no
+// float atomics): data-parallel replicas that receive the same all-reduced gradient must compute bit-identical clip
+// coefficients and updates, or they drift apart.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -37,8 +39,10 @@ __device__ __forceinline__ bool seg_locate(const int64_t* __restrict__ len, int 
 // (the segment bases are 16-byte aligned in the engine's flat buffer; the scalar loops handle any other caller and the tails)
 __device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+constexpr int SUMSQ_BLOCKS = 592;
+
 __global__ void seg_sumsq_kernel(const float* __restrict__ p, const int64_t* __restrict__ off, const int64_t* __restrict__ len,
-                                 int nseg, float* __restrict__ state) {
+                                 int nseg, float* __restrict__ part) {
   int s; int64_t start;
   if (!seg_locate(len, nseg, blockIdx.x, s, start)) return;
   const float* x = p + off[s] + start;
@@ -55,7 +59,27 @@ __global__ void seg_sumsq_kernel(const float* __restrict__ p, const int64_t* __r
   }
   for (int i = i0 + threadIdx.x; i < n; i += blockDim.x) acc += x[i] * x[i];
   acc = block_sum(acc);
-  if (threadIdx.x == 0 && acc != 0.f) atomicAdd(state + 4 + s, acc);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// block s: state[4 + s] = sum of the chunk partials of segment s, in chunk order
+__global__ void seg_reduce_kernel(const float* __restrict__ part, const int64_t* __restrict__ len, int nseg, float* __restrict__ state) {
+  const int s = blockIdx.x;
+  int64_t first = 0;
+  for (int i = 0; i < s; ++i) first += (len[i] + SEG_CHUNK - 1) / SEG_CHUNK;
+  const int nch = (int)((len[s] + SEG_CHUNK - 1) / SEG_CHUNK);
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nch; i += blockDim.x) acc += part[first + i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) state[4 + s] = acc;
+}
+
+// state[2] = sum of n per-block partials, fixed order
+__global__ void total_reduce_kernel(const float* __restrict__ part, int n, float* __restrict__ state) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) state[2] = acc;
 }
 
 // g += k W for one chunk of a regularised segment
@@ -95,7 +119,7 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __re
   }
   for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += g[i] * g[i];
   acc = block_sum(acc);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc;
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -146,15 +170,20 @@ extern "C" int nbasr_optim_step(float* param, float* grad, float* m, float* v, i
                                 const int64_t* seg_len, int nseg, int64_t seg_chunks, float reg_coef, float max_norm, float beta1,
                                 float beta2, float eps, float* state, void* stream) {
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(state + 2, 0, sizeof(float) * (2 + nseg), st);
+  float* part_total = state + 8 + nseg;              // SUMSQ_BLOCKS partials of ||grad||^2
+  float* part_seg = part_total + SUMSQ_BLOCKS;       // seg_chunks partials of the per-segment ||W||^2
   if (nseg > 0 && reg_coef != 0.f) {
     // seg_chunks = sum_s ceil(seg_len[s] / 16384), computed once by the host that owns the segment table
-    seg_sumsq_kernel<<<(unsigned)seg_chunks, 256, 0, st>>>(param, seg_off, seg_len, nseg, state);
+    seg_sumsq_kernel<<<(unsigned)seg_chunks, 256, 0, st>>>(param, seg_off, seg_len, nseg, part_seg);
+    NBASR_CHECK_LAUNCH();
+    seg_reduce_kernel<<<nseg, 256, 0, st>>>(part_seg, seg_len, nseg, state);
     NBASR_CHECK_LAUNCH();
     reg_grad_kernel<<<(unsigned)seg_chunks, 256, 0, st>>>(param, grad, seg_off, seg_len, nseg, state, reg_coef);
     NBASR_CHECK_LAUNCH();
   }
-  sumsq_kernel<<<592, 256, 0, st>>>(grad, n, state + 2);
+  sumsq_kernel<<<SUMSQ_BLOCKS, 256, 0, st>>>(grad, n, part_total);
+  NBASR_CHECK_LAUNCH();
+  total_reduce_kernel<<<1, 256, 0, st>>>(part_total, SUMSQ_BLOCKS, state);
   NBASR_CHECK_LAUNCH();
   adam_kernel<<<1184, 256, 0, st>>>(param, grad, m, v, n, max_norm, beta1, beta2, eps, state);
   NBASR_CHECK_LAUNCH();

@@ -1,6 +1,6 @@
 // Host side of the TMA path: a cache of cuTensorMapEncodeTiled descriptors keyed by (base, dims, strides, box).
 // Maps describe 2-byte elements (bf16 / fp16 alike: the copy engine never interprets them); rank 2 or 3,
-// dims[0] contiguous, strides in ELEMENTS for dims 1, 2; 128-byte swizzle unless swizzle128 = 0.
+// dims[0] contiguous, strides in ELEMENTS for dims 1, 2; swizzle: 1 = 128-byte (default), 0 = none, 2 = 64-byte.
 #include <cuda.h>
 
 #include <mutex>
@@ -46,7 +46,7 @@ std::mutex g_maps_mu;
 int sm100_get_map(const void* base, int rank, const uint64_t* dims, const int64_t* strides_el, const uint32_t* box, CUtensorMap* out,
                   int swizzle128) {
   MapKey k{};
-  k.v[0] = (uint64_t)base; k.v[1] = rank | (swizzle128 ? 0 : 16);
+  k.v[0] = (uint64_t)base; k.v[1] = rank | ((swizzle128 ^ 1) << 4);
   for (int i = 0; i < rank; ++i) { k.v[2 + i] = dims[i]; k.v[7 + i] = box[i]; }
   for (int i = 1; i < rank; ++i) k.v[4 + i] = (uint64_t)strides_el[i];
   std::lock_guard<std::mutex> lk(g_maps_mu);
@@ -64,7 +64,8 @@ int sm100_get_map(const void* base, int rank, const uint64_t* dims, const int64_
     if (gstr[i - 1] % 16 != 0) return nbasr_fail("TMA stride %llu not a multiple of 16 bytes", (unsigned long long)gstr[i - 1]);
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return nbasr_fail("cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu)", (int)r, rank,

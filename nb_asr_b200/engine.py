@@ -150,20 +150,28 @@ class Engine:
         flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.slices = {}
+        dinit = getattr(self.model, '_device_init', None)       # get_model(init='device'): storage is uninitialised
+        gen = torch.Generator(device=dev).manual_seed(dinit['seed']) if dinit else None
         with torch.no_grad():
             for name, p, off in zip(self.names, self.params, offs):
                 n = p.numel()
                 dst, gdst = flat_p[off:off + n], flat_g[off:off + n]
+                if dinit:
+                    self._device_init_param(name, p, dst, gen, dinit['conv_gain'])
                 if self._is_dense_conv_w(name):
                     co, ci, k = p.shape
-                    dst.view(co, k, ci).copy_(p.detach().to(dev).permute(0, 2, 1))
+                    if not dinit:
+                        dst.view(co, k, ci).copy_(p.detach().to(dev).permute(0, 2, 1))
                     p.data = dst.view(co, k, ci).permute(0, 2, 1)
                     p.grad = gdst.view(co, k, ci).permute(0, 2, 1)
                 else:
-                    dst.view(p.shape).copy_(p.detach().to(dev))
+                    if not dinit:
+                        dst.view(p.shape).copy_(p.detach().to(dev))
                     p.data = dst.view(p.shape)
                     p.grad = gdst.view(p.shape)
                 self.slices[name] = (off, n)
+        if dinit:
+            self.model._device_init = None       # a later re-bind copies the (now real) parameters like any other
         self.flat_p, self.flat_g = flat_p, flat_g
         self.n_flat = total
         self.adam_m = torch.zeros_like(flat_p)
@@ -174,7 +182,9 @@ class Engine:
         reg = [self.slices[n] for n in self.names if n.endswith('.conv.weight')]
         self.seg_off = torch.tensor([o for o, _ in reg], dtype=torch.int64, device=dev)
         self.seg_len = torch.tensor([l for _, l in reg], dtype=torch.int64, device=dev)
-        self.opt_state = torch.zeros(8 + len(reg), dtype=torch.float32, device=dev)
+        self.seg_chunks = int(sum((l + 16383) // 16384 for _, l in reg))
+        # [step, lr, ||g||^2, clip, per-segment ||W||^2 ...] + scratch of the deterministic reductions (nbasr.h)
+        self.opt_state = torch.zeros(8 + len(reg) + 592 + self.seg_chunks, dtype=torch.float32, device=dev)
         if old is not None and old[2].numel() == self.opt_state.numel():
             self.opt_state.copy_(old[2])
         self._lr_host = None          # the device copy of lr is rewritten by the next set_lr()
@@ -185,6 +195,25 @@ class Engine:
         self._compile_pack_jobs()
         self.plans = collections.OrderedDict()
         self._pack_version = None
+
+    @staticmethod
+    def _device_init_param(name, p, dst, gen, conv_gain):
+        """model/torch/__init__.py:13-29 on the device: xavier_uniform for Linear / Conv1d / LSTM weights (torch's fan
+        rule: fan_in = size(1) * receptive field, fan_out = size(0) * receptive field), zeros for biases, LayerNorm (1, 0).
+        i.i.d. entries: the tap-major storage of the dense conv weights needs no permutation."""
+        leaf = name.rsplit('.', 1)[-1]
+        if p.dim() >= 2:
+            rf = 1
+            for d in p.shape[2:]:
+                rf *= d
+            bound = math.sqrt(6.0 / (p.shape[1] * rf + p.shape[0] * rf))
+            if '.nodes.' in name and name.endswith('.conv.weight'):
+                bound *= conv_gain
+            dst.uniform_(-bound, bound, generator=gen)
+        elif leaf == 'weight':            # LayerNorm gamma
+            dst.fill_(1.0)
+        else:
+            dst.zero_()
 
     def P(self, name):
         off, _ = self.slices[name]
@@ -403,30 +432,33 @@ class Engine:
         e.accumulate = accumulate
         return e
 
-    def plan(self, B, T, training):
-        """Plans are cached per (B, T, training), least recently used first.  A plan owns every activation / mask /
+    def plan(self, B, T, training, grad=None):
+        """Plans are cached per (B, T, training, grad), least recently used first.  `training` switches dropout on; `grad`
+        (default: training) says whether a backward pass may follow: only then are gate-bit masks, bf16 twins of the
+        forward activations and the backward call list built (an eval step needs none of them).  A plan owns every activation / mask /
         gradient buffer of its shape (about 3.7 GB at 64 x 500) plus the CUDA graphs and CTC workspaces captured on it, so
         loaders whose padded length changes from batch to batch would otherwise grow without bound: beyond `max_plans`
         (NBASR_MAX_PLANS, default 6) the oldest plan is dropped and its memory returns to the allocator."""
-        key = (B, T, bool(training))
+        grad = bool(training) if grad is None else bool(grad)
+        key = (B, T, bool(training), grad)
         pl = self.plans.get(key)
         if pl is None:
             while len(self.plans) >= max(1, self.max_plans):
                 _, old = self.plans.popitem(last=False)
                 old.graphs.clear()
                 old.ws.clear()
-            pl = self.plans[key] = self._build_plan(B, T, bool(training))
+            pl = self.plans[key] = self._build_plan(B, T, bool(training), grad)
         else:
             self.plans.move_to_end(key)
         return pl
 
     @_on_device
-    def _build_plan(self, B, T, training):
+    def _build_plan(self, B, T, training, grad=True):
         self.bind()
         m, lib, dev, dt, tdt = self.model, self.lib, self.device, self.dt, self.tdt
         es = 2 if dt == BF16 else 4
         pl = _Plan()
-        pl.B, pl.T, pl.training = B, T, training
+        pl.B, pl.T, pl.training, pl.grad = B, T, training, grad
         pl.keep = []       # keeps ctypes structs / tensors alive
         pl.graphs, pl.ws = {}, {}     # CUDA graphs / CTC workspaces captured on this plan (trainer.py); die with the plan
         arena = pl.arena = _Arena(dev)
@@ -448,7 +480,7 @@ class Engine:
         def zact(rows, cols, copy=False):
             """forward activation buffer (activation format) and, if asked for in a 16-bit training plan, its bf16 twin"""
             t = arena.zeros((rows, cols), tadt)
-            if copy and training and adt != dt:
+            if copy and grad and adt != dt:
                 bcopy[id(t)] = arena.zeros((rows, cols), tdt)
             return t
 
@@ -506,7 +538,7 @@ class Engine:
             lpad, _ = pad_rule(8, 1, s)
             K = 8 * pg.C
             z = zact(geo.rows, Cc)
-            zmask = _Mask(geo.rows, Cc, 32, arena) if training else None     # gate bits are only read by the backward pass
+            zmask = _Mask(geo.rows, Cc, 32, arena) if grad else None     # gate bits are only read by the backward pass
             pl.keep.append(zmask)
             wf_ptr = self.wf[cname].data_ptr() if self.wf[cname] is not None else self.P(cname + '.weight')
             a_ptr = _ptr(prev, (PAD_L - lpad) * pg.C)
@@ -544,7 +576,7 @@ class Engine:
                     else:
                         # plane width = the producing kernel's slab: 32 (GEMM / SIMT) or 48/40 (tcgen05 grouped conv)
                         mwid = (40 if Cc // 100 == 10 else 48) if (op in CONV_EDGES and dt == BF16) else 32
-                        mask = _Mask(geo.rows, Cc, mwid, arena) if training else None
+                        mask = _Mask(geo.rows, Cc, mwid, arena) if grad else None
                         pl.keep.append(mask)
                         nrec['mask'] = mask
                         sl = next_salt()
@@ -638,6 +670,9 @@ class Engine:
                  self.P(hn + '.bias'), pl.logits.data_ptr(), pl.logp.data_ptr())
         pl.fwd = fwd
         pl.final = prev
+        if not grad:
+            pl.bwd, pl.buckets = None, []
+            return pl
 
         # =========================================================== backward plan
         bwd = []
@@ -817,13 +852,13 @@ class Engine:
         self.launches += n     # kernels launched (every C-ABI call launches >= 1 kernel of libnbasr)
 
     @_on_device
-    def forward(self, audio, training=None):
-        """audio (B, 80, T) fp32 cuda -> plan (holds logits / logp buffers)."""
+    def forward(self, audio, training=None, grad=None):
+        """audio (B, 80, T) fp32 cuda -> plan (holds logits / logp buffers).  grad: a backward pass may follow."""
         self.bind()
         training = self.model.training if training is None else training
         B, F, T = audio.shape
         assert F == FEATURES
-        pl = self.plan(B, T, training)
+        pl = self.plan(B, T, training, grad)
         self.refresh_packs()
         pl.audio.copy_(audio, non_blocking=True)
         if training and self.training_drop > 0:
@@ -833,6 +868,8 @@ class Engine:
 
     @_on_device
     def backward(self, pl, dlogits=None, zero_grad=True):
+        if pl.bwd is None:
+            raise RuntimeError('this plan was built for inference (grad=False): no gate masks / backward call list')
         if dlogits is not None:
             pl.dlogits.copy_(dlogits)
         if zero_grad:
@@ -877,7 +914,7 @@ class Engine:
                                              self.adam_v.data_ptr(), self.n_flat, self.seg_off.data_ptr(),
                                              self.seg_len.data_ptr(), int(self.seg_off.numel()), self.seg_chunks, reg_coef, max_norm,
                                              betas[0], betas[1], eps, self.opt_state.data_ptr(), st), 'optim')
-        self.launches += 5 if self.seg_off.numel() else 3
+        self.launches += 7 if self.seg_off.numel() else 4
         self.refresh_packs(force=True)
 
 
@@ -887,7 +924,9 @@ class ModelFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, audio, *params):
         eng = model.engine
-        pl = eng.forward(audio.contiguous().float())
+        # gradients may be requested in eval mode too (dropout off): the plan then still records gate masks
+        need = torch.is_grad_enabled() and (audio.requires_grad or any(p.requires_grad for p in eng.params))
+        pl = eng.forward(audio.contiguous().float(), grad=need or model.training)
         ctx.eng, ctx.pl = eng, pl
         return pl.logits.clone()
 

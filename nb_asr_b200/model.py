@@ -128,6 +128,7 @@ class ASRModel(nn.Module):
             layers.append(nn.Linear(FILTERS[-1], num_classes + 1))
         self.model = layers
         self._engine = None
+        self._device_init = None
         self.precision = kwargs.get('precision', 'bf16')
 
     # -- drop-in surface -------------------------------------------------------------------
@@ -168,10 +169,28 @@ class ASRModel(nn.Module):
         return ModelFunction.apply(self, input, *self.engine.params)
 
 
-def get_model(arch_vec, use_rnn, dropout_rate, gpu=None, precision='bf16'):
-    """model/torch/__init__.py:7-35: build, re-initialise (xavier / zeros), move to cuda:{gpu}."""
+def get_model(arch_vec, use_rnn, dropout_rate, gpu=None, precision='bf16', init='reference', seed=None, conv_gain=1.0):
+    """model/torch/__init__.py:7-35: build, re-initialise (xavier / zeros), move to cuda:{gpu}.
+
+    init='reference' (default): the reference's own procedure on the host RNG -- same seed, bit-identical weights.
+    init='device': for architecture sweeps (thousands of candidates; the host procedure costs 0.3-1.1 s each).  The
+    module tree is built without storage, materialised on cuda:{gpu} and initialised there by the engine from a device
+    generator seeded with `seed`: the same DISTRIBUTIONS as model/torch/__init__.py:13-29 (xavier_uniform weights, zero
+    biases, LayerNorm 1 / 0), not the same stream.  `conv_gain` multiplies the xavier bound of the grouped-conv edges
+    (sqrt(1 + groups) makes them variance-preserving: SURVEY finding 5, activations vanish through skip-free conv
+    cells at the reference's init)."""
     ss.validate_arch(arch_vec)
     arch_desc = ss.arch_vec_to_names(arch_vec)
+    if init == 'device':
+        if gpu is None:
+            raise ValueError("init='device' needs gpu=<index>")
+        with torch.device('meta'):
+            model = ASRModel(arch_desc, use_rnn=use_rnn, dropout_rate=dropout_rate, precision=precision)
+        model.to_empty(device=f'cuda:{gpu}')
+        model._device_init = dict(seed=1235 if seed is None else int(seed), conv_gain=float(conv_gain))
+        return model
+    if init != 'reference':
+        raise ValueError(f'unknown init {init!r}')
     model = ASRModel(arch_desc, use_rnn=use_rnn, dropout_rate=dropout_rate, precision=precision)
 
     def init_weights(m):

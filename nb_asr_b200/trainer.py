@@ -280,7 +280,7 @@ class Trainer:
     def _step_eager(self, audio, audio_len, targets, targets_len, training):
         model = self._model
         eng = model.engine
-        pl = eng.forward(audio, training=model.training)
+        pl = eng.forward(audio, training=model.training, grad=training)
         B, S = targets.shape
         ws = self._plan_ws(pl, self.device, B, S)
         self._ctc(eng, pl, targets, audio_len, targets_len, training, ws)
@@ -301,7 +301,7 @@ class Trainer:
         B, _, T = audio.shape
         S = targets.shape[1]
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        pl = eng.plan(B, T, model.training)
+        pl = eng.plan(B, T, model.training, training)
         key = (S, bool(training), multi)
         ent = pl.graphs.get(key)
         ws = self._plan_ws(pl, self.device, B, S)

@@ -478,7 +478,7 @@ def test_optim_step_matches_reference_formulas():
     m, v = torch.zeros(n, device=U.DEV), torch.zeros(n, device=U.DEV)
     so = torch.tensor([s[0] for s in segs], dtype=torch.int64, device=U.DEV)
     sl = torch.tensor([s[1] for s in segs], dtype=torch.int64, device=U.DEV)
-    state = torch.zeros(16, device=U.DEV)
+    state = torch.zeros(8 + 2 + 592 + 2, device=U.DEV)      # header + 2 segments + scratch of the deterministic reductions
     state[1] = 1e-3
     pr, mr, vr = p.clone(), torch.zeros(n), torch.zeros(n)
     for step in range(1, 4):

@@ -192,7 +192,7 @@ def test_plan_cache_is_bounded():
         loss, logp, ol = tr.step(batch, training=False)
         assert torch.isfinite(loss)
     assert len(model.engine.plans) == 3
-    assert (2, 64, False) in model.engine.plans           # re-built after eviction, most recent
+    assert (2, 64, False, False) in model.engine.plans    # re-built after eviction, most recent
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')

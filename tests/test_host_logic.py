@@ -97,3 +97,23 @@ def test_graph_hash_matches_reference_golden_and_kats():
     assert sum(1 for _, a in uniq if all(n[0] != 5 for n in a)) == 8000
     # isomorphic pair: a `zero` node cuts the chain, the skip keeps the path -> same graph as dropping that node's op
     assert G.get_model_hash([[5, 1], [1, 0, 0], [1, 0, 0, 0]]) != G.get_model_hash([[1, 0], [1, 0, 0], [1, 0, 0, 0]])
+
+
+def test_timit_shaped_eval_set():
+    """BASELINE.json configs[3] / SURVEY.md 8d: 1 344 utterances, clipped log-normal lengths (mean ~306 in [92, 778]),
+    targets ~ frames / 8 in [10, 75], sorted into batches of 64 padded to a multiple of 64 frames; all alignments feasible."""
+    from nb_asr_b200 import data
+    bs = data.timit_shaped_eval_set()
+    assert len(bs) == 21 and sum(b[0][1].numel() for b in bs) == 1344
+    lens = torch.cat([b[0][1] for b in bs]).float()
+    assert 92 <= lens.min() and lens.max() <= 778 and 290 < lens.mean() < 325
+    assert torch.equal(lens, lens.sort().values)                        # bucketed by length
+    assert len({b[0][0].shape[2] for b in bs}) <= 16                    # a handful of distinct padded shapes
+    for (audio, al), (tg, tl) in bs:
+        assert audio.shape[2] % 64 == 0 and audio.shape[2] >= int(al.max())
+        assert float(audio[0, :, int(al[0]):].abs().sum()) == 0.0       # zero padded like collate_fn (timit.py:104)
+        assert int(tl.min()) >= 1 and int(tl.max()) <= 75
+        assert bool((2 * tl <= al // 4).all())                          # feasible even if every label repeats
+        assert tg.dtype == torch.int32 and int(tg.max()) <= 48
+    again = data.timit_shaped_eval_set()
+    assert all(torch.equal(a[0][0], b[0][0]) and torch.equal(a[1][0], b[1][0]) for a, b in zip(bs, again))      # fixed set

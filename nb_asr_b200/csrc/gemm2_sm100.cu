@@ -33,15 +33,23 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_STAGE_BYTES = 128 * BK * 2;         // up to BN/2 = 128 rows: 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int THREADS = 320;
-// Staged epilogue (16-bit outputs): every epilogue warp owns 8 KB of shared memory -- out box | out2 box | two skip-operand
-// boxes, each 32 rows x 32 columns x 2 B in the 64-byte-swizzled TMA layout.  Skip tensors arrive by TMA load, results leave by
-// TMA store: full 64-byte row segments instead of 16 bytes per thread and row (the per-thread path moves half-used 32-byte
-// sectors, which made `linear` edges with skips and the bf16 twin memory-bound at ~0.3 of the tensor peak).
+constexpr int THREADS = 320;                        // direct epilogue: producer, MMA, 8 epilogue warps
+// Staged epilogue (16-bit outputs).  ncu on the direct version (profiles/r2_ncu_gemm_linear800.txt): a `linear` edge
+// (K = 600..1200: 3 us of MMAs per 256 x 224 tile) is EPILOGUE-bound -- 8 epilogue warps were busy 86 % of the time, the tensor
+// pipe 45 %, and per-thread 16-byte row stores half-use 32-byte sectors.  So:
+//  * 16 epilogue warps (4 per TMEM lane quadrant, every 4th 32-column chunk each): twice the latency hiding;
+//  * every epilogue warp owns two 32 x 32 boxes of shared memory (64-byte-swizzled TMA layout): the skip operands of a chunk
+//    arrive in them by TMA LOAD, are summed into the registers, then the boxes carry `out` / `out2` to a TMA STORE -- global
+//    traffic moves in full 64-byte row segments;
+//  * the bias of a chunk is one coalesced load per warp, broadcast by shuffles (not 32 loads per thread);
+//  * the accumulator stage is released with a RELAXED cluster arrive (a release compiles to MEMBAR.ALL + ERRBAR, 15 % of the
+//    epilogue's samples; the TMEM reads are already ordered by tcgen05.wait::ld + fence::before_thread_sync).
+constexpr int ST_THREADS = 576;                     // producer, MMA, 16 epilogue warps (<= 112 registers per thread)
+constexpr int ST_EPI_WARPS = 16;
 constexpr int ST_STAGES = 5;                        // 5 x 32 KB ring + 64 KB staging
-constexpr int ST_WARP_BYTES = 8192;
+constexpr int ST_WARP_BYTES = 4096;
 constexpr int ST_BOX_BYTES = 2048;
-constexpr int ST_SMEM_BYTES = ST_STAGES * STAGE_BYTES + 8 * ST_WARP_BYTES + 1024 + 256;
+constexpr int ST_SMEM_BYTES = ST_STAGES * STAGE_BYTES + ST_EPI_WARPS * ST_WARP_BYTES + 1024 + 256;
 
 struct Args {
   int nb, nr, K, N, BN, f16, n_add_staged;
@@ -69,6 +77,9 @@ __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster, uin
   // .relaxed: a cluster-scope release here compiles to MEMBAR + ERRBAR, which waits for the producer's outstanding TMA
   // loads and serialises the whole ring (ncu: ~1 us per K block); the data itself is published by complete_tx.
   asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
@@ -116,11 +127,13 @@ struct StMaps {      // tensor maps of the staged epilogue: out, out2, up to thr
 };
 
 template <bool STAGED>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(STAGED ? ST_THREADS : THREADS, 1)
 gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ StMaps sm,
                     const Args p) {
   constexpr int STAGES = STAGED ? ST_STAGES : ::STAGES;
-  constexpr int STG_BYTES = STAGED ? 8 * ST_WARP_BYTES : 0;
+  constexpr int EPI_WARPS = STAGED ? ST_EPI_WARPS : 8;
+  constexpr int NSUB = EPI_WARPS / 4;               // epilogue warps per TMEM lane quadrant
+  constexpr int STG_BYTES = STAGED ? ST_EPI_WARPS * ST_WARP_BYTES : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -130,7 +143,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   auto add_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4 + w); };      // one per epilogue warp (staged)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + STAGES * STAGE_BYTES + STG_BYTES + 8 * (2 * STAGES + 4 + 8));
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + STAGES * STAGE_BYTES + STG_BYTES + 8 * (2 * STAGES + 4 + 16));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,11 +161,11 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 16);    // 8 epilogue warps x 2 CTAs (used in the leader only)
+      mbar_init(tempty_bar(s), 2 * EPI_WARPS);    // every epilogue warp of both CTAs (used in the leader only)
     }
     if (STAGED) {
       prefetch_tmap(&sm.o);
-      for (int w = 0; w < 8; ++w) mbar_init(add_bar(w), 1);
+      for (int w = 0; w < EPI_WARPS; ++w) mbar_init(add_bar(w), 1);
     }
     fence_barrier_init();
   }
@@ -217,8 +230,8 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     const int q = warp & 3;           // TMEM lane quadrant this warp may access
-    const int hh = (warp - 2) >> 2;   // the two warps of a quadrant take alternate 32-column chunks
-    // staged epilogue state (see ST_* above): this warp's four 2 KB boxes and its skip-operand barrier
+    const int sub = (warp - 2) >> 2;  // the NSUB warps of a quadrant take every NSUB-th 32-column chunk
+    // staged epilogue state: this warp's two 2 KB boxes and its skip-operand barrier
     const int ew = warp - 2;
     uint8_t* stg = smem_al + STAGES * STAGE_BYTES + ew * ST_WARP_BYTES;
     const uint32_t stg_u = smem_base + STAGES * STAGE_BYTES + ew * ST_WARP_BYTES;
@@ -242,68 +255,94 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (!STAGED) {
         mbar_wait(tfull_bar(as), aphase_t);
         tcgen05_fence_after();
-        for (int c = 32 * hh; c < p.BN; c += 64) {
+        for (int c = 32 * sub; c < p.BN; c += 32 * NSUB) {
           if (n0 + c >= ncol) break;   // warp-uniform
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + c, v);
           if (r < p.nr && m_raw < p.m_tiles) epilogue_chunk(p.epi, rho, n0 + c, ncol, v);
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
       } else {
         const nbasr_epilogue& e = p.epi;
         const int rbox = r0 + q * 32;                                   // first row of this warp's 32-row box
         const bool box_ok = m_raw < p.m_tiles && rbox < p.nr;           // warp-uniform
-        auto load_adds = [&](int c) {                                    // skip operands of chunk c -> shared memory
+        const float acc_s = epi_acc_scale(e), bias_s = epi_bias_scale(e), relu_hi = epi_relu_hi(e);
+        const uint32_t hi_bits = __float_as_uint(relu_hi);
+        const bool plain = e.drop_p == 0.f;                              // (dropout goes through the general routine)
+        // Skip operands of chunk c -> this warp's boxes.  The boxes also carry the previous chunk's results to their TMA
+        // stores, so the stores must have finished READING shared memory first.
+        auto load_adds = [&](int c) {
           if (box_ok && na > 0 && lane == 0 && c < p.BN && n0 + c < ncol) {   // (only chunks that will be processed)
+            bulk_wait_read0();
             mbar_expect_tx(abar, ST_BOX_BYTES * min(na, 2));
-            tma_load_3d(stg_u + 2 * ST_BOX_BYTES, &sm.a0, abar, n0 + c, rbox, b);
-            if (na > 1) tma_load_3d(stg_u + 3 * ST_BOX_BYTES, &sm.a1, abar, n0 + c, rbox, b);
+            tma_load_3d(stg_u, &sm.a0, abar, n0 + c, rbox, b);
+            if (na > 1) tma_load_3d(stg_u + ST_BOX_BYTES, &sm.a1, abar, n0 + c, rbox, b);
           }
         };
-        load_adds(32 * hh);                   // before the accumulator wait: the load overlaps the tile's last MMAs
+        auto add_box = [&](int box, float* v) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float t[8];
+            load8_h(stg + box * ST_BOX_BYTES + sw_row + ((j ^ sw_x) << 4), e.add_dtype, t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j * 8 + i] += t[i];
+          }
+        };
+        load_adds(32 * sub);                  // before the accumulator wait: the load overlaps the tile's last MMAs
         mbar_wait(tfull_bar(as), aphase_t);
         tcgen05_fence_after();
-        for (int c = 32 * hh; c < p.BN; c += 64) {
+        for (int c = 32 * sub; c < p.BN; c += 32 * NSUB) {
           if (n0 + c >= ncol) break;   // warp-uniform
+          // bias of this chunk: one coalesced load per warp (lane i <- column c + i), broadcast by shuffles below
+          float bl = 0.f;
+          if (e.bias && n0 + c + lane < ncol) bl = __ldg(e.bias + n0 + c + lane) * bias_s;
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + c, v);
           if (box_ok) {
             const int nvalid = min(32, ncol - (n0 + c));
             uint32_t m[4];
-            if (nvalid == 32) epilogue_compute<32, true, false, true>(e, rho, n0 + c, 32, v, m);
-            else epilogue_compute<32, false, false, true>(e, rho, n0 + c, nvalid, v, m);
+            if (plain) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint32_t mm = 0xffu;
+                if (e.relu20) {
+                  mm = 0;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float z = fmaf(v[g * 8 + i], acc_s, __shfl_sync(0xffffffffu, bl, g * 8 + i));
+                    // 0 < z <= hi  <=>  bits(z) - 1 < bits(hi) as unsigned (negative z and +0 wrap to huge values)
+                    mm |= ((__float_as_uint(z) - 1u) < hi_bits) ? (1u << i) : 0u;
+                    v[g * 8 + i] = fminf(fmaxf(z, 0.f), relu_hi);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[g * 8 + i] = fmaf(v[g * 8 + i], acc_s, __shfl_sync(0xffffffffu, bl, g * 8 + i));
+                }
+                m[g] = mm;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], acc_s, __shfl_sync(0xffffffffu, bl, i));
+              if (nvalid == 32) epilogue_compute<32, true, true, true>(e, rho, n0 + c, 32, v, m);
+              else epilogue_compute<32, false, true, true>(e, rho, n0 + c, nvalid, v, m);
+            }
             if (na > 0) {
               mbar_wait(abar, aphase);
               aphase ^= 1;
-#pragma unroll
-              for (int a = 0; a < 2; ++a) {
-                if (a < na) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    float t[8];
-                    load8_h(stg + (2 + a) * ST_BOX_BYTES + sw_row + ((j ^ sw_x) << 4), e.add_dtype, t);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[j * 8 + i] += t[i];
-                  }
-                }
-              }
+              add_box(0, v);
+              if (na > 1) add_box(1, v);
               if (na > 2) {                     // third skip tensor: through the first box once everyone has read it
                 __syncwarp();
                 if (lane == 0) {
                   mbar_expect_tx(abar, ST_BOX_BYTES);
-                  tma_load_3d(stg_u + 2 * ST_BOX_BYTES, &sm.a2, abar, n0 + c, rbox, b);
+                  tma_load_3d(stg_u, &sm.a2, abar, n0 + c, rbox, b);
                 }
                 mbar_wait(abar, aphase);
                 aphase ^= 1;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float t[8];
-                  load8_h(stg + 2 * ST_BOX_BYTES + sw_row + ((j ^ sw_x) << 4), e.add_dtype, t);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) v[j * 8 + i] += t[i];
-                }
+                add_box(0, v);
               }
-              __syncwarp();
-              load_adds(c + 64);      // next chunk's skip operands
             }
             // gate bits of the second output (backward: dZ of the previous node), one byte per 8 columns
             uint32_t w2[4] = {0xffu, 0xffu, 0xffu, 0xffu};
@@ -312,8 +351,9 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int g = 0; g < 4; ++g)
                 if (g * 8 < nvalid) w2[g] = reinterpret_cast<const uint8_t*>(e.mask2)[mask_byte_addr(rho, n0 + c + g * 8, e.mask2_w, e.mask_rows)];
             }
-            // the previous chunk's TMA stores must have finished READING the boxes before they are overwritten
-            if (lane == 0) bulk_wait_read0();
+            // the boxes are free once (a) every lane has read its skip operands and (b) the previous chunk's TMA stores have
+            // finished reading them (already waited for by load_adds when there are skip operands)
+            if (na == 0 && lane == 0) bulk_wait_read0();
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -346,12 +386,13 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (e.out2) tma_store_3d(&sm.o2, stg_u + ST_BOX_BYTES, n0 + c, rbox, b);
               bulk_commit();
             }
+            load_adds(c + 32 * NSUB);          // next chunk's skip operands (waits for the stores just issued to read the boxes)
           }
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa(tempty_bar(as), 0));
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
     }
     if (STAGED && lane == 0) bulk_wait0();
   }
@@ -531,7 +572,7 @@ static int max_resident_pairs(int smem_bytes, cudaStream_t st) {
   if (!cached[dev]) {
     const int sms = nbasr_sm_count();
     cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(STAGED ? ST_THREADS : THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -608,7 +649,7 @@ int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
       attr = true;
     }
     const int npairs = std::max(1, std::min(a.pair_tiles, max_resident_pairs<true>(ST_SMEM_BYTES, st)));
-    err = launch_pdl(gemm_tn_pair_kernel<true>, dim3(2 * npairs), dim3(THREADS), (size_t)ST_SMEM_BYTES, st, 2, tmA, tmB, sm, a);
+    err = launch_pdl(gemm_tn_pair_kernel<true>, dim3(2 * npairs), dim3(ST_THREADS), (size_t)ST_SMEM_BYTES, st, 2, tmA, tmB, sm, a);
   } else {
     static DevOnce attr;
     if (!attr) {

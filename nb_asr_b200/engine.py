@@ -55,8 +55,10 @@ class _Arena:
     """Zero-initialised device memory for one plan, carved from a few large blocks (64 MiB, doubling up to 2 GiB): one
     fill launch per block instead of one per buffer, and everything a plan owns is freed together when it is evicted."""
 
-    def __init__(self, dev):
-        self.dev, self.blocks, self.off, self.next = dev, [], 0, 64 << 20
+    def __init__(self, dev, first_block=64 << 20):
+        # first_block: an estimate of the whole arena (one fill launch, and the caching allocator hands the same block back
+        # to the next plan of this shape); it only has to be roughly right -- further blocks follow the doubling rule
+        self.dev, self.blocks, self.off, self.next = dev, [], 0, max(1 << 20, int(first_block))
         self.bytes = 0
 
     def raw(self, nbytes):
@@ -94,7 +96,10 @@ def _on_device(fn):
     cuda:k must not run in another device's context (Trainer(gpus=[k]) / get_model(gpu=k) without torch.cuda.set_device)."""
     @functools.wraps(fn)
     def wrapped(self, *a, **k):
-        dev = getattr(self, 'device', None) or self.params[0].device
+        dev = getattr(self, 'device', None)
+        if dev is None:
+            di = getattr(self.model, '_device_init', None)
+            dev = di['device'] if di else self.params[0].device
         if dev.type != 'cuda':
             raise RuntimeError('nb_asr_b200 needs the model on a CUDA device (no CPU fallback)')
         with torch.cuda.device(dev):
@@ -133,7 +138,8 @@ class Engine:
         p0 = self.params[0]
         if self.flat_p is not None and self._bound_ptr == (p0.data_ptr(), p0.device):
             return
-        dev = p0.device
+        dinit = getattr(self.model, '_device_init', None)
+        dev = dinit['device'] if dinit else p0.device
         if dev.type != 'cuda':
             raise RuntimeError('nb_asr_b200 needs the model on a CUDA device (no CPU fallback)')
         with torch.cuda.device(dev):
@@ -150,25 +156,29 @@ class Engine:
         flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.slices = {}
-        dinit = getattr(self.model, '_device_init', None)       # get_model(init='device'): storage is uninitialised
+        dinit = getattr(self.model, '_device_init', None)       # get_model(init='device'): parameters have no storage yet
         gen = torch.Generator(device=dev).manual_seed(dinit['seed']) if dinit else None
         with torch.no_grad():
-            for name, p, off in zip(self.names, self.params, offs):
+            for i, (name, p, off) in enumerate(zip(self.names, self.params, offs)):
                 n = p.numel()
                 dst, gdst = flat_p[off:off + n], flat_g[off:off + n]
-                if dinit:
-                    self._device_init_param(name, p, dst, gen, dinit['conv_gain'])
                 if self._is_dense_conv_w(name):
                     co, ci, k = p.shape
-                    if not dinit:
-                        dst.view(co, k, ci).copy_(p.detach().to(dev).permute(0, 2, 1))
-                    p.data = dst.view(co, k, ci).permute(0, 2, 1)
-                    p.grad = gdst.view(co, k, ci).permute(0, 2, 1)
+                    pv, gv = dst.view(co, k, ci).permute(0, 2, 1), gdst.view(co, k, ci).permute(0, 2, 1)
                 else:
-                    if not dinit:
-                        dst.view(p.shape).copy_(p.detach().to(dev))
-                    p.data = dst.view(p.shape)
-                    p.grad = gdst.view(p.shape)
+                    pv, gv = dst.view(p.shape), gdst.view(p.shape)
+                if dinit:
+                    # storage-less (meta) parameter: draw the values on the device, then swap in a real Parameter that views
+                    # the flat buffer (a meta tensor cannot be re-pointed with .data)
+                    self._device_init_param(name, p, dst, gen, dinit['conv_gain'])
+                    newp = torch.nn.Parameter(pv, requires_grad=p.requires_grad)
+                    mod_name, _, leaf = name.rpartition('.')
+                    self.model.get_submodule(mod_name)._parameters[leaf] = newp
+                    self.params[i] = p = newp
+                else:
+                    pv.copy_(p.detach().to(dev))
+                    p.data = pv
+                p.grad = gv
                 self.slices[name] = (off, n)
         if dinit:
             self.model._device_init = None       # a later re-bind copies the (now real) parameters like any other
@@ -452,6 +462,22 @@ class Engine:
             self.plans.move_to_end(key)
         return pl
 
+    def _plan_bytes_estimate(self, B, T, grad):
+        """Rough size of a plan's arena: per encoder block (2 + 4 per cell) activation buffers, with gradients also their
+        bf16 twins, 7 gradient buffers and 1 bit per element of gate masks; head and small buffers on top."""
+        es = 2 if self.dt == BF16 else 4
+        total, Tcur = B * (T + 16) * FEATURES * es * 2, T
+        for i in range(4):
+            Tcur = Tcur if TR_STRIDES[i] == 1 else (Tcur + 1) // 2
+            rows = B * (Tcur + PAD_L + PAD_R + 1) + 8
+            per = rows * FILTERS[i] * es
+            nbuf = 2 + 4 * CELLS_PER_BLOCK[i]
+            total += per * nbuf
+            if grad:
+                total += per * (nbuf * (1 if self.adt != self.dt else 0) + 7) + per * nbuf // (8 * es) + per // 4
+        total += B * Tcur * (4 * HIDDEN * 4 * (3 if grad else 1) + HP * 2 + HIDDEN * 4 * 3 + 49 * 4 * 3)
+        return int(total * 1.05) + (8 << 20)
+
     @_on_device
     def _build_plan(self, B, T, training, grad=True):
         self.bind()
@@ -461,7 +487,7 @@ class Engine:
         pl.B, pl.T, pl.training, pl.grad = B, T, training, grad
         pl.keep = []       # keeps ctypes structs / tensors alive
         pl.graphs, pl.ws = {}, {}     # CUDA graphs / CTC workspaces captured on this plan (trainer.py); die with the plan
-        arena = pl.arena = _Arena(dev)
+        arena = pl.arena = _Arena(dev, self._plan_bytes_estimate(B, T, grad))
         fwd, bwd_rev = [], []   # bwd_rev: groups appended in forward order, executed reversed
         drop_p = self.training_drop if training else 0.0
         dscale = 1.0 / (1.0 - drop_p) if drop_p > 0 else 1.0

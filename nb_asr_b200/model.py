@@ -186,8 +186,9 @@ def get_model(arch_vec, use_rnn, dropout_rate, gpu=None, precision='bf16', init=
             raise ValueError("init='device' needs gpu=<index>")
         with torch.device('meta'):
             model = ASRModel(arch_desc, use_rnn=use_rnn, dropout_rate=dropout_rate, precision=precision)
-        model.to_empty(device=f'cuda:{gpu}')
-        model._device_init = dict(seed=1235 if seed is None else int(seed), conv_gain=float(conv_gain))
+        # no storage yet: the engine gives every parameter a view of its flat device buffer and fills it there
+        model._device_init = dict(seed=1235 if seed is None else int(seed), conv_gain=float(conv_gain),
+                                  device=torch.device('cuda', int(gpu)))
         return model
     if init != 'reference':
         raise ValueError(f'unknown init {init!r}')

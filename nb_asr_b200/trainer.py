@@ -56,18 +56,20 @@ class _CtcWorkspace:
         self.cache = collections.OrderedDict()
 
     @staticmethod
-    def make(dev, B, T, V, S):
+    def make(dev, B, T, V, S, arena=None):
+        """arena: the engine plan's arena (zero-filled device memory): one carve instead of nine allocations + fills"""
         L = 2 * S + 1
+        z = arena.zeros if arena is not None else (lambda shape, dtype: torch.zeros(shape, dtype=dtype, device=dev))
         w = _Ws()
-        w.work = torch.empty(2 * B * T * L + 16, dtype=torch.float32, device=dev)
-        w.nll = torch.zeros(B, dtype=torch.float32, device=dev)
-        w.loss = torch.zeros(1, dtype=torch.float32, device=dev)
-        w.dlogits = torch.zeros((B, T, V), dtype=torch.float32, device=dev)
-        w.hyp = torch.zeros((B, T), dtype=torch.int32, device=dev)
-        w.hyp_len = torch.zeros(B, dtype=torch.int32, device=dev)
-        w.dist = torch.zeros(B, dtype=torch.int32, device=dev)
-        w.per = torch.zeros(2, dtype=torch.float64, device=dev)
-        w.iwork = torch.zeros(B * (S + 2) + 16, dtype=torch.int32, device=dev)
+        w.work = z(2 * B * T * L + 16, torch.float32)
+        w.nll = z(B, torch.float32)
+        w.loss = z(1, torch.float32)
+        w.dlogits = z((B, T, V), torch.float32)
+        w.hyp = z((B, T), torch.int32)
+        w.hyp_len = z(B, torch.int32)
+        w.dist = z(B, torch.int32)
+        w.per = z(2, torch.float64)
+        w.iwork = z(B * (S + 2) + 16, torch.int32)
         return w
 
     def get(self, dev, B, T, V, S):
@@ -266,7 +268,7 @@ class Trainer:
         """CTC / decode workspace of this (plan, S): owned by the plan, so it lives as long as graphs captured on it."""
         ws = pl.ws.get(S)
         if ws is None:
-            ws = pl.ws[S] = _CtcWorkspace.make(dev, B, pl.Tq, pl.V, S)
+            ws = pl.ws[S] = _CtcWorkspace.make(dev, B, pl.Tq, pl.V, S, arena=pl.arena)
         return ws
 
     def _ctc(self, eng, pl, targets, audio_len, targets_len, training, ws):

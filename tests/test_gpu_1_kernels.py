@@ -569,3 +569,57 @@ def test_lstm_cluster_tensor_core_forward(B, T):
     torch.cuda.synchronize()
     assert U.relerr(dgx.cpu(), dgx_ref.cpu()) < 1.5e-2, U.relerr(dgx.cpu(), dgx_ref.cpu())     # bf16 W_hh / dg / partial sums
     assert U.relerr(dgx16.float().cpu(), dgx.cpu()) < 4e-3
+
+
+@pytest.mark.parametrize('B,T', [(32, 125), (64, 125), (32, 750)])
+def test_lstm_cluster_long_sequences_vs_torch_autograd(B, T):
+    """The cluster recurrence at the lengths the configs use (cfg 2: T' = 125, cfg 5: T' = 750), forward against the
+    step-by-step torch recurrence with the same operand rounding, BACKWARD against torch autograd through that recurrence
+    (straight-through for the bf16 rounding of h) -- not against another kernel of this library."""
+    torch.manual_seed(8)
+    H = 500
+    gx = (torch.randn(B, T, 4 * H) * 0.7).requires_grad_(True)
+    w_hh = torch.randn(4 * H, H) * 0.05
+    w_bf = w_hh.bfloat16().float()
+    h = torch.zeros(B, H)
+    c = torch.zeros(B, H)
+    outs = []
+    for t in range(T):
+        hr = h + (h.bfloat16().float() - h).detach()               # bf16 operand, identity gradient
+        g = gx[:, t] + hr @ w_bf.t()
+        i, f, gg, o = g.split(H, 1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        outs.append(h)
+    hs = torch.stack(outs, 1)
+    dh = torch.randn(B, T, H) * (1.0 / T)
+    (dgx_ref,) = torch.autograd.grad(hs, gx, dh)
+    lib = _lib.load()
+    whh = w_hh.to(U.DEV)
+    wp = torch.zeros(16 * 128 * 512, dtype=torch.bfloat16, device=U.DEV)
+    job = (_lib.PackJob * 1)()
+    job[0].kind, job[0].out_dtype, job[0].src, job[0].dst, job[0].n_out = 4, BF16, whh.data_ptr(), wp.data_ptr(), 16 * 128 * 512
+    job[0].a[0] = H
+    jd = torch.frombuffer(bytearray(bytes(job)), dtype=torch.uint8).to(U.DEV)
+    nblk = (16 * 128 * 512 + 4095) // 4096
+    bmap = torch.stack([torch.zeros(nblk, dtype=torch.int32), torch.arange(nblk, dtype=torch.int32)], 1).contiguous().to(U.DEV)
+    _lib.check(lib.nbasr_pack_batch(jd.data_ptr(), 1, bmap.data_ptr(), nblk, U.stream()))
+    gxd = gx.detach().contiguous().to(U.DEV)
+    hseq = torch.zeros(B, T, 512, dtype=torch.bfloat16, device=U.DEV)
+    gates = torch.zeros(B * T, 4 * H, device=U.DEV)
+    cst = torch.zeros(B * T, H, device=U.DEV)
+    work = torch.zeros(2 * B * H + 256, device=U.DEV)
+    _lib.check(lib.nbasr_lstm_fwd(gxd.data_ptr(), whh.data_ptr(), T, B, H, hseq.data_ptr(), BF16, T * 512, 512, 512, gates.data_ptr(),
+                                  cst.data_ptr(), wp.data_ptr(), work.data_ptr(), U.stream()), 'lstm_fwd cluster')
+    torch.cuda.synchronize()
+    assert U.relerr(hseq[:, :, :H].float().cpu(), hs.detach()) < 8e-3          # bf16 output rounding, no drift over T steps
+    assert U.relerr(cst.view(B, T, H)[:, -1].cpu(), c.detach()) < 5e-3
+    dhd = dh.contiguous().to(U.DEV)
+    dgx = torch.zeros(B * T, 4 * H, device=U.DEV)
+    dgx16 = torch.zeros(B * T, 4 * H, dtype=torch.bfloat16, device=U.DEV)
+    _lib.check(lib.nbasr_lstm_bwd(dhd.data_ptr(), T * H, H, H, whh.data_ptr(), gates.data_ptr(), cst.data_ptr(), T, B, H,
+                                  dgx.data_ptr(), work.data_ptr(), wp.data_ptr(), dgx16.data_ptr(), U.stream()), 'lstm_bwd cluster')
+    torch.cuda.synchronize()
+    err = U.relerr(dgx.view(B, T, 4 * H).cpu(), dgx_ref)
+    assert err < 2e-2, err                                                     # bf16 W_hh / dg operands through T steps
+    assert U.relerr(dgx16.float().cpu(), dgx.cpu()) < 4e-3

@@ -19,7 +19,7 @@ int nbasr_fail(const char* fmt, ...) {
 namespace {
 struct EnvState {
   bool flag[NBASR_ENV_COUNT];
-  int gemm_bn;
+  int gemm_bn, gemm_l2pf;
   double wgrad_epi_us;
   EnvState() {
     static const char* names[NBASR_ENV_COUNT] = {"NBASR_FORCE_SIMT", "NBASR_NO_PDL", "NBASR_GCONV_NO_PREFETCH", "NBASR_LSTM_SS",
@@ -27,6 +27,8 @@ struct EnvState {
     for (int i = 0; i < NBASR_ENV_COUNT; ++i) flag[i] = getenv(names[i]) != nullptr;
     const char* bn = getenv("NBASR_GEMM_BN");
     gemm_bn = bn ? atoi(bn) : 0;
+    const char* pf = getenv("NBASR_GEMM_L2PF");
+    gemm_l2pf = pf ? atoi(pf) : 0;
     const char* eu = getenv("NBASR_WGRAD_EPI_US");
     wgrad_epi_us = eu ? atof(eu) : 3.0;
   }
@@ -35,6 +37,7 @@ const EnvState g_env;
 }  // namespace
 bool nbasr_env_flag(int which) { return g_env.flag[which]; }
 int nbasr_env_gemm_bn() { return g_env.gemm_bn; }
+int nbasr_env_gemm_l2pf() { return g_env.gemm_l2pf; }
 double nbasr_env_wgrad_epi_us() { return g_env.wgrad_epi_us; }
 
 extern "C" {

@@ -329,7 +329,8 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
   const uint32_t tfull = bar0 + 8u * (2 * NSTAGE);
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(al + NSTAGE * WG_STAGE + 8 * (2 * NSTAGE + 2));
+  auto ready_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 1 + s); };     // "ones column written" (bias gradient)
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(al + NSTAGE * WG_STAGE + 8 * (3 * NSTAGE + 2));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab = blockIdx.x % p.nslabs;
   const int lane_id = blockIdx.x / p.nslabs;
@@ -340,7 +341,7 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmDZ);
     prefetch_tmap(&tmX);
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), 1); }
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
@@ -378,18 +379,10 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
       uint32_t phase = 0;
       bool first = true;
       for (int u = lane_id; u < p.nunits; u += p.nlanes) {
-        mbar_wait(full_bar(stage), phase);
+        // with a bias gradient the stage is usable once the helper warp has planted the ones column (below)
+        mbar_wait(p.dbias ? ready_bar(stage) : full_bar(stage), phase);
         const uint32_t sa = base + stage * WG_STAGE;
         const uint32_t sb = sa + DZ_BYTES;
-        if (p.dbias) {
-          // channel 63 of the X window (never part of a slab) <- 1.0 for every frame row: element 7 of the
-          // 16-byte chunk 7, at its 128B-swizzled position (chunk ^ (row & 7)).
-          uint8_t* xb = al + stage * WG_STAGE + DZ_BYTES;
-          for (int r = lane; r < AROWS; r += 32)
-            *reinterpret_cast<uint16_t*>(xb + r * 128 + ((7 ^ (r & 7)) << 4) + 14) = 0x3F80;
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-        }
         tcgen05_fence_after();
         if (lane == 0) {
 #pragma unroll
@@ -407,6 +400,24 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
       if (lane == 0) umma_commit(tfull);
     }
   } else if (has_work) {
+    if (warp == 2 && p.dbias) {
+      // Bias gradient = dZ^T 1: channel 63 of the X window (never part of a slab) <- 1.0 for every frame row (element 7 of
+      // the 16-byte chunk 7, at its 128B-swizzled position chunk ^ (row & 7)).  Done by this otherwise idle epilogue warp as
+      // soon as a stage has landed, OFF the MMA warp's critical path (ncu r2: tensor pipe 37 % busy with the write + proxy
+      // fence in front of every unit's MMAs).
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = lane_id; u < p.nunits; u += p.nlanes) {
+        mbar_wait(full_bar(stage), phase);
+        uint8_t* xb = al + stage * WG_STAGE + DZ_BYTES;
+        for (int r = lane; r < AROWS; r += 32)
+          *reinterpret_cast<uint16_t*>(xb + r * 128 + ((7 ^ (r & 7)) << 4) + 14) = 0x3F80;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar(stage));
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int half = m >> 6, co_l = m & 63;

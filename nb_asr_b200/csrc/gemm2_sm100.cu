@@ -52,7 +52,7 @@ constexpr int ST_BOX_BYTES = 2048;
 constexpr int ST_SMEM_BYTES = ST_STAGES * STAGE_BYTES + ST_EPI_WARPS * ST_WARP_BYTES + 1024 + 256;
 
 struct Args {
-  int nb, nr, K, N, BN, f16, n_add_staged;
+  int nb, nr, K, N, BN, f16, n_add_staged, l2_prefetch;
   int mt_per_utt, m_tiles, n_tiles, pair_tiles;
   int64_t o_r0, o_bs, o_rs;
   nbasr_epilogue epi;
@@ -183,11 +183,24 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_tx = A_STAGE_BYTES + half_bn * BK * 2;
+      // optional L2 prefetch cursor, `l2_prefetch` K blocks ahead of the load cursor (across tile boundaries)
+      int ppt = pair_id, pkb = 0;
+      auto pf_issue = [&]() {
+        if (ppt < p.pair_tiles) {
+          const int pn = ppt % p.n_tiles;
+          const int pm = min(2 * (ppt / p.n_tiles) + (int)rank, p.m_tiles - 1);
+          tma_prefetch_3d(&tmA, pkb * BK, (pm % p.mt_per_utt) * BM, pm / p.mt_per_utt);
+          tma_prefetch_2d(&tmB, pkb * BK, pn * p.BN + (int)rank * half_bn);
+          if (++pkb == num_kb) { pkb = 0; ppt += npairs; }
+        }
+      };
+      for (int i = 0; i < p.l2_prefetch; ++i) pf_issue();
       for (int pt = pair_id; pt < p.pair_tiles; pt += npairs) {
         const int n_idx = pt % p.n_tiles;
         const int m_idx = min(2 * (pt / p.n_tiles) + (int)rank, p.m_tiles - 1);   // odd tile count: the peer repeats the last tile
         const int b = m_idx / p.mt_per_utt, r0 = (m_idx % p.mt_per_utt) * BM;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (p.l2_prefetch) pf_issue();
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
@@ -597,6 +610,7 @@ int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
   Args a{};
   a.nb = g->nb; a.nr = g->nr; a.K = g->K; a.N = g->N;
   a.f16 = g->dtype == NBASR_F16 ? 1 : 0;
+  a.l2_prefetch = nbasr_env_gemm_l2pf();
   a.mt_per_utt = (g->nr + BM - 1) / BM;
   a.m_tiles = a.mt_per_utt * g->nb;
   const int sms = nbasr_sm_count();

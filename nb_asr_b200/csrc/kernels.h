@@ -10,6 +10,7 @@ enum NbasrEnvFlag { NBASR_ENV_FORCE_SIMT = 0, NBASR_ENV_NO_PDL, NBASR_ENV_GCONV_
                     NBASR_ENV_GEMM_DIRECT_EPI, NBASR_ENV_COUNT };
 bool nbasr_env_flag(int which);
 int nbasr_env_gemm_bn();          // NBASR_GEMM_BN tuning override (0 = cost model)
+int nbasr_env_gemm_l2pf();        // NBASR_GEMM_L2PF: K blocks the GEMM producer L2-prefetches ahead of its loads
 double nbasr_env_wgrad_epi_us();  // NBASR_WGRAD_EPI_US cost-model constant (default 3.0)
 
 // "Do once per device" latch for cudaFuncSetAttribute(MaxDynamicSharedMemorySize): the attribute is per (function, device),

@@ -558,6 +558,209 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
   }
 }
 
+// ---------------------------------------------------------------- weight gradient, persistent (round 2)
+// The kernel above pays its set-up (barriers, TMEM allocation, cluster sync, pipeline fill) and its ~3 us fp32 `red.global`
+// drain once per (tile, split) CTA pair -- about half of its time on the step's shapes (ncu r2: tensor pipe 43 % busy, 339
+// CTAs per launch).  Here ONE wave of CTA pairs walks a list of work items (tile, split of the frame range) with TWO TMEM
+// accumulator stages: the drain of item i overlaps the MMAs of item i + 1, and the set-up is paid once.
+//   * tile = 256 output rows (m) x 248 columns (n): the leader CTA feeds N columns 0..127 of the 256-wide MMA, of which
+//     0..119 are X columns n0..n0+119 and 120..127 are (for the first column tile, when a bias gradient is wanted) a
+//     block of ONES planted by a helper warp, so accumulator column 120 = sum_t dY[t][m] = the bias gradient; the peer CTA feeds
+//     columns 128..255 = X columns n0+120..n0+247.  (Without bias those 8 columns duplicate n0+120..n0+127 and are skipped.)
+//   * barriers as in the forward kernel: full[] (+ ready[] = "ones planted") and tempty[] in the leader, empty[] / tfull[] in
+//     both CTAs by multicast commit; the 4 drain warps of each CTA release a TMEM stage with a relaxed remote arrive.
+struct WgArgs3 {
+  int nb, nr, M, N;
+  int m_pairs, n_tiles, chunks_per_utt, total_units, tiles, span;
+  float* dw;
+  int64_t ldw;
+  float* dbias;
+};
+constexpr int WG3_TW = 248;                          // X columns per tile
+constexpr int WG3_THREADS = 224;                     // producer, MMA, ones helper, 4 drain warps
+constexpr int WG3_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(WG3_THREADS, 1)
+gemm_wgrad_persist_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgArgs3 p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto ready_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = blockIdx.x >> 1;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(ready_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);       // 4 drain warps x 2 CTAs (used in the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
+  pdl_launch_dependents();
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  // Stream-K: the (tile, frame unit) space is one line of tiles * total_units K blocks, tile-major; pair i owns the contiguous
+  // span [i * span, (i + 1) * span) and cuts it at tile boundaries into items (m pair, n tile, unit range).  Every pair does the
+  // same number of K blocks (no wave quantisation) and drains ~2 partial tiles instead of one tile per split -- the red.global
+  // traffic of a many-way split saturated L2 atomics when every SM drained continuously (r2: 706 vs 817 TFLOP/s).
+  const int g_begin = pair_id * p.span, g_end = min(p.tiles * p.total_units, g_begin + p.span);
+  const int tile_first = g_begin / p.total_units;
+  auto item_geo = [&](int it, int& mp, int& nt, int& u0, int& u1) -> bool {
+    const int tile = tile_first + it;
+    const int s0 = max(g_begin, tile * p.total_units), s1 = min(g_end, (tile + 1) * p.total_units);
+    if (s0 >= s1) return false;
+    mp = tile % p.m_pairs;
+    nt = tile / p.m_pairs;
+    u0 = s0 - tile * p.total_units;
+    u1 = s1 - tile * p.total_units;
+    return true;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0;; ++it) {
+        int mp, nt, u0, u1;
+        if (!item_geo(it, mp, nt, u0, u1)) break;
+        const int m0 = mp * 2 * BM + (int)rank * BM;
+        const int xc = nt * WG3_TW + (rank ? 120 : 0);
+        for (int u = u0; u < u1; ++u) {
+          const int b = u / p.chunks_per_utt, r0 = (u % p.chunks_per_utt) * BK;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t fb = mapa(full_bar(stage), 0);
+          mbar_expect_tx_cluster(fb, 4 * 64 * 64 * 2);
+          tma2_load_3d(sa, &tmDY, fb, m0, r0, b);
+          tma2_load_3d(sa + 8192, &tmDY, fb, m0 + 64, r0, b);
+          tma2_load_3d(sb, &tmX, fb, xc, r0, b);
+          tma2_load_3d(sb + 8192, &tmX, fb, xc + 64, r0, b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(2 * BM, 256, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0;; ++it) {
+        int mp, nt, u0, u1;
+        if (!item_geo(it, mp, nt, u0, u1)) break;
+        const int as = it & 1;
+        mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int u = u0; u < u1; ++u) {
+          // with a bias gradient EVERY stage goes through the helper warp (it arrives on ready[] once per use, after the
+          // stage has landed), so that the phases of ready[] stay in lockstep with those of the ring
+          mbar_wait(p.dbias != nullptr ? ready_bar(stage) : full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t ad = make_smem_desc(sa + k * 2048, 8192, 1024);
+            uint64_t bd = make_smem_desc(sb + k * 2048, 8192, 1024);
+            umma2_bf16(d_tmem, ad, bd, idesc, (u > u0 || k > 0) ? 1u : 0u);
+          }
+          umma2_commit(empty_bar(stage));
+          if (u == u1 - 1) umma2_commit(tfull_bar(as));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (rank == 0 && p.dbias != nullptr) {
+      // ones block: X columns 120..127 of the leader's half = the last 16-byte chunk of every K row of its second 64-column box
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0;; ++it) {
+        int mp, nt, u0, u1;
+        if (!item_geo(it, mp, nt, u0, u1)) break;
+        for (int u = u0; u < u1; ++u) {
+          mbar_wait(full_bar(stage), phase);
+          if (nt == 0) {
+            uint8_t* xb = smem_al + stage * STAGE_BYTES + A_STAGE_BYTES + 8192;
+            for (int r = lane; r < BK; r += 32)
+              *reinterpret_cast<uint4*>(xb + r * 128 + ((7 ^ (r & 7)) << 4)) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+            fence_async_smem();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    for (int it = 0;; ++it) {
+      int mp, nt, u0, u1;
+      if (!item_geo(it, mp, nt, u0, u1)) break;
+      const bool bias_item = p.dbias != nullptr && nt == 0;
+      const int as = it & 1;
+      const int m = mp * 2 * BM + (int)rank * BM + q * 32 + lane;
+      const int n0 = nt * WG3_TW;
+      mbar_wait(tfull_bar(as), (it >> 1) & 1);
+      tcgen05_fence_after();
+      for (int c = 0; c < 256; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + c, v);
+        if (c == 224) {                       // last chunk is in registers: hand the accumulator stage back before the adds
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(mapa(tempty_bar(as), 0));
+        }
+        if (m < p.M) {
+          // accumulator column j: j < 120 -> X column n0 + j; 120..127 -> ones block (bias) / duplicate; j >= 128 -> n0 + j - 8
+          float* row = p.dw + (int64_t)m * p.ldw;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int j = c + g * 4;
+            if (j >= 120 && j < 128) {
+              if (j == 120 && bias_item) atomicAdd(p.dbias + m, v[g * 4]);
+              continue;
+            }
+            const int col = n0 + (j < 120 ? j : j - 8);
+            if (col < p.N)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + col), "f"(v[g * 4]), "f"(v[g * 4 + 1]),
+                           "f"(v[g * 4 + 2]), "f"(v[g * 4 + 3])
+                           : "memory");
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 // waves x cycles per K block , for the paired tile 256 x BN: four MMAs of max(88, BN/2)
 // cycles against 16 KB of A + 64 BN bytes of B ingest per CTA
 int pick_bn_pair(int N, int m_tiles, int pairs) {
@@ -678,8 +881,45 @@ int sm100_gemm_tn_pair(const nbasr_gemm* g, cudaStream_t st) {
   return 0;
 }
 
+static int sm100_gemm_wgrad_persist(const nbasr_wgrad* g, cudaStream_t st) {
+  WgArgs3 a{};
+  a.nb = g->nb; a.nr = g->nr; a.M = g->M; a.N = g->N;
+  a.m_pairs = (g->M + 2 * BM - 1) / (2 * BM);
+  a.n_tiles = (g->N + WG3_TW - 1) / WG3_TW;
+  a.chunks_per_utt = (g->nr + BK - 1) / BK;
+  a.total_units = a.chunks_per_utt * g->nb;
+  const int sms = nbasr_sm_count();
+  const int slots = std::max(1, sms / 2);
+  a.tiles = a.m_pairs * a.n_tiles;
+  // one contiguous span of K blocks per pair; a pair should carry >= ~12 K blocks (0.27 us each) per ~3 us drain
+  const long total = (long)a.tiles * a.total_units;
+  NBASR_REQUIRE(total < (1L << 30), "wgrad problem too large for 32-bit unit indices");
+  int npairs = (int)std::max(1L, std::min((long)slots, total / 12));
+  a.span = (int)((total + npairs - 1) / npairs);
+  npairs = (int)((total + a.span - 1) / a.span);
+  a.dw = g->dw; a.ldw = g->ldw; a.dbias = g->dbias;
+  CUtensorMap tmDY, tmX;
+  uint64_t dd[3] = {(uint64_t)g->M, (uint64_t)g->nr, (uint64_t)g->nb};
+  int64_t sd[3] = {1, g->dy_rs, g->dy_bs};
+  uint32_t bx[3] = {64, BK, 1};
+  if (sm100_get_map(g->dy, 3, dd, sd, bx, &tmDY)) return 1;
+  uint64_t dx[3] = {(uint64_t)g->N, (uint64_t)g->nr, (uint64_t)g->nb};
+  int64_t sx[3] = {1, g->x_rs, g->x_bs};
+  if (sm100_get_map(g->x, 3, dx, sx, bx, &tmX)) return 1;
+  static DevOnce attr;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG3_SMEM_BYTES);
+    if (e != cudaSuccess) return nbasr_fail("gemm_wgrad_persist smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  cudaError_t e = launch_pdl(gemm_wgrad_persist_kernel, dim3(2 * npairs), dim3(WG3_THREADS), (size_t)WG3_SMEM_BYTES, st, 2, tmDY, tmX, a);
+  if (e != cudaSuccess) return nbasr_fail("gemm_wgrad_persist launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int sm100_gemm_wgrad_pair(const nbasr_wgrad* g, cudaStream_t st) {
   NBASR_REQUIRE(g->N % 4 == 0 && g->ldw % 4 == 0, "wgrad N / ldw must be multiples of 4");
+  if (!nbasr_env_flag(NBASR_ENV_WGRAD_V1)) return sm100_gemm_wgrad_persist(g, st);
   WgArgs2 a{};
   a.nb = g->nb; a.nr = g->nr; a.M = g->M; a.N = g->N;
   a.BN = g->N >= 256 ? 256 : ((g->N + 127) / 128) * 128;      // each CTA loads BN/2 columns in whole 64-column boxes

@@ -7,7 +7,7 @@
 
 // Environment switches are read ONCE, when the library is loaded (api.cu), never on the call path.
 enum NbasrEnvFlag { NBASR_ENV_FORCE_SIMT = 0, NBASR_ENV_NO_PDL, NBASR_ENV_GCONV_NO_PREFETCH, NBASR_ENV_LSTM_SS, NBASR_ENV_DEBUG,
-                    NBASR_ENV_GEMM_DIRECT_EPI, NBASR_ENV_COUNT };
+                    NBASR_ENV_GEMM_DIRECT_EPI, NBASR_ENV_WGRAD_V1, NBASR_ENV_COUNT };
 bool nbasr_env_flag(int which);
 int nbasr_env_gemm_bn();          // NBASR_GEMM_BN tuning override (0 = cost model)
 int nbasr_env_gemm_l2pf();        // NBASR_GEMM_L2PF: K blocks the GEMM producer L2-prefetches ahead of its loads

@@ -211,9 +211,11 @@ def test_two_rank_nccl_step_equals_single_process_step(precision, tmp_path):
     assert res['ranks_equal'], 'replicas diverged'
     assert res['loss0_rel'] < 1e-6, res                 # same forward arithmetic per utterance
     # the exchanged gradient (mean over ranks + regulariser) equals the single-process gradient of the whole batch up to
-    # fp32 summation order; the Adam update it produces agrees accordingly
+    # fp32 summation order.  The Adam update's first steps are -lr * sign(g) wherever |g| >> eps = 1e-7, so the ~1e-6 summation
+    # noise flips whole +-lr steps on the elements whose true gradient is 0 (biases in front of a LayerNorm): the update is
+    # compared on the elements with a significant reference gradient, the parameters themselves with a bound of a few flips
     assert res['grad_rel'] < (1e-5 if precision == 'fp32' else 1e-4), res
-    assert res['update_rel'] < (1e-3 if precision == 'fp32' else 1e-2), res
-    assert res['params_rel'] < 1e-6, res
+    assert res['sig_frac'] > 0.5 and res['update_rel_sig'] < 5e-2, res
+    assert res['params_rel'] < 2e-3, res
     assert res['loss2_rel'] < (1e-4 if precision == 'fp32' else 2e-2), res
     assert res['used_graph'] and res['buckets'] == 5

@@ -539,6 +539,22 @@ class Engine:
             call(lst, lib.nbasr_gemm_wgrad, C.byref(w))
             pl.keep.append(w)
 
+        # Chains of grouped-conv edges (a cell's consecutive conv nodes forward, their input gradients backward) run as ONE
+        # launch each (nbasr_gconv_chain).  The flag / epoch work buffer is shared by every chain of the plan (one stream).
+        t_blk, tt = [], T
+        for s_ in TR_STRIDES:
+            tt = tt if s_ == 1 else (tt + 1) // 2
+            t_blk.append(tt)
+        wbytes = max(int(lib.nbasr_gconv_chain_work_bytes(B, t_blk[i_], FILTERS[i_], FILTERS[i_] // 100, 3)) for i_ in range(4))
+        pl.chain_work = arena.zeros(((wbytes + 3) // 4,), torch.int32)
+
+        def flush_chain(lst, chain):
+            if not chain:
+                return
+            arr = (GConv * len(chain))(*chain)
+            call(lst, lib.nbasr_gconv_chain, arr, len(chain), pl.chain_work.data_ptr(), pl.chain_work.numel() * 4)
+            del chain[:]
+
         # ---- input
         pl.audio = arena.zeros((B, FEATURES, T), torch.float32)
         g_in = _Geo(B, T, FEATURES)
@@ -585,6 +601,7 @@ class Engine:
             for cellname in self.block_cells[i]:
                 outs = [cur]
                 crec = dict(name=cellname, outs=outs, masks=[], nodes=[])
+                chain = []
                 for n, node in enumerate(arch):
                     op, branches = node[0], node[1:]
                     src = outs[-1]
@@ -595,6 +612,8 @@ class Engine:
                     pn = f'{cellname}.nodes.{n}.op'
                     nrec = dict(op=op, branches=list(branches), pn=pn, mask=None, salt=0)
                     adds = [t.data_ptr() for t in skips]
+                    if op not in CONV_EDGES:
+                        flush_chain(fwd, chain)
                     if op == 'zero':
                         epi = self._epi(Cc, adds=adds, out=o.data_ptr(), fwd=True, copy=cptr(o))
                         call(fwd, lib.nbasr_eltwise, adt, None, Cc, B, Ti, Tp, Cc, C.byref(epi))
@@ -623,11 +642,12 @@ class Engine:
                                 gc.w, gc.w_packed = self.P(pn + '.conv.weight'), 0
                             gc.epi = self._epi(Cc, bias=self.P(pn + '.conv.bias'), relu=1, drop_p=drop_p, salt=sl, adds=adds,
                                                out=o.data_ptr(), mask_out=mask, mask_rows=geo.rows, fwd=True, copy=cptr(o))
-                            call(fwd, lib.nbasr_gconv_fwd, C.byref(gc))
+                            chain.append(gc)
                             pl.keep.append(gc)
                             nrec.update(k=k, d=d, lp=lp)
                     crec['nodes'].append(nrec)
                     outs.append(o)
+                flush_chain(fwd, chain)
                 if m.use_norm:
                     co = zact(geo.rows, Cc, copy=True)
                     mean = zbuf(geo.rows, 1, torch.float32)
@@ -707,7 +727,9 @@ class Engine:
         pools = []
         for geo in pl.block_geo:
             pools.append([zbuf(geo.rows, geo.C) for _ in range(5)])
-        dzs = [[zbuf(geo.rows, geo.C) for _ in range(2)] for geo in pl.block_geo]
+        # one dZ buffer per node: a chain writes dZ_{j-1} while neighbouring CTAs still read dZ_j, and the weight gradients of
+        # the whole chain run after it
+        dzs = [[zbuf(geo.rows, geo.C) for _ in range(max(2, len(arch)))] for geo in pl.block_geo]
 
         gout = pools[3].pop()
         if m.use_rnn:
@@ -780,7 +802,7 @@ class Engine:
                     g[nn_] = pool.pop()
                     dz_t = None
                     if last['op'] != 'zero':
-                        dz_t = dz[(nn_ - 1) & 1]
+                        dz_t = dz[nn_ - 1]
                         dzb[nn_ - 1] = dz_t
                     call(bwd, lib.nbasr_layernorm_bwd, dt, gout.data_ptr(), outs[nn_].data_ptr(), adt, S, crec['mean'].data_ptr(),
                          crec['rstd'].data_ptr(), self.P(crec['name'] + '.norm_layer.weight'), B, Ti, Tp, Cc,
@@ -792,11 +814,20 @@ class Engine:
                 else:
                     g[nn_] = gout
                     if last['op'] != 'zero':
-                        dz_t = dz[(nn_ - 1) & 1]
+                        dz_t = dz[nn_ - 1]
                         dzb[nn_ - 1] = dz_t
                         epi = self._epi(Cc, out2=dz_t.data_ptr(), mask2=last['mask'], scale2=dscale, mask_rows=geo.rows)
                         call(bwd, lib.nbasr_eltwise, dt, gout.data_ptr(), Cc, B, Ti, Tp, Cc, C.byref(epi))
                         pl.keep.append(epi)
+                chain, chain_wg = [], []
+
+                def flush_bwd():
+                    # input-gradient chain first (it produces the dZ of every node), then the chain's weight gradients
+                    flush_chain(bwd, chain)
+                    for a_ in chain_wg:
+                        call(bwd, lib.nbasr_gconv_wgrad, *a_)
+                    del chain_wg[:]
+
                 for j in range(nn_ - 1, -1, -1):
                     nrec = nodes[j]
                     op, pn = nrec['op'], nrec['pn']
@@ -807,9 +838,11 @@ class Engine:
                     # the epilogue that produces g[j] also emits dZ_{j-1} = g[j] * mask_{j-1}
                     o2, m2 = 0, None
                     if j >= 1 and nodes[j - 1]['op'] != 'zero':
-                        dzb[j - 1] = dz[(j - 1) & 1]
+                        dzb[j - 1] = dz[j - 1]
                         o2, m2 = dzb[j - 1].data_ptr(), nodes[j - 1]['mask']
                     epi = self._epi(Cc, adds=adds, out=g[j].data_ptr(), out2=o2, mask2=m2, scale2=dscale, mask_rows=geo.rows)
+                    if op not in CONV_EDGES:
+                        flush_bwd()
                     if op == 'zero':
                         call(bwd, lib.nbasr_eltwise, dt, None, Cc, B, Ti, Tp, Cc, C.byref(epi))
                         pl.keep.append(epi)
@@ -824,15 +857,16 @@ class Engine:
                     else:
                         d = dzb[j]
                         k, dd, lp = nrec['k'], nrec['d'], nrec['lp']
-                        call(bwd, lib.nbasr_gconv_wgrad, dt, d.data_ptr(), Bc(src).data_ptr(), B, Ti, Tp, Cc, Cc // 100, k, -lp, dd,
-                             self.G(pn + '.conv.weight'), self.G(pn + '.conv.bias'))
+                        chain_wg.append((dt, d.data_ptr(), Bc(src).data_ptr(), B, Ti, Tp, Cc, Cc // 100, k, -lp, dd,
+                                         self.G(pn + '.conv.weight'), self.G(pn + '.conv.bias')))
                         gc = GConv()
                         gc.dtype, gc.x, gc.B, gc.T, gc.Tp, gc.C, gc.cpg = dt, d.data_ptr(), B, Ti, Tp, Cc, Cc // 100
                         gc.ktaps, gc.off0, gc.dstep, gc.w = k, lp - (k - 1) * dd, dd, self.wt[pn].data_ptr()
                         gc.w_packed = 3 if dt == BF16 else 0      # packed | stable
                         gc.epi = epi
-                        call(bwd, lib.nbasr_gconv_fwd, C.byref(gc))
+                        chain.append(gc)
                         pl.keep.append(gc)
+                flush_bwd()
                 for k in range(1, nn_ + 1):   # (without norm, g[nn_] is the consumed incoming buffer)
                     pool.append(g[k])
                 gout = g[0]

@@ -43,6 +43,14 @@ def op_work(fn_name, args, es):
         n_t = 1 + g.epi.n_add + (1 if g.epi.out else 0) + (1 if (g.epi.out2 and g.epi.mask2) else 0)     # tensors read/written once
         n_m = (1 if g.epi.mask_out else 0) + (1 if g.epi.mask2 else 0)                 # 1 bit / element each
         return f'gconv C={g.C} k={g.ktaps} d={g.dstep}', 2.0 * el * g.cpg * g.ktaps, el * es * n_t + el * n_m / 8.0
+    if fn_name == 'nbasr_gconv_chain':
+        # a chain launch processes n nodes: algorithmic work = the sum of its nodes' (SURVEY.md 8d per-node figures)
+        fl = by = 0.0
+        for i in range(args[1]):
+            _, f1, b1 = op_work('nbasr_gconv_fwd', (C.byref(args[0][i]),), es)
+            fl, by = fl + f1, by + b1
+        g = args[0][0]
+        return f'gconv C={g.C} x{args[1]}', fl, by
     if fn_name == 'nbasr_gconv_wgrad':
         dt, dz, x, B, T, Tp, Cc, cpg, k = args[:9]
         el = B * T * Cc
@@ -66,6 +74,8 @@ def op_work(fn_name, args, es):
 def gconv_issue_floor_cycles(fn_name, args):
     """Structural floor of the tcgen05 grouped-conv forward / input-gradient kernel: 3*k MMAs of N = 48 per
     128-frame x 48-channel tile, each >= 88 cycles of tensor-pipe issue (both operands in shared memory), on one SM."""
+    if fn_name == 'nbasr_gconv_chain':
+        return sum(gconv_issue_floor_cycles('nbasr_gconv_fwd', (C.byref(args[0][i]),)) for i in range(args[1]))
     if fn_name != 'nbasr_gconv_fwd':
         return 0.0
     g = _struct_of(args[0], GConv)

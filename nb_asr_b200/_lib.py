@@ -43,7 +43,7 @@ _SIGS = {
     'nbasr_gemm_tn': [C.POINTER(Gemm), _vp],
     'nbasr_gemm_wgrad': [C.POINTER(Wgrad), _vp],
     'nbasr_gconv_fwd': [C.POINTER(GConv), _vp],
-    'nbasr_gconv_chain': [C.POINTER(GConv), C.c_int, _vp, _i64, _vp],
+    'nbasr_gconv_chain': [C.POINTER(GConv), C.c_int, C.c_int, _vp, _i64, _vp],
     'nbasr_gconv_chain_work_bytes': [C.c_int] * 5,
     'nbasr_pack_gconv_dgrad': [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp],
     'nbasr_pack_gconv_mma': [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],

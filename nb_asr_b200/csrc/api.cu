@@ -23,7 +23,7 @@ struct EnvState {
   double wgrad_epi_us;
   EnvState() {
     static const char* names[NBASR_ENV_COUNT] = {"NBASR_FORCE_SIMT", "NBASR_NO_PDL", "NBASR_GCONV_NO_PREFETCH", "NBASR_LSTM_SS",
-                                                 "NBASR_DEBUG", "NBASR_GEMM_DIRECT_EPI", "NBASR_WGRAD_V1", "NBASR_GCONV_NO_CHAIN"};
+                                                 "NBASR_DEBUG", "NBASR_GEMM_DIRECT_EPI", "NBASR_WGRAD_V1"};
     for (int i = 0; i < NBASR_ENV_COUNT; ++i) {
       const char* v = getenv(names[i]);      // set and non-empty and not "0"
       flag[i] = v != nullptr && v[0] != 0 && !(v[0] == '0' && v[1] == 0);

@@ -246,12 +246,12 @@ int nbasr_gconv_fwd(const nbasr_gconv* p, void* stream) {
   return 0;
 }
 
-int nbasr_gconv_chain(const nbasr_gconv* nodes, int n, void* work, int64_t work_bytes, void* stream) {
+int nbasr_gconv_chain(const nbasr_gconv* nodes, int n, int fused, void* work, int64_t work_bytes, void* stream) {
   NBASR_REQUIRE(nodes != nullptr && n >= 1 && n <= 3, "chain of 1..3 grouped-conv edges");
   if (nodes[0].B <= 0 || nodes[0].T <= 0) return 0;
   bool packed = true;
   for (int i = 0; i < n; ++i) packed = packed && (nodes[i].w_packed & 1) && nodes[i].dtype != NBASR_F32;
-  if (packed) return sm100_gconv_chain(nodes, n, work, work_bytes, as_stream(stream));
+  if (packed) return sm100_gconv_chain(nodes, n, fused, work, work_bytes, as_stream(stream));
   for (int i = 0; i < n; ++i)       // fp32 / unpacked weights: the SIMT kernel, node by node
     if (nbasr_gconv_fwd(nodes + i, stream)) return 1;
   return 0;

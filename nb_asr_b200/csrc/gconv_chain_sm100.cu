@@ -76,15 +76,83 @@ __device__ __forceinline__ void wait_flag(const uint32_t* f, uint32_t done, uint
     }
   }
 }
-// v[0..8) += 16 bytes of a 16-bit tensor, read through L2 only
-__device__ __forceinline__ void add8_cg(const void* base, int dtype, int64_t idx, float* v) {
-  const uint4 r = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + idx));
+// v[0..8) += 16 bytes of a 16-bit tensor.  cg: read through L2 only.  Needed when a slab is not a whole number of 32-byte
+// sectors (40-channel slabs): the neighbouring slab's CTA may then have pulled a sector into this SM's L1 before the bytes
+// of THIS slab -- produced earlier in the same launch -- were written.  48-channel slabs own their sectors: cached loads.
+__device__ __forceinline__ void add8_cg(const void* base, int dtype, int64_t idx, float* v, bool cg = true) {
+  const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + idx);
+  const uint4 r = cg ? __ldcg(q) : *q;
   const uint32_t* h = reinterpret_cast<const uint32_t*>(&r);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float2 f = dtype == NBASR_F16 ? f16x2_to_f2(h[i]) : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h[i]));
     v[2 * i] += f.x;
     v[2 * i + 1] += f.y;
+  }
+}
+
+// ---- packed fp32 pairs (FFMA2 / FMUL2)
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// Specialised epilogue of one thread's 24 accumulator columns, for the configurations the train / eval step actually uses
+// (full slab, no dropout, no skip operand): straight-line code, packed fp32 arithmetic, outputs left PACKED in registers.
+// The runtime-configurable path below spends ~630 issued instructions per warp and tile, most of them branches and flag
+// tests (ncu r2: the kernel ran at IPC 2.0 = the issue limit of the fma / alu pipes, i.e. it was bound by its own epilogue,
+// at twice the MMA issue floor).  Arithmetic is identical to the general path (same fma, same roundings).
+//   RELU : z = acc * acc_s + bias, gate bit = (0 < z <= hi), z = clamp(z, 0, hi)      (forward edge)
+//          else z = acc                                                              (input gradient: no bias, acc_s = 1)
+//   F16OUT: `out` is fp16 (else bf16);  O2K: 0 no second output, 1 bf16(z * scale2) (the weight gradient's unscaled copy),
+//          2 bf16(z * scale2) where the gate bit of w2 is set, else 0 (dZ of the previous node)
+template <bool RELU, bool F16OUT, int O2K>
+__device__ __forceinline__ void tile_fast(const float* v, const float4* bias4, float acc_s, float relu_hi, uint32_t hi_bits,
+                                          const uint32_t* w2, float scale2, uint32_t* po, uint32_t* po2, uint32_t* m,
+                                          const nbasr_epilogue& epi, int64_t eidx, bool cg) {
+  const u64 as2 = pk2(acc_s, acc_s), sc2 = pk2(scale2, scale2);
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    float z[8];
+    uint32_t mm = 0xffu;
+    if (RELU) {
+      const float4 b0 = bias4[2 * g], b1 = bias4[2 * g + 1];
+      upk2(fma2(pk2(v[g * 8 + 0], v[g * 8 + 1]), as2, pk2(b0.x, b0.y)), z[0], z[1]);
+      upk2(fma2(pk2(v[g * 8 + 2], v[g * 8 + 3]), as2, pk2(b0.z, b0.w)), z[2], z[3]);
+      upk2(fma2(pk2(v[g * 8 + 4], v[g * 8 + 5]), as2, pk2(b1.x, b1.y)), z[4], z[5]);
+      upk2(fma2(pk2(v[g * 8 + 6], v[g * 8 + 7]), as2, pk2(b1.z, b1.w)), z[6], z[7]);
+      mm = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        // 0 < z <= hi  <=>  bits(z) - 1 < bits(hi) as unsigned (negative z and +0 wrap to huge values)
+        mm |= ((__float_as_uint(z[i]) - 1u) < hi_bits) ? (1u << i) : 0u;
+        z[i] = fminf(fmaxf(z[i], 0.f), relu_hi);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] = v[g * 8 + i];
+    }
+    m[g] = mm;
+    for (int a = 0; a < epi.n_add; ++a) add8_cg(epi.add[a], epi.add_dtype, eidx + g * 8, z, cg);      // skip-connection sum
+#pragma unroll
+    for (int k = 0; k < 4; ++k) po[g * 4 + k] = F16OUT ? f2_to_f16x2(z[2 * k], z[2 * k + 1]) : f2_to_bf16x2(z[2 * k], z[2 * k + 1]);
+    if (O2K == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a, b;
+        upk2(mul2(pk2(z[2 * k], z[2 * k + 1]), sc2), a, b);
+        po2[g * 4 + k] = f2_to_bf16x2(a, b);
+      }
+    } else if (O2K == 2) {
+      const uint32_t w = w2[g];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = ((w >> (2 * k)) & 1u) ? z[2 * k] * scale2 : 0.f;
+        const float b = ((w >> (2 * k + 1)) & 1u) ? z[2 * k + 1] * scale2 : 0.f;
+        po2[g * 4 + k] = f2_to_bf16x2(a, b);
+      }
+    }
   }
 }
 
@@ -115,7 +183,7 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
   const int lane_id = blockIdx.x / p.nslabs;
   const int c0 = slab * p.OUT;
   // contiguous range of frame tiles: only its two ends depend on other CTAs
-  const bool strided = (p.dbg & 4) != 0;       // (timing experiment: the strided assignment of gconv_mma_fwd_kernel)
+  const bool strided = (p.dbg & 4) != 0;       // (timing experiment only: the strided assignment of gconv_mma_fwd_kernel)
   const int tb = strided ? lane_id : (int)((int64_t)lane_id * p.ntiles / p.nlanes);
   const int te = strided ? p.ntiles : (int)((int64_t)(lane_id + 1) * p.ntiles / p.nlanes);
   const int tstep = strided ? p.nlanes : 1;
@@ -263,6 +331,7 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
     const int cbeg = c0 + 24 * hh;
     const int nvalid = max(0, min(24, min(p.C, c0 + p.OUT) - cbeg));     // multiple of 8
     const int OUTB = p.OUT * 2;              // staged row pitch in bytes
+    const bool cg_adds = (OUTB & 31) != 0;   // slabs that share 32-byte sectors with their neighbours (see add8_cg)
     int it = 0;
     // (thread etid 0) Landing of the TMA stores is observed in BATCHES: `cp.async.bulk.wait_group` (the full-completion
     // form) compiles to DEPBAR + CCTL.IVALL -- it invalidates the SM's whole L1 -- so it runs once per PUBLISH_EVERY tiles
@@ -283,6 +352,13 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
       if (etid < NW) bsm[etid] = (epi.bias && c0 + etid < min(p.C, c0 + p.OUT)) ? __ldg(epi.bias + c0 + etid) * bias_s : 0.f;
       named_bar_sync(1, NEPI);
       const float4* bias4 = reinterpret_cast<const float4*>(bsm + 24 * hh);
+      // specialised epilogue (tile_fast) when this node's configuration is one of the six the step uses; -1: general path
+      int mode = -1;
+      if (nvalid == 24 && epi.drop_p == 0.f && (epi.n_add == 0 || epi.add_dtype != NBASR_F32) && epi.out && !(p.dbg & 16) && (!epi.out2 || epi.out2_dtype == NBASR_BF16)) {
+        const int o2k = !epi.out2 ? 0 : (epi.mask2 ? 2 : 1);
+        if (epi.relu20 && o2k != 2) mode = (epi.out_dtype == NBASR_F16 ? 0 : 2) + o2k;              // 0..3
+        else if (!epi.relu20 && !epi.bias && acc_s == 1.f && epi.out_dtype == NBASR_BF16 && o2k != 1) mode = 4 + (o2k >> 1);   // 4, 5
+      }
       for (int tile = tb; tile < te; tile += tstep, ++it) {
         const int as = it % NACC;
         const uint32_t aphase = (it / NACC) & 1;
@@ -319,30 +395,18 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
         const bool rowok = t < p.T;
         const int64_t rho = (int64_t)b * p.Tp + NBASR_PAD_L + t;
         uint32_t m[3] = {0, 0, 0};
-        if (rowok) {
-          if (nvalid == 24 && epi.drop_p == 0.f && epi.n_add == 0) {
-            // lean path (every forward of a skip-free node, most input-gradients)
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-              uint32_t mm = 0xffu;
-              const float4 b0 = bias4[2 * g], b1 = bias4[2 * g + 1];
-              const float bias_r[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-              if (epi.relu20) {
-                mm = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float z = fmaf(v[g * 8 + i], acc_s, bias_r[i]);
-                  // 0 < z <= hi  <=>  bits(z) - 1 < bits(hi) as unsigned (negative z and +0 wrap to huge values)
-                  mm |= ((__float_as_uint(z) - 1u) < hi_bits) ? (1u << i) : 0u;
-                  v[g * 8 + i] = fminf(fmaxf(z, 0.f), relu_hi);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[g * 8 + i] = fmaf(v[g * 8 + i], acc_s, bias_r[i]);
-              }
-              m[g] = mm;
-            }
-          } else {
+        uint32_t po[12], po2[12];            // this thread's 24 columns of `out` / `out2`, packed 16-bit pairs
+        if (rowok && mode >= 0) {
+          switch (mode) {
+            case 0: tile_fast<true, true, 0>(v, bias4, acc_s, relu_hi, hi_bits, w2, epi.scale2, po, po2, m, epi, rho * epi.ld_out + cbeg, cg_adds); break;
+            case 1: tile_fast<true, true, 1>(v, bias4, acc_s, relu_hi, hi_bits, w2, epi.scale2, po, po2, m, epi, rho * epi.ld_out + cbeg, cg_adds); break;
+            case 2: tile_fast<true, false, 0>(v, bias4, acc_s, relu_hi, hi_bits, w2, epi.scale2, po, po2, m, epi, rho * epi.ld_out + cbeg, cg_adds); break;
+            case 3: tile_fast<true, false, 1>(v, bias4, acc_s, relu_hi, hi_bits, w2, epi.scale2, po, po2, m, epi, rho * epi.ld_out + cbeg, cg_adds); break;
+            case 4: tile_fast<false, false, 0>(v, bias4, acc_s, relu_hi, hi_bits, w2, epi.scale2, po, po2, m, epi, rho * epi.ld_out + cbeg, cg_adds); break;
+            default: tile_fast<false, false, 2>(v, bias4, acc_s, relu_hi, hi_bits, w2, epi.scale2, po, po2, m, epi, rho * epi.ld_out + cbeg, cg_adds); break;
+          }
+        } else {
+          if (rowok) {
 #pragma unroll
             for (int g = 0; g < 6; ++g) {
               const float4 bq = bias4[g];
@@ -356,12 +420,24 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
             for (int a = 0; a < epi.n_add; ++a) {
 #pragma unroll
               for (int g = 0; g < 3; ++g)
-                if (g * 8 < nvalid) add8_cg(epi.add[a], epi.add_dtype, rho * epi.ld_out + cbeg + g * 8, v + g * 8);
+                if (g * 8 < nvalid) add8_cg(epi.add[a], epi.add_dtype, rho * epi.ld_out + cbeg + g * 8, v + g * 8, cg_adds);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 24; ++i) v[i] = 0.f;      // rows past the utterance land on zero pad rows / are clipped
+          }
+          const bool o16 = epi.out_dtype == NBASR_F16, o216 = epi.out2_dtype == NBASR_F16;
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const uint32_t w = w2[g];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float a = v[g * 8 + 2 * k], b2 = v[g * 8 + 2 * k + 1];
+              po[g * 4 + k] = o16 ? f2_to_f16x2(a, b2) : f2_to_bf16x2(a, b2);
+              const float a2 = ((w >> (2 * k)) & 1u) ? a * epi.scale2 : 0.f, c2 = ((w >> (2 * k + 1)) & 1u) ? b2 * epi.scale2 : 0.f;
+              po2[g * 4 + k] = o216 ? f2_to_f16x2(a2, c2) : f2_to_bf16x2(a2, c2);
             }
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 24; ++i) v[i] = 0.f;      // rows past the utterance land on zero pad rows / are clipped
         }
         // staging buffers are free once the previous tile's TMA stores have finished READING shared memory
         if (etid == 0) bulk_wait_read0();
@@ -370,14 +446,9 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
           if (g * 8 < nvalid) {
-            if (epi.out) store8_h(orow + g * 16, epi.out_dtype, v + g * 8);
-            if (epi.out2) {
-              const uint32_t w = w2[g];
-              float t2[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) t2[i] = ((w >> i) & 1u) ? v[g * 8 + i] * epi.scale2 : 0.f;
-              store8_h(orow + OSTAGE_BYTES + g * 16, epi.out2_dtype, t2);
-            }
+            *reinterpret_cast<uint4*>(orow + g * 16) = make_uint4(po[g * 4], po[g * 4 + 1], po[g * 4 + 2], po[g * 4 + 3]);
+            if (epi.out2)
+              *reinterpret_cast<uint4*>(orow + OSTAGE_BYTES + g * 16) = make_uint4(po2[g * 4], po2[g * 4 + 1], po2[g * 4 + 2], po2[g * 4 + 3]);
           }
           if (epi.mask_out) mst[row * 8 + 3 * hh + g] = (g * 8 < nvalid) ? (uint8_t)m[g] : (uint8_t)0;   // 8-byte entry per row
         }
@@ -437,19 +508,9 @@ int64_t sm100_gconv_chain_work_bytes(int B, int T, int C, int cpg, int n) {
   return (CH_WORK_HDR + (int64_t)n * nslabs * ntiles) * 4;
 }
 
-int sm100_gconv_chain(const nbasr_gconv* g, int n, void* work, int64_t work_bytes, cudaStream_t st) {
-  NBASR_REQUIRE((n >= 1 && n <= MAXCHAIN) || n == -1, "chain length");
-  if (n > 1 && (nbasr_env_chain_dbg() & 8)) {       // (timing experiment: the chain kernel, one node per launch)
-    for (int i = 0; i < n; ++i) {
-      nbasr_gconv one[2] = {g[i], g[i]};
-      one[1].x = g[i].epi.out ? g[i].epi.out : g[i].epi.out2;
-      if (sm100_gconv_chain(one, -1, work, work_bytes, st)) return 1;
-    }
-    return 0;
-  }
-  const bool single = n == -1;
-  if (single) n = 1;
-  if (nbasr_env_flag(NBASR_ENV_GCONV_NO_CHAIN) || (n == 1 && !single)) {
+int sm100_gconv_chain(const nbasr_gconv* g, int n, int fused, void* work, int64_t work_bytes, cudaStream_t st) {
+  NBASR_REQUIRE(n >= 1 && n <= MAXCHAIN, "chain length");
+  if (!fused || n == 1) {       // one launch of gconv_mma_fwd_kernel per node (programmatic dependent launches)
     for (int i = 0; i < n; ++i)
       if (sm100_gconv_fwd(g + i, st)) return 1;
     return 0;

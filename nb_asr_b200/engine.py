@@ -128,6 +128,8 @@ class Engine:
         self._pack_version = None
         self._bound_ptr = None
         self.training_drop = float(model.dropout_rate)
+        # NBASR_GCONV_CHAIN=1: a cell's chained grouped-conv edges run as ONE persistent launch (nbasr_gconv_chain fused = 1)
+        self.fuse_chains = 1 if os.environ.get('NBASR_GCONV_CHAIN', '0') not in ('', '0') else 0
         self.launches = 0
 
     # ------------------------------------------------------------------ parameter binding
@@ -539,8 +541,9 @@ class Engine:
             call(lst, lib.nbasr_gemm_wgrad, C.byref(w))
             pl.keep.append(w)
 
-        # Chains of grouped-conv edges (a cell's consecutive conv nodes forward, their input gradients backward) run as ONE
-        # launch each (nbasr_gconv_chain).  The flag / epoch work buffer is shared by every chain of the plan (one stream).
+        # Chains of grouped-conv edges (a cell's consecutive conv nodes forward, their input gradients backward) go through
+        # nbasr_gconv_chain: one launch per node by default, ONE launch per chain with NBASR_GCONV_CHAIN=1 (measured slower,
+        # DESIGN.md 3.2).  The flag / epoch work buffer is shared by every chain of the plan (one stream).
         t_blk, tt = [], T
         for s_ in TR_STRIDES:
             tt = tt if s_ == 1 else (tt + 1) // 2
@@ -552,7 +555,7 @@ class Engine:
             if not chain:
                 return
             arr = (GConv * len(chain))(*chain)
-            call(lst, lib.nbasr_gconv_chain, arr, len(chain), pl.chain_work.data_ptr(), pl.chain_work.numel() * 4)
+            call(lst, lib.nbasr_gconv_chain, arr, len(chain), self.fuse_chains, pl.chain_work.data_ptr(), pl.chain_work.numel() * 4)
             del chain[:]
 
         # ---- input

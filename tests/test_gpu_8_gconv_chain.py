@@ -107,7 +107,7 @@ def test_chain_equals_node_by_node(case):
         if rep:
             for o in outs:
                 o.zero_()
-        _lib.check(lib.nbasr_gconv_chain(arr, n, work.data_ptr(), wb, U.stream()), 'gconv_chain')
+        _lib.check(lib.nbasr_gconv_chain(arr, n, 1, work.data_ptr(), wb, U.stream()), 'gconv_chain')
         torch.cuda.synchronize()
         assert int(work[2]) == 0, 'a tile dependency timed out'
         assert int(work[0]) == rep + 1 and int(work[1]) == 0
@@ -132,11 +132,11 @@ def test_chain_graph_replay_and_shared_work_buffer():
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.stream(st):
         for a in arrs:       # warm-up launch outside the capture (attribute opt-in, descriptor cache)
-            _lib.check(lib.nbasr_gconv_chain(a, len(a), work.data_ptr(), wb, st.cuda_stream))
+            _lib.check(lib.nbasr_gconv_chain(a, len(a), 1, work.data_ptr(), wb, st.cuda_stream))
         st.synchronize()
         with torch.cuda.graph(graph, stream=st):
             for a in arrs:
-                _lib.check(lib.nbasr_gconv_chain(a, len(a), work.data_ptr(), wb, st.cuda_stream))
+                _lib.check(lib.nbasr_gconv_chain(a, len(a), 1, work.data_ptr(), wb, st.cuda_stream))
     for rep in range(3):
         for b in built:
             for o in b[1][1]:

@@ -145,14 +145,17 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto add_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4 + w); };      // one per epilogue warp (staged)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + STAGES * STAGE_BYTES + STG_BYTES + 8 * (2 * STAGES + 4 + 16));
 
-  const int warp = threadIdx.x >> 5;
+  // Warp roles: 0 .. EPI_WARPS-1 epilogue, then the producer, then the MMA warp LAST: the issue arbiter prefers the highest warp
+  // id, and as warp 1 the thread that issues the MMAs was starved by the epilogue warps (see gconv_sm100.cu, r2).
+  constexpr int W_PROD = EPI_WARPS, W_MMA = EPI_WARPS + 1;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int num_kb = (p.K + BK - 1) / BK;
   const int half_bn = p.BN >> 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_PROD && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
@@ -169,7 +172,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
+  if (warp == W_MMA) tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
   pdl_launch_dependents();
   tcgen05_fence_before();
   __syncthreads();
@@ -178,7 +181,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
 
-  if (warp == 0) {
+  if (warp == W_PROD) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -212,8 +215,10 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+  } else if (warp == W_MMA) {
+    if (rank == 0) {
+      // the whole warp walks the loop (uniform control flow: descriptors in uniform registers, one add per MMA instead of the
+      // ELECT / R2UR.BROADCAST sequence ptxas emits inside `if (lane == 0)`); one elected lane issues MMAs and commits
       const uint32_t idesc = make_idesc(2 * BM, p.BN, 0, 0, p.f16);
       int stage = 0;
       uint32_t phase = 0;
@@ -228,24 +233,23 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t ad0 = make_smem_desc(sa, 16, 1024), bd0 = make_smem_desc(sa + A_STAGE_BYTES, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024);
-            uint64_t bd = make_smem_desc(sb + k * 32, 16, 1024);
-            umma2_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) umma2_bf16(d_tmem, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            umma2_commit(empty_bar(stage));
+            if (kb == num_kb - 1) umma2_commit(tfull_bar(as));
           }
-          umma2_commit(empty_bar(stage));
-          if (kb == num_kb - 1) umma2_commit(tfull_bar(as));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
     const int q = warp & 3;           // TMEM lane quadrant this warp may access
-    const int sub = (warp - 2) >> 2;  // the NSUB warps of a quadrant take every NSUB-th 32-column chunk
+    const int sub = warp >> 2;        // the NSUB warps of a quadrant take every NSUB-th 32-column chunk
     // staged epilogue state: this warp's two 2 KB boxes and its skip-operand barrier
-    const int ew = warp - 2;
+    const int ew = warp;
     uint8_t* stg = smem_al + STAGES * STAGE_BYTES + ew * ST_WARP_BYTES;
     const uint32_t stg_u = smem_base + STAGES * STAGE_BYTES + ew * ST_WARP_BYTES;
     const uint32_t abar = add_bar(ew);
@@ -412,7 +416,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();                  // nobody leaves (or frees TMEM) while the pair's MMAs / multicasts may still touch it
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tcgen05_fence_after();
     tmem_dealloc2(tmem_base, 512);
   }
@@ -592,11 +596,12 @@ gemm_wgrad_persist_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
   auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
-  const int warp = threadIdx.x >> 5;
+  // warp roles: 0..3 drain (TMEM lane quadrant = warp), 4 ones helper, 5 producer, 6 MMA issue (highest id: issue priority)
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair_id = blockIdx.x >> 1;
-  if (warp == 0 && lane == 0) {
+  if (warp == 5 && lane == 0) {
     prefetch_tmap(&tmDY);
     prefetch_tmap(&tmX);
     for (int s = 0; s < STAGES; ++s) {
@@ -610,7 +615,7 @@ gemm_wgrad_persist_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
+  if (warp == 6) tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
   pdl_launch_dependents();
   tcgen05_fence_before();
   __syncthreads();
@@ -636,7 +641,7 @@ gemm_wgrad_persist_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
     return true;
   };
 
-  if (warp == 0) {
+  if (warp == 5) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -660,8 +665,9 @@ gemm_wgrad_persist_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+  } else if (warp == 6) {
+    if (rank == 0) {
+      // uniform control flow, one elected lane issues (see gemm_tn_pair_kernel)
       const uint32_t idesc = make_idesc(2 * BM, 256, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
@@ -678,20 +684,20 @@ gemm_wgrad_persist_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
           mbar_wait(p.dbias != nullptr ? ready_bar(stage) : full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t ad0 = make_smem_desc(sa, 8192, 1024), bd0 = make_smem_desc(sa + A_STAGE_BYTES, 8192, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            uint64_t ad = make_smem_desc(sa + k * 2048, 8192, 1024);
-            uint64_t bd = make_smem_desc(sb + k * 2048, 8192, 1024);
-            umma2_bf16(d_tmem, ad, bd, idesc, (u > u0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma2_bf16(d_tmem, ad0 + (uint64_t)(k * 128), bd0 + (uint64_t)(k * 128), idesc, (u > u0 || k > 0) ? 1u : 0u);
+            umma2_commit(empty_bar(stage));
+            if (u == u1 - 1) umma2_commit(tfull_bar(as));
           }
-          umma2_commit(empty_bar(stage));
-          if (u == u1 - 1) umma2_commit(tfull_bar(as));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == 4) {
     if (rank == 0 && p.dbias != nullptr) {
       // ones block: X columns 120..127 of the leader's half = the last 16-byte chunk of every K row of its second 64-column box
       int stage = 0;
@@ -755,7 +761,7 @@ gemm_wgrad_persist_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 1) {
+  if (warp == 6) {
     tcgen05_fence_after();
     tmem_dealloc2(tmem_base, 512);
   }

@@ -84,6 +84,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of the (converged) warp: the predicate of elect.sync.  Used so that the thread that issues tcgen05.mma sits in
+// WARP-UNIFORM control flow -- inside `if (lane == 0)` ptxas keeps every descriptor in vector registers and wraps each MMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~20 instructions per MMA); in uniform code the operands live in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+// warp index that the compiler can prove uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

@@ -1,7 +1,8 @@
 """nbasr_gconv_chain (several grouped-conv edges of a cell in one launch) == the same edges launched one by one.
 
 The chain kernel runs the same tile engine as nbasr_gconv_fwd (itself pinned to F.conv1d(groups=100) + autograd in
-test_gpu_1_kernels.py), so the comparison is BIT-exact; what is under test is the cross-CTA tile dependency protocol
+test_gpu_1_kernels.py): input-gradient chains are compared BIT-exactly, forward chains to 16-bit rounding (the fused
+kernel evaluates ReLU20 as fma.sat on z / hi); what is under test is the cross-CTA tile dependency protocol
 (flags / epoch in the work buffer), the node-boundary hand-over of the weight tile, skip-sum operands produced inside the
 chain, repeated launches on one work buffer and CUDA-graph replay.  Reference: model.py:13-22,49-59."""
 import ctypes as C
@@ -24,12 +25,21 @@ def _pack(lib, w, Cc, cpg, k, transposed, dt):
     return out
 
 
-def _same(a, b, Cc):
-    """bit equality; of a gate-bit plane entry (8 bytes per row) only the slab's 6 (or 5) bytes are defined"""
+def _same(a, b, Cc, exact=True):
+    """exact: bit equality.  Otherwise (forward chains: the fused kernel's ReLU20 runs as fma.sat on z / hi, see tile_fast in
+    gconv_chain_sm100.cu) outputs agree to 16-bit rounding and gate bits differ on < 1e-3 of the elements.
+    Of a gate-bit plane entry (8 bytes per row) only the slab's 6 (or 5) bytes are defined."""
     if a.dtype == torch.uint8:
         nb = (40 if Cc // 100 == 10 else 48) // 8
-        return torch.equal(a[..., :nb], b[..., :nb])
-    return torch.equal(a, b)
+        x, y = a[..., :nb], b[..., :nb]
+        if exact:
+            return torch.equal(x, y)
+        diff = (x ^ y).to(torch.int32)
+        nbits = sum(((diff >> i) & 1).sum().item() for i in range(8))
+        return nbits < 1e-3 * x.numel() * 8
+    if exact:
+        return torch.equal(a, b)
+    return U.relerr(a.float(), b.float()) < 2e-3
 
 
 def _build(lib, Cc, B, T, ops, skips, dt, backward, seed):
@@ -112,7 +122,7 @@ def test_chain_equals_node_by_node(case):
         assert int(work[2]) == 0, 'a tile dependency timed out'
         assert int(work[0]) == rep + 1 and int(work[1]) == 0
         for a, b in zip(outs, ref_outs):
-            assert _same(a, b, Cc), (case, rep)
+            assert _same(a, b, Cc, exact=backward), (case, rep)
     assert float(ref_outs[0].float().abs().sum()) > 0
 
 
@@ -144,6 +154,6 @@ def test_chain_graph_replay_and_shared_work_buffer():
         graph.replay()
         torch.cuda.synchronize()
         assert int(work[2]) == 0
-        for (_, ref_outs, _), (_, outs, _) in built:
+        for ((_, ref_outs, _), (_, outs, _)), bwd in zip(built, [sp[6] for sp in specs]):
             for a, b in zip(outs, ref_outs):
-                assert _same(a, b, b.shape[-1] if b.dtype != torch.uint8 else (1000 if b.shape[0] == 25 else 600)), rep
+                assert _same(a, b, b.shape[-1] if b.dtype != torch.uint8 else (1000 if b.shape[0] == 25 else 600), exact=bwd), rep

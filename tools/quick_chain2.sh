@@ -1,15 +1,5 @@
 #!/bin/bash
-timeout 300 python -m pytest tests/test_gpu_8_gconv_chain.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python -m pytest tests/test_gpu_8_gconv_chain.py -m gpu -x -q 2>&1 | tail -5
 python tools/one_chain.py
-OPS=conv7d2,conv7d2,conv7d2 SKIPS=1 python tools/one_chain.py
-OPS=conv7d2,conv7d2,conv7d2 SKIPS=1 BWD=1 python tools/one_chain.py
-C=1000 OPS=conv7d2,conv7d2,conv7d2 SKIPS=1 python tools/one_chain.py
-for nc in 0 1; do
-for arch in default c7d2_skips; do
-  NBASR_GCONV_NO_CHAIN=$nc timeout 300 python bench.py --arch $arch --steps 10 --warmup 3 --profile --no-cpu-baseline --no-extra 2>gpurun_out/full_prof_${arch}_$nc.txt | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-f=d['roofline']['families']
-print('nochain=$nc $arch', 'step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],3), {k:(v['ms'],v['n']) for k,v in f.items() if 'gconv' in k})"
-done
-done
+NBASR_CHAIN_DBG=16 python tools/one_chain.py
+bash tools/quick_chain5.sh | tail -2 | cut -c1-600

@@ -245,9 +245,13 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;      // rows past the utterance land on zero pad rows / are clipped
       }
-      // staging buffers are free once the previous tile's TMA stores have finished READING shared memory
-      if (etid == 0) bulk_wait_read0();
-      named_bar_sync(1, NEPI);
+      // The four TMEM lane quadrants (32 frames each, three warps) stage, synchronise and store INDEPENDENTLY: quadrant q owns
+      // rows 32 q .. 32 q + 31 of the staging tile, named barrier 1 + q (96 threads) and its own TMA stores / bulk groups
+      // (leader: lane 0 of warp q), so a slow warp or a pending store only holds up its own quadrant.
+      const bool qlead = hh == 0 && lane == 0;
+      // the quadrant's staging rows are free once ITS previous TMA stores have finished READING shared memory
+      if (qlead) bulk_wait_read0();
+      named_bar_sync(1 + q, 96);
       uint8_t* orow = ost + row * OUTB + 32 * hh;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -264,19 +268,20 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (epi.mask_out) mst[row * 8 + 2 * hh + g] = (g * 8 < nvalid) ? (uint8_t)m[g] : (uint8_t)0;   // 8-byte entry per row
       }
       fence_async_smem();
-      named_bar_sync(1, NEPI);
-      if (epi.mask_out && etid < GT && t0 + etid < p.T) {
-        // 128 consecutive 8-byte entries of this slab's mask plane: one fully coalesced store per warp
-        const int64_t r2 = (int64_t)b * p.Tp + NBASR_PAD_L + t0 + etid;
-        reinterpret_cast<uint64_t*>(epi.mask_out)[(int64_t)slab * epi.mask_rows + r2] = reinterpret_cast<const uint64_t*>(mst)[etid];
+      named_bar_sync(1 + q, 96);
+      if (epi.mask_out && hh == 0 && t < p.T) {
+        // 32 consecutive 8-byte entries of this slab's mask plane (warp q = the quadrant's rows): one coalesced store
+        const int64_t r2 = (int64_t)b * p.Tp + NBASR_PAD_L + t;
+        reinterpret_cast<uint64_t*>(epi.mask_out)[(int64_t)slab * epi.mask_rows + r2] = reinterpret_cast<const uint64_t*>(mst)[row];
       }
-      if (etid == 0) {
-        if (epi.out) tma_store_3d(&tmO, osm, c0, NBASR_PAD_L + t0, b);
-        if (epi.out2) tma_store_3d(&tmO2, osm + OSTAGE_BYTES, c0, NBASR_PAD_L + t0, b);
+      if (qlead) {
+        const uint32_t qoff = (uint32_t)(q * 32 * OUTB);
+        if (epi.out) tma_store_3d(&tmO, osm + qoff, c0, NBASR_PAD_L + t0 + 32 * q, b);
+        if (epi.out2) tma_store_3d(&tmO2, osm + OSTAGE_BYTES + qoff, c0, NBASR_PAD_L + t0 + 32 * q, b);
         bulk_commit();
       }
     }
-    if (etid == 0) bulk_wait0();
+    if (hh == 0 && lane == 0) bulk_wait0();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -484,7 +489,7 @@ int sm100_gconv_fwd(const nbasr_gconv* g, cudaStream_t st) {
   int64_t sw[2] = {1, 64};
   uint32_t bw[2] = {64, NW};
   if (sm100_get_map(g->w, 2, dw, sw, bw, &tmW)) return 1;
-  uint32_t bo[3] = {(uint32_t)a.OUT, GT, 1};
+  uint32_t bo[3] = {(uint32_t)a.OUT, 32, 1};             // one store per TMEM lane quadrant (32 frames)
   const void* o1 = g->epi.out ? g->epi.out : g->x;       // unused maps still need a valid descriptor
   const void* o2 = g->epi.out2 ? g->epi.out2 : g->x;
   if (sm100_get_map(o1, 3, dx, sx, bo, &tmO, 0)) return 1;

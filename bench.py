@@ -418,8 +418,8 @@ def roofline_entry(args, torch, profiling, eng, B, T, clocks, dev):
     # command (profiles/r*_ncu_step_full.json, written by tools/ncu_summary.py); null when no capture is committed
     traffic, traffic_note = None, None
     fam_kernel = {'gconv': 'gconv_mma_fwd_kernel', 'gconv_wgrad': 'gconv_mma_wgrad_kernel', 'gemm_tn': 'gemm_tn_pair_kernel',
-                  'gemm_wgrad': 'gemm_wgrad_pair_kernel', 'ln_bwd': 'ln2_bwd_kernel', 'ln_fwd': 'ln2_fwd_kernel'}
-    for ncu_name in ('r2_ncu_step_full.json', 'r1_ncu_step_full.json'):
+                  'gemm_wgrad': 'gemm_wgrad_persist_kernel', 'ln_bwd': 'ln2_bwd_kernel', 'ln_fwd': 'ln2_fwd_kernel'}
+    for ncu_name in ('r2_ncu_step_final.json', 'r2_ncu_step_full.json', 'r1_ncu_step_full.json'):
         ncu_path = os.path.join(ROOT, 'profiles', ncu_name)
         if os.path.exists(ncu_path) and dom_name in fam_kernel:
             nc = json.load(open(ncu_path)).get('kernels', {}).get(fam_kernel[dom_name])

@@ -907,12 +907,14 @@ class Engine:
     def _run(self, ops):
         st = torch.cuda.current_stream().cuda_stream
         n = 0
+        chain = self.lib.nbasr_gconv_chain
         for fn, args in ops:
             rc = fn(*args, st)
             if rc != 0:
                 raise _lib.NbasrError(f'{fn.__name__}: {self.lib.nbasr_last_error().decode()}')
-            n += 1
-        self.launches += n     # kernels launched (every C-ABI call launches >= 1 kernel of libnbasr)
+            # kernels launched: every C-ABI call launches >= 1 kernel of libnbasr; an unfused chain launches one per node
+            n += args[1] if (fn is chain and not args[2]) else 1
+        self.launches += n
 
     @_on_device
     def forward(self, audio, training=None, grad=None):

@@ -50,7 +50,7 @@ def op_work(fn_name, args, es):
             _, f1, b1 = op_work('nbasr_gconv_fwd', (C.byref(args[0][i]),), es)
             fl, by = fl + f1, by + b1
         g = args[0][0]
-        return f'gconv C={g.C} x{args[1]}', fl, by
+        return f'gconv C={g.C} chain of {args[1]}', fl, by
     if fn_name == 'nbasr_gconv_wgrad':
         dt, dz, x, B, T, Tp, Cc, cpg, k = args[:9]
         el = B * T * Cc
@@ -103,7 +103,8 @@ def profile_ops(engine, ops, iters=3):
             tag, fl, by = op_work(fn.__name__, args, es)
             d = acc.setdefault(tag, dict(n=0, ms=0.0, flops=0.0, bytes=0.0, floor_cycles=0.0))
             d['floor_cycles'] += gconv_issue_floor_cycles(fn.__name__, args)
-            d['n'] += 1
+            # kernel launches of this entry (an unfused grouped-conv chain launches one kernel per node)
+            d['n'] += args[1] if (fn.__name__ == 'nbasr_gconv_chain' and not args[2]) else 1
             d['ms'] += evs[i].elapsed_time(evs[i + 1])
             d['flops'] += fl
             d['bytes'] += by

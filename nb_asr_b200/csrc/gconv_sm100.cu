@@ -258,10 +258,15 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (g * 8 < nvalid) {
           if (epi.out) store8_h(orow + g * 16, epi.out_dtype, v + g * 8);
           if (epi.out2) {
-            const uint32_t w = w2[g];
             float t2[8];
+            if (epi.mask2) {               // gated second output (input gradient: dZ of the previous node)
+              const uint32_t w = w2[g];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t2[i] = ((w >> i) & 1u) ? v[g * 8 + i] * epi.scale2 : 0.f;
+              for (int i = 0; i < 8; ++i) t2[i] = ((w >> i) & 1u) ? v[g * 8 + i] * epi.scale2 : 0.f;
+            } else {                       // plain scaled copy (forward: the weight gradient's bf16 operand): no bit tests
+#pragma unroll
+              for (int i = 0; i < 8; ++i) t2[i] = v[g * 8 + i] * epi.scale2;
+            }
             store8_h(orow + OSTAGE_BYTES + g * 16, epi.out2_dtype, t2);
           }
         }
@@ -299,7 +304,7 @@ constexpr int WG_SMEM = NSTAGE * WG_STAGE + 1024 + 256;
 
 struct GcWgArgs {
   int B, T, C, cpg, OUT, ktaps, dstep, off0;
-  int nslabs, nchunks, nunits, nlanes;
+  int nslabs, nchunks, nunits, nlanes, dbg;
   float* dw;
   float* dbias;   // optional: db[c] += sum_t dZ[t][c], computed by the tensor core against a column of ones
 };
@@ -373,7 +378,8 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
         const uint64_t bd0 = make_smem_desc(sa + DZ_BYTES, 2u * (uint32_t)p.dstep * 128u, 1024);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GT / 16; ++k) umma_bf16(tm, ad0 + (uint64_t)(k * 128), bd0 + (uint64_t)(k * 128), idesc, (!first || k > 0) ? 1u : 0u);
+          for (int k = 0; k < GT / 16; ++k)
+            if (!(p.dbg & 2048) || k == 0) umma_bf16(tm, ad0 + (uint64_t)(k * 128), bd0 + (uint64_t)(k * 128), idesc, (!first || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));
         }
         __syncwarp();
@@ -418,7 +424,7 @@ gconv_mma_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_co
       const int tap = half ? 2 * pr : 2 * pr + 1;
       // column 63 of atom 0, rows 64..127 (tap 0, unshifted dZ) = sum_t dZ[t][co]
       if (pr == 0 && p.dbias && row_ok && half) atomicAdd(p.dbias + co, v[63]);
-      if (row_ok && tap < p.ktaps) {
+      if (row_ok && tap < p.ktaps && !(p.dbg & 1024)) {
         float* dst = p.dw + ((int64_t)co * p.cpg) * p.ktaps + tap;
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
@@ -519,6 +525,7 @@ int sm100_gconv_wgrad(const void* dz, const void* x, int B, int T, int Tp, int C
   a.nlanes = std::max(1, std::min(a.nunits, slots / a.nslabs));
   a.dw = dw;
   a.dbias = dbias;
+  a.dbg = nbasr_env_chain_dbg();       // timing experiments only (bits 1024: no gradient atomics, 2048: one MMA per unit)
   CUtensorMap tmDZ, tmX;
   uint64_t dd[3] = {(uint64_t)C, (uint64_t)Tp, (uint64_t)B};
   int64_t sd[3] = {1, C, (int64_t)Tp * C};

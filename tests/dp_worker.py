@@ -75,7 +75,8 @@ def main():
     # Adam's first steps are -lr * g / (|g| + eps): wherever the true gradient is ~0 (e.g. every bias in front of a LayerNorm)
     # the step is +-lr with the sign of fp32 summation noise, so the update is compared on the elements whose reference
     # gradient is significant (and the fraction of such elements is reported)
-    sig = ref_grad.abs() > 1e-3 * ref_grad.abs().mean()
+    # (16-bit mode: the exchanged gradient agrees to ~1e-4 of its norm, so 'significant' starts further above the noise)
+    sig = ref_grad.abs() > (1e-3 if precision == 'fp32' else 5e-2) * ref_grad.abs().mean()
     upd, ref_upd = (params - init_params).double(), (ref_params - init_params).double()
     res = dict(ranks_equal=bool(torch.equal(lo, hi)),
                loss0_rel=abs(losses[0] - ref_losses[0]) / abs(ref_losses[0]),

@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(LC_FWD_THREADS, 1) lstm_cluster_fwd_kernel(con
 // 16 partials in fp32.  Again the mbarrier byte count is the only inter-CTA synchronisation.
 constexpr int LB_DG_BYTES = 128 * LC_BG * 2;          // 4096: dg operand (N=16 x K=128)
 constexpr int LB_SEND_BYTES = LC_NCTA * LC_SLICE;     // 16384: one 1-KB block per destination
+constexpr int LB_A_COL = 64;             // backward: first TMEM column of the resident W^T tiles (4 m-tiles x 64 columns)
 constexpr int LB_SMEM = LC_W_BYTES + LB_DG_BYTES + 2 * LB_SEND_BYTES + 2 * LB_SEND_BYTES + 1024 + 256;
 
 struct LstmCBwdArgs {
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(LC_FWD_THREADS, 1) lstm_cluster_bwd_kernel(con
   const uint32_t bar0 = rcv + 2 * LB_SEND_BYTES;
   const uint32_t wbar = bar0, mma_bar = bar0 + 8, dg_bar = bar0 + 16;
   auto rfull = [&](int b) { return bar0 + 24 + 8u * b; };
+  const uint32_t aready = bar0 + 40;           // the transposed W slice is resident in tensor memory
   uint32_t* tptr = reinterpret_cast<uint32_t*>(rcv_p + 2 * LB_SEND_BYTES + 64);
   constexpr int W_MMA = LC_FWD_EPI / 32;       // warp roles as in the forward kernel: 0..15 cells / drain, 16 MMA issue
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
@@ -300,9 +302,10 @@ __global__ void __launch_bounds__(LC_FWD_THREADS, 1) lstm_cluster_bwd_kernel(con
     mbar_init(dg_bar, LC_FWD_EPI);
     mbar_init(rfull(0), 1);
     mbar_init(rfull(1), 1);
+    mbar_init(aready, LC_FWD_EPI);
     fence_barrier_init();
   }
-  if (warp == W_MMA) tmem_alloc(smem_u32(tptr), 64);
+  if (warp == W_MMA) tmem_alloc(smem_u32(tptr), 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -315,10 +318,12 @@ __global__ void __launch_bounds__(LC_FWD_THREADS, 1) lstm_cluster_bwd_kernel(con
       for (int kb = 0; kb < 8; ++kb) tma_load_2d(wsm + kb * 16384, &tmW, wbar, kb * 64, (int)j * 128);
     }
     __syncwarp();
-    const uint32_t idesc = make_idesc(128, LC_BG, 1, 0);        // A: MN-major (W slice read "transposed"), B: K-major
-    const uint64_t ad0 = make_smem_desc(wsm, 16384, 1024);
+    // A operand = W^T tiles resident in TENSOR MEMORY (copied once by the epilogue warps below): with both operands in shared
+    // memory each of the 32 MMAs of a step costs >= 88 cycles (1.4 us of the ~3.6 us step); from tensor memory the N = 16 MMA
+    // is bounded by its small B operand only, as in the forward kernel.
+    const uint32_t idesc = make_idesc(128, LC_BG, 0, 0);
     const uint64_t bd0 = make_smem_desc(dsm, 256, 128) & ~((uint64_t)7 << 61);
-    mbar_wait(wbar, 0);
+    mbar_wait(aready, 0);
     for (int s = 0; s + 1 < p.T; ++s) {                          // step s handles t = T-1-s; the last step needs no matmul
       if (elect_one()) mbar_expect_tx(rfull(s & 1), LB_SEND_BYTES);             // arm the buffer that receives this step's partials
       __syncwarp();
@@ -328,8 +333,8 @@ __global__ void __launch_bounds__(LC_FWD_THREADS, 1) lstm_cluster_bwd_kernel(con
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)       // A: + 2 mt * 16384 + k * 2048 bytes, B: + k * 512 bytes
-            umma_bf16(tm + mt * 16, ad0 + (uint64_t)(mt * 2048 + k * 128), bd0 + (uint64_t)(k * 32), idesc, k != 0);
+          for (int k = 0; k < 8; ++k)       // A: 8 columns (16 gate rows) per K step, B: + k * 512 bytes
+            umma_bf16_ts(tm + mt * 16, tm + LB_A_COL + mt * 64 + 8 * k, bd0 + (uint64_t)(k * 32), idesc, k != 0);
         }
         umma_commit(mma_bar);
       }
@@ -361,6 +366,29 @@ __global__ void __launch_bounds__(LC_FWD_THREADS, 1) lstm_cluster_bwd_kernel(con
       }
     };
     if (p.T > 0) prefetch(p.T - 1);
+    {
+      // W^T into tensor memory, once: lane (q*32 + lane) of m-tile mt_own is hidden unit kcol; its 128 K elements are the own
+      // gate rows r of W_hh[r][kcol], read column-wise from the 128B-swizzled K-major slice and packed two per 32-bit column
+      mbar_wait(wbar, 0);
+      const int kcol = mt_own * 128 + q * 32 + lane;
+      const uint8_t* wcol = al + (kcol >> 6) * 16384 + (kcol & 7) * 2;
+      const int chunk = (kcol & 63) >> 3;
+#pragma unroll 2
+      for (int k = 0; k < 8; ++k) {
+        uint32_t regs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r0 = 16 * k + 2 * i, r1 = r0 + 1;
+          const uint32_t lo = *reinterpret_cast<const uint16_t*>(wcol + r0 * 128 + ((chunk ^ (r0 & 7)) << 4));
+          const uint32_t hi = *reinterpret_cast<const uint16_t*>(wcol + r1 * 128 + ((chunk ^ (r1 & 7)) << 4));
+          regs[i] = lo | (hi << 16);
+        }
+        tmem_st8(tm + ((uint32_t)(q * 32) << 16) + LB_A_COL + mt_own * 64 + 8 * k, regs);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      mbar_arrive(aready);
+    }
     for (int s = 0; s < p.T; ++s) {
       const int t = p.T - 1 - s;
       if (s > 0) {
@@ -432,7 +460,7 @@ __global__ void __launch_bounds__(LC_FWD_THREADS, 1) lstm_cluster_bwd_kernel(con
   cluster_sync_all();
   if (warp == W_MMA) {
     tcgen05_fence_after();
-    tmem_dealloc(tm, 64);
+    tmem_dealloc(tm, 512);
   }
 }
 

@@ -214,7 +214,9 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
   // number of this CTA's tiles (node-major order) whose stores have landed: the producer polls THIS word for the tiles of
   // its own range (a global acquire per dependency, ~3 L2 round trips per tile, made the producer the bottleneck: r2)
   const uint32_t own_prog = bar0 + 8u * (2 + 8 + 2 * NACC) + 8u;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp roles: 0..7 epilogue, 8 producer, 9 MMA issue (highest id = issue priority; warp-uniform MMA loop, see gconv_sm100.cu)
+  constexpr int W_PROD = CH_NEPI / 32, W_MMA = CH_NEPI / 32 + 1;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int slab = blockIdx.x % p.nslabs;
   const int lane_id = blockIdx.x / p.nslabs;
   const int c0 = slab * p.OUT;
@@ -224,7 +226,7 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
   const int te = strided ? p.ntiles : (int)((int64_t)(lane_id + 1) * p.ntiles / p.nlanes);
   const int tstep = strided ? p.nlanes : 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_PROD && lane == 0) {
     prefetch_tmap(&maps.x[0]);
     prefetch_tmap(&maps.w[0]);
     mbar_init(wbar, 1);
@@ -234,7 +236,7 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
     for (int s = 0; s < NACC; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CH_NEPI); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tptr), 256);
+  if (warp == W_MMA) tmem_alloc(smem_u32(tptr), 256);
   pdl_launch_dependents();
   tcgen05_fence_before();
   __syncthreads();
@@ -245,15 +247,15 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
     mbar_expect_tx(wbar, kt * WTAP_BYTES);
     for (int j = 0; j < kt; ++j) tma_load_2d(wsm + j * WTAP_BYTES, &maps.w[nd], wbar, 0, (slab * kt + j) * NW);
   };
-  if (p.w_stable && warp == 0 && lane == 0) load_weights(0);
+  if (p.w_stable && warp == W_PROD && lane == 0) load_weights(0);
   pdl_wait();                                  // everything above overlapped the previous kernel's tail
-  if (!p.w_stable && warp == 0 && lane == 0) load_weights(0);
+  if (!p.w_stable && warp == W_PROD && lane == 0) load_weights(0);
   // flag value of THIS launch (the epoch only advances when every CTA of a launch has left)
   const uint32_t done = *reinterpret_cast<volatile uint32_t*>(p.work) + 1u;
   uint32_t* flags = p.work + CH_WORK_HDR + (int64_t)slab * p.ntiles;
   const int64_t node_flags = (int64_t)p.nslabs * p.ntiles;
 
-  if (warp == 0) {
+  if (warp == W_PROD) {
     int stage = 0;
     uint32_t phase = 0;
     int known_prog = 0;        // (lane 0) own tiles known to have landed AND already ordered by a proxy fence
@@ -328,41 +330,41 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, NW, 0, 0, p.f16);
-      int stage = 0, it = 0;
-      uint32_t phase = 0;
-      for (int nd = 0; nd < p.n_nodes; ++nd) {
-        const int kt = p.node[nd].ktaps, ds = p.node[nd].dstep;
-        mbar_wait(wbar, nd & 1);
-        for (int tile = tb; tile < te; tile += tstep, ++it) {
-          const int as = it % NACC;
-          const uint32_t aphase = (it / NACC) & 1;
-          mbar_wait(tempty_bar(as), aphase ^ 1);
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
-          const uint32_t sa = asm0 + stage * A_BYTES;
+  } else if (warp == W_MMA) {
+    const uint32_t idesc = make_idesc(128, NW, 0, 0, p.f16);
+    const uint64_t bd0 = make_smem_desc(wsm, 16, 1024);
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int nd = 0; nd < p.n_nodes; ++nd) {
+      const int kt = p.node[nd].ktaps, ds = p.node[nd].dstep;
+      mbar_wait(wbar, nd & 1);
+      for (int tile = tb; tile < te; tile += tstep, ++it) {
+        const int as = it % NACC;
+        const uint32_t aphase = (it / NACC) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        const uint64_t ad0 = make_smem_desc(asm0 + stage * A_BYTES, 16, 1024);
+        if (elect_one()) {
           for (int j = 0; j < kt; ++j) {
 #pragma unroll
-            for (int k = 0; k < NW / 16; ++k) {
-              uint64_t ad = make_smem_desc(sa + (j * ds) * 128 + k * 32, 16, 1024);
-              uint64_t bd = make_smem_desc(wsm + j * WTAP_BYTES + k * 32, 16, 1024);
-              umma_bf16(tm + as * 64, ad, bd, idesc, (j | k) != 0);
-            }
+            for (int k = 0; k < NW / 16; ++k)
+              umma_bf16(tm + as * 64, ad0 + (uint64_t)(j * ds * 8 + k * 2), bd0 + (uint64_t)(j * (WTAP_BYTES >> 4) + k * 2), idesc, (j | k) != 0);
           }
           umma_commit(empty_bar(stage));
           umma_commit(tfull_bar(as));
-          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
-        umma_commit(wfree);
+        __syncwarp();
+        if (++stage == NS) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(wfree);
+      __syncwarp();
     }
   } else {
-    const int ew = warp - 2;                 // 0..7
+    const int ew = warp;                     // 0..7
     const int q = warp & 3;                  // TMEM lane quadrant of this warp
     const int hh = ew >> 2;                  // column half: cols [24*hh, 24*hh + 24)
-    const int etid = threadIdx.x - 64;
+    const int etid = threadIdx.x;
     const int row = q * 32 + lane;
     const int cbeg = c0 + 24 * hh;
     const int nvalid = max(0, min(24, min(p.C, c0 + p.OUT) - cbeg));     // multiple of 8
@@ -529,11 +531,11 @@ gconv_chain_kernel(const __grid_constant__ GcChainMaps maps, const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tcgen05_fence_after();
     tmem_dealloc(tm, 256);
   }
-  if (threadIdx.x == 0) {
+  if (warp == W_PROD && lane == 0) {
     // exit ticket: the last CTA advances the epoch (every flag of this launch becomes stale) and re-arms the ticket
     __threadfence();
     const uint32_t tk = atomicAdd(p.work + 1, 1u);

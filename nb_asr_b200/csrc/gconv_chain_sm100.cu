@@ -33,7 +33,7 @@ using namespace sm100;
 namespace {
 
 constexpr int MAXCHAIN = 3;
-constexpr int CH_THREADS = 320;             // producer, MMA, 8 epilogue warps (two column halves x four TMEM lane quadrants)
+constexpr int CH_THREADS = 320;             // 8 epilogue warps (two column halves x four TMEM lane quadrants), producer, MMA
 constexpr int CH_NEPI = 256;
 constexpr int CH_WORK_HDR = 16;            // u32 words in front of the flags: [0] epoch, [1] exit ticket, [2] error
 

@@ -10,7 +10,9 @@
 //    descriptor whose start address is advanced by whole 128-byte rows (swizzle is a function of the
 //    absolute smem address, verified on B200 with tools/experiments/dbg.cu) -- no im2col, no per-tap reload.
 //  * A CTA keeps one slab's block-diagonal weights (<= 7 taps x 6 KB) in smem and walks frame tiles;
-//    2 CTAs / SM, 3-stage TMA ring, 4 TMEM accumulator stages, warp roles as in gemm_sm100.cu.
+//    2 CTAs / SM, 3-stage TMA ring, 4 TMEM accumulator stages.  Warps 0..11: epilogue (three column thirds x four TMEM
+//    lane quadrants, each quadrant staging and storing on its own), warp 12: TMA producer, warp 13: MMA issue (last =
+//    highest issue priority; warp-uniform loop, one elected lane issues).
 //  * Forward and input-gradient share the kernel (different weight pack / tap offsets); the fused
 //    epilogue (bias, ReLU20, dropout, skip-sum, gradient mask) works on 8-column groups because slab
 //    boundaries are only 8-aligned.

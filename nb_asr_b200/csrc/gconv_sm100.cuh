@@ -12,8 +12,8 @@ constexpr int NW = 48;                     // MMA N (and K window) of a slab
 constexpr int WTAP_BYTES = NW * 128;       // 6144
 constexpr int NSTAGE = 3;                  // (weight-gradient kernel)
 constexpr int NACC = 4;
-constexpr int GC_THREADS = 192;            // weight-gradient kernel: producer, MMA, 4 epilogue warps
-constexpr int FWD_THREADS = 448;           // forward kernel: producer, MMA, 12 epilogue warps
+constexpr int GC_THREADS = 192;            // weight-gradient kernel: 4 drain warps, producer, MMA
+constexpr int FWD_THREADS = 448;           // forward kernel: 12 epilogue warps, producer, MMA
 constexpr int NEPI = 384;                  // (three column thirds x four TMEM lane quadrants)
 constexpr int OSTAGE_BYTES = GT * NW * 2;  // 12288: bf16 output tile staged for the TMA store
 constexpr int FWD_SMEM_BUDGET = 112 * 1024;
